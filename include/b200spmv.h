@@ -1,0 +1,267 @@
+/*
+ * b200spmv.h -- C ABI of libb200spmv.so, the B200 (sm_100a) SpMV library.
+ *
+ * This header is the drop-in boundary.  The reference (sgartkink/opencl-spmv-algorithms) has no
+ * plugin API: its seam is the set of OpenCL runtime calls inlined in each driver's main() plus
+ * three helpers in inc/helper_functions.h.  Every entry point below names the reference call(s)
+ * it replaces (file:line relative to the reference root).  Conventions kept from the reference:
+ *
+ *   - every call returns an int status, 0 == success (cl_int / CL_SUCCESS, e.g. csr.c:117);
+ *   - the caller owns host memory; the library owns device memory behind plain device pointers
+ *     that the caller releases explicitly (csr.c:260-263);
+ *   - one context = one device + one in-order stream (clCreateContext +
+ *     clCreateCommandQueueWithProperties(props = 0), csr.c:107,115); uploads are asynchronous and
+ *     completed by b200_sync (clEnqueueWriteBuffer(CL_FALSE) + clFinish, csr.c:183-193); downloads
+ *     block (clEnqueueReadBuffer(CL_TRUE), csr.c:220);
+ *   - kernels are compiled ahead of time into the library: there is no runtime source read
+ *     (read_source_from_cl_file / clCreateProgramWithSource / clBuildProgram / clCreateKernel,
+ *     csr.c:136-159, have no counterpart and the kernels/ directory dependency disappears).
+ *
+ * Signatures use only plain pointers and sizes.  All "const T *" array arguments of the launch,
+ * build and generator entry points are DEVICE pointers obtained from b200_malloc (or any CUDA
+ * allocation, e.g. a torch tensor's data_ptr()).  There is no CPU fallback anywhere: without a
+ * CUDA device every entry point that needs one fails with B200_ERR_NO_DEVICE / B200_ERR_CUDA.
+ */
+#ifndef B200SPMV_H
+#define B200SPMV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPMV_VERSION 100 /* 1.0.0 */
+
+/* status codes; the drivers map them to the reference's ReturnCode (inc/enums.h:4-11):
+ * B200_ERR_NO_DEVICE -> OpenCLDeviceError(1), every other failure -> OpenCLProgramError(2). */
+enum {
+    B200_SUCCESS = 0,
+    B200_ERR_NO_DEVICE = 1,
+    B200_ERR_CUDA = 2,
+    B200_ERR_INVALID_VALUE = 3,
+    B200_ERR_OUT_OF_MEMORY = 4,
+    B200_ERR_UNSUPPORTED = 5,
+    B200_ERR_DOMAIN = 6 /* input outside the builder's domain (e.g. rows not sorted) */
+};
+
+typedef struct b200_ctx b200_ctx;     /* cl_context + cl_command_queue */
+typedef struct b200_event b200_event; /* cl_event, but with device timestamps */
+
+const char *b200_status_string(int status);
+const char *b200_last_error(void); /* detail of the last failure on this thread */
+int b200_version(void);
+
+/* ---- devices: replaces get_device_ids (inc/helper_functions.h:76-129) ---- */
+int b200_get_device_count(int *count);
+int b200_device_name(int device, char *buf, size_t buf_len);
+int b200_device_sm_count(int device, int *sm_count);
+
+/* ---- context / queue: clCreateContext + clCreateCommandQueueWithProperties (csr.c:107-121),
+ *      clFlush/clReleaseCommandQueue/clReleaseContext (csr.c:273-277) ---- */
+int b200_ctx_create(int device, b200_ctx **ctx);
+/* same, but enqueue on an existing CUDA stream (a cudaStream_t passed as void*, 0 = default) */
+int b200_ctx_create_on_stream(int device, void *cuda_stream, b200_ctx **ctx);
+int b200_ctx_destroy(b200_ctx *ctx);
+int b200_ctx_device(const b200_ctx *ctx, int *device);
+/* keep `bytes` at `dptr` (normally x) resident in L2 for later launches (access-policy window);
+ * bytes = 0 clears the window.  New: the OpenCL reference has no equivalent. */
+int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes);
+
+/* ---- buffers: clCreateBuffer (csr.c:123-127), clReleaseMemObject (csr.c:260-263),
+ *      clEnqueueWriteBuffer (csr.c:183-186), clEnqueueReadBuffer (csr.c:220), clFinish ---- */
+int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);
+int b200_free(b200_ctx *ctx, void *dptr);
+int b200_memcpy_h2d_async(b200_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+int b200_memcpy_d2h(b200_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
+int b200_memcpy_d2h_async(b200_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
+int b200_memcpy_d2d_async(b200_ctx *ctx, void *dst_device, const void *src_device, size_t bytes);
+int b200_memset_async(b200_ctx *ctx, void *dst_device, int byte_value, size_t bytes);
+int b200_sync(b200_ctx *ctx);
+int b200_host_alloc_pinned(size_t bytes, void **hptr);
+int b200_host_free_pinned(void *hptr);
+
+/* ---- timing: the reference brackets the launch with clock_gettime + clWaitForEvents
+ *      (csr.c:198-206); these are device timestamps on the context's stream ---- */
+int b200_event_create(b200_ctx *ctx, b200_event **ev);
+int b200_event_record(b200_ctx *ctx, b200_event *ev);
+int b200_event_elapsed_ms(b200_event *start, b200_event *stop, float *ms); /* waits for `stop` */
+int b200_event_destroy(b200_event *ev);
+
+/* =====================================================================================
+ * SpMV launches.  One entry per format x dtype; argument order = the order the reference
+ * driver sets with clSetKernelArg, followed by what the OpenCL kernel took from its launch
+ * shape or left undefined.  All launches are asynchronous on the context's stream.
+ * ===================================================================================== */
+
+/* CSR: kernel csr(ptr,col,data,vect,output,N) kernels/Csr.cl:1, args csr.c:170-175.
+ * `plan` carries the row-length statistics that pick the lanes-per-row variant and the
+ * long-row list; NULL = analyse `ptr` on the fly (one extra pass + a small sync). */
+typedef struct b200_csr_plan b200_csr_plan;
+typedef struct {
+    int n_rows;
+    long long nnz;
+    int min_len, max_len;
+    double mean_len;
+    int lanes_per_row; /* 2,4,8,16,32: the vector-kernel variant chosen */
+    int long_threshold; /* rows longer than this go to the block-per-row kernel */
+    int n_long_rows;
+} b200_csr_plan_info;
+int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_plan **plan);
+int b200_csr_plan_get_info(const b200_csr_plan *plan, b200_csr_plan_info *info);
+int b200_csr_plan_destroy(b200_csr_plan *plan);
+int b200_spmv_csr_f64(b200_ctx *ctx, const int *ptr, const int *col, const double *data,
+                      const double *vect, double *output, int n_rows, const b200_csr_plan *plan);
+int b200_spmv_csr_f32(b200_ctx *ctx, const int *ptr, const int *col, const float *data,
+                      const float *vect, float *output, int n_rows, const b200_csr_plan *plan);
+
+/* COO: kernel coo(row,col,data,vect,output,N=nnz) kernels/Coo.cl:24, args coo.c:163-168.
+ * Entries may be in any order.  `output` (n_rows elements) is zero-filled by the call (the
+ * reference never zeroes it: coo.c:120, quirk q1), then accumulated with a segmented warp
+ * reduction and one atomic per (warp, row-run). */
+int b200_spmv_coo_f64(b200_ctx *ctx, const int *row, const int *col, const double *data,
+                      const double *vect, double *output, int nnz, int n_rows);
+int b200_spmv_coo_f32(b200_ctx *ctx, const int *row, const int *col, const float *data,
+                      const float *vect, float *output, int nnz, int n_rows);
+
+/* ELL, the reference's ROW-MAJOR arrays: kernel ell(data,indices,vect,output,N,row_size,local)
+ * kernels/Ell.cl:1, args ell.c:242-248 (the __local scratch argument disappears). */
+int b200_spmv_ell_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                      double *output, int n_rows, int row_size);
+int b200_spmv_ell_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
+                      float *output, int n_rows, int row_size);
+/* ELL, COLUMN-MAJOR device layout (element k of row r at k*pitch + r, pitch % 32 == 0,
+ * pitch >= n_rows): the transpose of the same K-padded matrix, built by b200_build_ell_colmajor
+ * or b200_ell_transpose.  This is the coalesced thread-per-row kernel. */
+int b200_spmv_ellcm_f64(b200_ctx *ctx, const double *data_cm, const int *indices_cm,
+                        const double *vect, double *output, int n_rows, int row_size, int pitch);
+int b200_spmv_ellcm_f32(b200_ctx *ctx, const float *data_cm, const int *indices_cm,
+                        const float *vect, float *output, int n_rows, int row_size, int pitch);
+
+/* SELL-C (C = 32): kernel sigma_c(data,indices,vect,output,row_indices,C) kernels/Sigma_C.cl:1,
+ * args sigma_c.c:280-285.  The reference launches one 32-lane group per slice and writes
+ * n_slices*32 outputs including the padding rows of the last slice (Sigma_C.cl:17,
+ * sigma_c.c:212); `n_out` says how many leading outputs to write (n_slices*32 for the
+ * reference's padded buffer, n_rows otherwise).  `perm` (new; NULL = identity) is the
+ * sigma-window permutation perm[new_row] = old_row: row new_row's result goes to
+ * output[perm[new_row]].  chunk must be 32 (warp-aligned chunks). */
+int b200_spmv_sell_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                       double *output, const int *row_indices, int chunk, int n_slices, int n_out,
+                       const int *perm);
+int b200_spmv_sell_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
+                       float *output, const int *row_indices, int chunk, int n_slices, int n_out,
+                       const int *perm);
+/* same with 64-bit chunk pointers (the reference's cl_int row_indices overflows when the padded
+ * size exceeds 2^31, sigma_c.c:41,118-119) */
+int b200_spmv_sell64_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                         double *output, const long long *slice_ptr, int chunk, int n_slices,
+                         int n_out, const int *perm);
+int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
+                         float *output, const long long *slice_ptr, int chunk, int n_slices,
+                         int n_out, const int *perm);
+
+/* CMRS: kernel cmrs(data,indices,strip_ptr,row_in_strip,vect,output,N=strips,height,local)
+ * kernels/Cmrs.cl:1, args cmrs.c:197-205.  `n_rows` bounds the store of the last strip (the
+ * reference writes height outputs per strip unconditionally, Cmrs.cl:38-41, quirk q5).
+ * height <= 32. */
+int b200_spmv_cmrs_f64(b200_ctx *ctx, const double *data, const int *indices, const int *strip_ptr,
+                       const int *row_in_strip, const double *vect, double *output, int n_strips,
+                       int height, int n_rows);
+int b200_spmv_cmrs_f32(b200_ctx *ctx, const float *data, const int *indices, const int *strip_ptr,
+                       const int *row_in_strip, const float *vect, float *output, int n_strips,
+                       int height, int n_rows);
+
+/* =====================================================================================
+ * Format builds on the GPU (new; in the reference they are host loops inlined in each main()).
+ * Input: device COO triples as the drivers parse them ("%d %d %lg", 1-based -> 0-based,
+ * coo.c:79-84), SORTED BY ROW for everything except COO itself.  On the reference's
+ * well-defined domain (rows sorted, none empty, first row 0) every integer array is identical
+ * to the reference's; empty rows are handled correctly instead of shifting (quirk q4).
+ * ===================================================================================== */
+
+/* checks sortedness; B200_ERR_DOMAIN if rows are not non-decreasing or out of range */
+int b200_check_sorted_rows(b200_ctx *ctx, const int *rows, int nnz, int n_rows);
+/* CSR row pointer (csr.c:72-91): ptr has n_rows+1 entries */
+int b200_build_csr_ptr(b200_ctx *ctx, const int *rows, int nnz, int n_rows, int *ptr);
+/* row-length statistics from ptr (host outputs).  *_excl_last reproduce what ell.c:68-104 prints
+ * (the reference never counts the last row) */
+typedef struct {
+    int max_len, min_len;
+    long long sum_len;
+    int max_len_excl_last, min_len_excl_last;
+    long long sum_len_excl_last;
+    int last_len;
+} b200_row_stats;
+int b200_row_length_stats(b200_ctx *ctx, const int *ptr, int n_rows, b200_row_stats *stats);
+/* ELL (ell.c:118-164): row-major, padding = (col 0, value 0) */
+int b200_build_ell_f64(b200_ctx *ctx, const int *ptr, const int *cols, const double *vals,
+                       int n_rows, int row_size, int *ell_cols, double *ell_data);
+int b200_build_ell_f32(b200_ctx *ctx, const int *ptr, const int *cols, const double *vals,
+                       int n_rows, int row_size, int *ell_cols, float *ell_data);
+int b200_build_ell_colmajor_f64(b200_ctx *ctx, const int *ptr, const int *cols, const double *vals,
+                                int n_rows, int row_size, int pitch, int *cm_cols,
+                                double *cm_data);
+int b200_build_ell_colmajor_f32(b200_ctx *ctx, const int *ptr, const int *cols, const double *vals,
+                                int n_rows, int row_size, int pitch, int *cm_cols, float *cm_data);
+/* SELL-C-sigma (sigma_c.c:71-202 at sigma <= 1).  Two steps so the caller can allocate:
+ *  1. b200_build_sell_ptr: perm (n_rows ints; identity for sigma <= 1; may be NULL when
+ *     sigma <= 1), slice_ptr (n_slices+1 int64) and the padded size *total (host output);
+ *  2. b200_build_sell_fill_*: column-major-in-slice fill, padding = (col 0, value 0).
+ * b200_sell_ptr_to_i32 narrows slice_ptr to the reference's cl_int row_indices
+ * (B200_ERR_DOMAIN on overflow). */
+int b200_sell_num_slices(int n_rows, int chunk);
+int b200_build_sell_ptr(b200_ctx *ctx, const int *ptr, int n_rows, int chunk, int sigma, int *perm,
+                        long long *slice_ptr, long long *total);
+int b200_sell_ptr_to_i32(b200_ctx *ctx, const long long *slice_ptr, int n_slices,
+                         int *row_indices);
+int b200_build_sell_fill_f64(b200_ctx *ctx, const int *ptr, const int *cols, const double *vals,
+                             int n_rows, int chunk, const int *perm, const long long *slice_ptr,
+                             int *sell_cols, double *sell_data);
+int b200_build_sell_fill_f32(b200_ctx *ctx, const int *ptr, const int *cols, const double *vals,
+                             int n_rows, int chunk, const int *perm, const long long *slice_ptr,
+                             int *sell_cols, float *sell_data);
+/* CMRS (cmrs.c:72-117): strip_ptr has ceil(n_rows/height)+1 entries, row_in_strip has nnz */
+int b200_cmrs_num_strips(int n_rows, int height);
+int b200_build_cmrs(b200_ctx *ctx, const int *rows, const int *ptr, int nnz, int n_rows,
+                    int height, int *strip_ptr, int *row_in_strip);
+/* value conversion for the fp32 path (the reference is fp64-only) */
+int b200_convert_f64_to_f32(b200_ctx *ctx, const double *src, float *dst, long long n);
+/* x[i] = i, the reference's input vector (csr.c:95-99) */
+int b200_fill_ramp_f64(b200_ctx *ctx, double *x, int n);
+int b200_fill_ramp_f32(b200_ctx *ctx, float *x, int n);
+
+/* =====================================================================================
+ * Synthetic matrices generated on the device (BASELINE.json configs 3-5; the reference can only
+ * ingest MatrixMarket text).  Each fills rows [row_begin, row_begin+row_count) of the global
+ * matrix as row-sorted COO triples with global column indices; *_nnz gives the exact count.
+ * ===================================================================================== */
+long long b200_gen_banded_nnz(long long n_global, int row_begin, int row_count, int nnz_per_row);
+int b200_gen_banded_coo(b200_ctx *ctx, int n_global, int row_begin, int row_count, int nnz_per_row,
+                        int half_band, uint64_t seed, int *rows, int *cols, double *vals);
+long long b200_gen_laplace7_nnz(int nx, int ny, int nz, int row_begin, int row_count);
+int b200_gen_laplace7_coo(b200_ctx *ctx, int nx, int ny, int nz, int row_begin, int row_count,
+                          int *rows, int *cols, double *vals);
+int b200_gen_uniform_f64(b200_ctx *ctx, double *x, long long n, uint64_t seed, double lo, double hi);
+int b200_gen_uniform_f32(b200_ctx *ctx, float *x, long long n, uint64_t seed, float lo, float hi);
+/* host twins of the generators' per-element functions (same integer hash; bit-identical), so a
+ * CPU-only process can rebuild any row block of the same matrix */
+int b200_gen_banded_coo_host(int n_global, int row_begin, int row_count, int nnz_per_row,
+                             int half_band, uint64_t seed, int *rows, int *cols, double *vals);
+int b200_gen_uniform_f64_host(double *x, long long n, uint64_t seed, double lo, double hi);
+
+/* =====================================================================================
+ * Multi-GPU row partition (new): contiguous, nnz-balanced row blocks whose cut points are
+ * multiples of `align` (lcm of the SELL chunk, CMRS height and sigma window) so that every
+ * shard's format arrays are slices of the global build.  Host function over a host ptr[].
+ * cuts has n_parts+1 entries: part p owns rows [cuts[p], cuts[p+1]).
+ * ===================================================================================== */
+int b200_partition_rows(const int *ptr_host, int n_rows, int n_parts, int align, int *cuts);
+/* power-iteration helpers for the iterated mode: y *= scale; sum of squares into *acc (device) */
+int b200_scale_f64(b200_ctx *ctx, double *y, long long n, const double *scale_device, int invert_sqrt);
+int b200_sumsq_f64(b200_ctx *ctx, const double *y, long long n, double *acc_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPMV_H */

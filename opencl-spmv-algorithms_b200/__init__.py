@@ -1,0 +1,269 @@
+"""b200spmv -- Python host side over the C ABI of libb200spmv.so (include/b200spmv.h).
+
+The product is the CUDA library and the C drivers in host/; this module is the thin ctypes
+mirror used by tests/, bench.py and __graft_entry__.py.  It never computes anything itself and has
+no CPU fallback: if the shared library is missing, or there is no CUDA device, calls raise.
+
+The directory name contains '-', so import it through `__graft_entry__.load_package()` (which
+registers it as module `spmv_b200`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libb200spmv.so"
+HEADER_PATH = PKG_DIR.parent / "include" / "b200spmv.h"
+
+SUCCESS = 0
+ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID_VALUE, ERR_OOM, ERR_UNSUPPORTED, ERR_DOMAIN = 1, 2, 3, 4, 5, 6
+
+
+class B200Error(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str):
+        super().__init__(f"{where}: status {status}: {detail}")
+        self.status = status
+
+
+class CsrPlanInfo(C.Structure):
+    _fields_ = [("n_rows", C.c_int), ("nnz", C.c_longlong), ("min_len", C.c_int),
+                ("max_len", C.c_int), ("mean_len", C.c_double), ("lanes_per_row", C.c_int),
+                ("long_threshold", C.c_int), ("n_long_rows", C.c_int)]
+
+
+class RowStats(C.Structure):
+    _fields_ = [("max_len", C.c_int), ("min_len", C.c_int), ("sum_len", C.c_longlong),
+                ("max_len_excl_last", C.c_int), ("min_len_excl_last", C.c_int),
+                ("sum_len_excl_last", C.c_longlong), ("last_len", C.c_int)]
+
+
+_vp, _i, _ll, _u64, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_uint64, C.c_size_t
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); the single source of truth for the ABI seen from Python.
+# tests/test_abi.py cross-checks this table against include/b200spmv.h.
+SIGNATURES = {
+    "b200_status_string": (C.c_char_p, [_i]),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_version": (_i, []),
+    "b200_get_device_count": (_i, [C.POINTER(_i)]),
+    "b200_device_name": (_i, [_i, C.c_char_p, _sz]),
+    "b200_device_sm_count": (_i, [_i, C.POINTER(_i)]),
+    "b200_ctx_create": (_i, [_i, _vpp]),
+    "b200_ctx_create_on_stream": (_i, [_i, _vp, _vpp]),
+    "b200_ctx_destroy": (_i, [_vp]),
+    "b200_ctx_device": (_i, [_vp, C.POINTER(_i)]),
+    "b200_ctx_set_l2_persist": (_i, [_vp, _vp, _sz]),
+    "b200_malloc": (_i, [_vp, _sz, _vpp]),
+    "b200_free": (_i, [_vp, _vp]),
+    "b200_memcpy_h2d_async": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memcpy_d2h_async": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memcpy_d2d_async": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memset_async": (_i, [_vp, _vp, _i, _sz]),
+    "b200_sync": (_i, [_vp]),
+    "b200_host_alloc_pinned": (_i, [_sz, _vpp]),
+    "b200_host_free_pinned": (_i, [_vp]),
+    "b200_event_create": (_i, [_vp, _vpp]),
+    "b200_event_record": (_i, [_vp, _vp]),
+    "b200_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
+    "b200_event_destroy": (_i, [_vp]),
+    "b200_csr_plan_create": (_i, [_vp, _vp, _i, _vpp]),
+    "b200_csr_plan_get_info": (_i, [_vp, C.POINTER(CsrPlanInfo)]),
+    "b200_csr_plan_destroy": (_i, [_vp]),
+    "b200_spmv_csr_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "b200_spmv_csr_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "b200_spmv_coo_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "b200_spmv_coo_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "b200_spmv_ell_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "b200_spmv_ell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "b200_spmv_ellcm_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "b200_spmv_ellcm_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "b200_spmv_sell_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_spmv_sell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_spmv_sell64_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_spmv_sell64_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_spmv_cmrs_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "b200_spmv_cmrs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "b200_check_sorted_rows": (_i, [_vp, _vp, _i, _i]),
+    "b200_build_csr_ptr": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200_row_length_stats": (_i, [_vp, _vp, _i, C.POINTER(RowStats)]),
+    "b200_build_ell_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "b200_build_ell_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "b200_build_ell_colmajor_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b200_build_ell_colmajor_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b200_sell_num_slices": (_i, [_i, _i]),
+    "b200_build_sell_ptr": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(_ll)]),
+    "b200_sell_ptr_to_i32": (_i, [_vp, _vp, _i, _vp]),
+    "b200_build_sell_fill_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200_build_sell_fill_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200_cmrs_num_strips": (_i, [_i, _i]),
+    "b200_build_cmrs": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b200_convert_f64_to_f32": (_i, [_vp, _vp, _vp, _ll]),
+    "b200_fill_ramp_f64": (_i, [_vp, _vp, _i]),
+    "b200_fill_ramp_f32": (_i, [_vp, _vp, _i]),
+    "b200_gen_banded_nnz": (_ll, [_ll, _i, _i, _i]),
+    "b200_gen_banded_coo": (_i, [_vp, _i, _i, _i, _i, _i, _u64, _vp, _vp, _vp]),
+    "b200_gen_laplace7_nnz": (_ll, [_i, _i, _i, _i, _i]),
+    "b200_gen_laplace7_coo": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b200_gen_uniform_f64": (_i, [_vp, _vp, _ll, _u64, C.c_double, C.c_double]),
+    "b200_gen_uniform_f32": (_i, [_vp, _vp, _ll, _u64, C.c_float, C.c_float]),
+    "b200_gen_banded_coo_host": (_i, [_i, _i, _i, _i, _i, _u64, _vp, _vp, _vp]),
+    "b200_gen_uniform_f64_host": (_i, [_vp, _ll, _u64, C.c_double, C.c_double]),
+    "b200_partition_rows": (_i, [_vp, _i, _i, _i, _vp]),
+    "b200_scale_f64": (_i, [_vp, _vp, _ll, _vp, _i]),
+    "b200_sumsq_f64": (_i, [_vp, _vp, _ll, _vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200spmv.so (built in-tree by `make -C opencl-spmv-algorithms_b200 lib`)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with __graft_entry__.build(); "
+                "there is no CPU fallback")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(status: int, where: str) -> None:
+    if status != SUCCESS:
+        raise B200Error(status, where, lib().b200_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().b200_get_device_count(C.byref(n)), "b200_get_device_count")
+    return n.value
+
+
+_DT = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+
+
+def suffix(dtype) -> str:
+    return _DT[np.dtype(dtype)]
+
+
+class DeviceArray:
+    """A typed device allocation owned through the C ABI (b200_malloc / b200_free)."""
+
+    def __init__(self, ctx: "Context", n: int, dtype):
+        self.ctx, self.n, self.dtype = ctx, int(n), np.dtype(dtype)
+        p = C.c_void_p()
+        check(lib().b200_malloc(ctx.h, self.nbytes, C.byref(p)), "b200_malloc")
+        self.ptr = p.value or 0
+        self._p = p
+
+    @property
+    def nbytes(self) -> int:
+        return self.n * self.dtype.itemsize
+
+    def upload(self, host: np.ndarray) -> "DeviceArray":
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.size == self.n, (host.size, self.n)
+        self._keep = host  # the copy is asynchronous
+        check(lib().b200_memcpy_h2d_async(self.ctx.h, self.ptr, host.ctypes.data, self.nbytes),
+              "b200_memcpy_h2d_async")
+        return self
+
+    def download(self, count: int | None = None) -> np.ndarray:
+        n = self.n if count is None else int(count)
+        out = np.empty(n, self.dtype)
+        check(lib().b200_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, n * self.dtype.itemsize),
+              "b200_memcpy_d2h")
+        return out
+
+    def fill_bytes(self, value: int = 0) -> "DeviceArray":
+        check(lib().b200_memset_async(self.ctx.h, self.ptr, value, self.nbytes), "b200_memset_async")
+        return self
+
+    def free(self) -> None:
+        if self.ptr:
+            check(lib().b200_free(self.ctx.h, self.ptr), "b200_free")
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx.h:
+                lib().b200_free(self.ctx.h, self.ptr)
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+class Context:
+    """One device + one in-order stream (cl_context + cl_command_queue of the reference)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        if stream is None:
+            check(lib().b200_ctx_create(device, C.byref(h)), "b200_ctx_create")
+        else:
+            check(lib().b200_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h)),
+                  "b200_ctx_create_on_stream")
+        self.h = h
+        self.device = device
+
+    def empty(self, n, dtype) -> DeviceArray:
+        return DeviceArray(self, n, dtype)
+
+    def zeros(self, n, dtype) -> DeviceArray:
+        return DeviceArray(self, n, dtype).fill_bytes(0)
+
+    def array(self, host: np.ndarray, dtype=None) -> DeviceArray:
+        host = np.asarray(host)
+        return DeviceArray(self, host.size, dtype or host.dtype).upload(host)
+
+    def sync(self) -> None:
+        check(lib().b200_sync(self.h), "b200_sync")
+
+    def set_l2_persist(self, arr: DeviceArray | None) -> None:
+        check(lib().b200_ctx_set_l2_persist(self.h, arr.ptr if arr else None,
+                                            arr.nbytes if arr else 0), "b200_ctx_set_l2_persist")
+
+    def event(self) -> "Event":
+        return Event(self)
+
+    def close(self) -> None:
+        if self.h:
+            lib().b200_ctx_destroy(self.h)
+            self.h = None
+
+
+class Event:
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(lib().b200_event_create(ctx.h, C.byref(self.h)), "b200_event_create")
+
+    def record(self) -> "Event":
+        check(lib().b200_event_record(self.ctx.h, self.h), "b200_event_record")
+        return self
+
+    def elapsed_ms_until(self, stop: "Event") -> float:
+        ms = C.c_float()
+        check(lib().b200_event_elapsed_ms(self.h, stop.h, C.byref(ms)), "b200_event_elapsed_ms")
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b200_event_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix,  # noqa: E402,F401
+                      algorithmic_bytes, build_all, partition_rows)

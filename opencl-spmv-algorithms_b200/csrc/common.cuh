@@ -1,0 +1,128 @@
+// common.cuh -- shared device/host helpers of libb200spmv (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200spmv.h"
+
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 1000
+#error "libb200spmv is written for sm_100a (B200) only"
+#endif
+
+struct b200_ctx {
+    int device;
+    cudaStream_t stream;
+    bool owns_stream;
+    int sm_count;
+    int l2_bytes;
+    int max_persist_l2;
+    int *scratch;          // small device scratch (flags / counters), 4 KiB
+    void *host_scratch;    // pinned, 4 KiB, for small readbacks
+};
+
+struct b200_event {
+    cudaEvent_t ev;
+    int device;
+};
+
+void b200_set_error(const char *fmt, ...);
+int b200_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define B200_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return b200_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                                                \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            b200_set_error("%s: %s", __func__, msg);                           \
+            return B200_ERR_INVALID_VALUE;                                     \
+        }                                                                      \
+    } while (0)
+
+#define B200_LAUNCH_CHECK() B200_CUDA(cudaGetLastError())
+
+static inline int b200_ctx_enter(const b200_ctx *ctx)
+{
+    if (!ctx) {
+        b200_set_error("null context");
+        return B200_ERR_INVALID_VALUE;
+    }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return b200_cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    return B200_SUCCESS;
+}
+#define B200_ENTER(ctx)                          \
+    do {                                         \
+        int rc__ = b200_ctx_enter(ctx);          \
+        if (rc__) return rc__;                   \
+    } while (0)
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static inline unsigned ceil_div_u(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------
+// Loads.  Matrix arrays (indices, values) are read exactly once per SpMV: stream them with
+// evict-first (ld.global.cs) so they do not push x out of L1/L2.  x is gathered through the
+// read-only path (ld.global.nc) and is the only data worth caching.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_stream(const int4 *p) { return __ldcs(p); }
+__device__ __forceinline__ int2 ld_stream(const int2 *p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ long long ld_stream(const long long *p) { return __ldcs(p); }
+
+template <typename T>
+__device__ __forceinline__ T ld_x(const T *x, int c)
+{
+    return __ldg(x + c);
+}
+
+// four consecutive values as one (fp32) or two (fp64) 128-bit loads
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+    float v[4];
+    __device__ __forceinline__ void load(const float *p)
+    {
+        float4 t = ld_stream(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <>
+struct Vec4<double> {
+    double v[4];
+    __device__ __forceinline__ void load(const double *p)
+    {
+        double2 a = ld_stream(reinterpret_cast<const double2 *>(p));
+        double2 b = ld_stream(reinterpret_cast<const double2 *>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
+struct IVec4 {
+    int v[4];
+    __device__ __forceinline__ void load(const int *p)
+    {
+        int4 t = ld_stream(reinterpret_cast<const int4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+
+template <int LANES, typename T>
+__device__ __forceinline__ T subwarp_sum(T v)
+{
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+#endif  // __CUDACC__

@@ -1,0 +1,293 @@
+// runtime.cu -- contexts, buffers, events, errors: the C-ABI replacement of the OpenCL runtime
+// calls the reference drivers make (include/b200spmv.h cites each one).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_last_error[512] = "";
+
+void b200_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+    va_end(ap);
+}
+
+int b200_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    b200_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    // clear sticky-free errors so that the next call reports its own failure
+    (void)cudaGetLastError();
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+        return B200_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return B200_ERR_OUT_OF_MEMORY;
+    return B200_ERR_CUDA;
+}
+
+extern "C" {
+
+const char *b200_status_string(int status)
+{
+    switch (status) {
+    case B200_SUCCESS: return "success";
+    case B200_ERR_NO_DEVICE: return "no CUDA device";
+    case B200_ERR_CUDA: return "CUDA runtime error";
+    case B200_ERR_INVALID_VALUE: return "invalid value";
+    case B200_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case B200_ERR_UNSUPPORTED: return "unsupported";
+    case B200_ERR_DOMAIN: return "input outside the builder's domain";
+    default: return "unknown status";
+    }
+}
+
+const char *b200_last_error(void) { return g_last_error; }
+
+int b200_version(void) { return B200SPMV_VERSION; }
+
+int b200_get_device_count(int *count)
+{
+    B200_REQUIRE(count, "null count");
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return b200_cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    if (n <= 0) {
+        b200_set_error("no CUDA device present");
+        return B200_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return B200_SUCCESS;
+}
+
+int b200_device_name(int device, char *buf, size_t buf_len)
+{
+    B200_REQUIRE(buf && buf_len > 0, "null buffer");
+    cudaDeviceProp p;
+    B200_CUDA(cudaGetDeviceProperties(&p, device));
+    snprintf(buf, buf_len, "%s", p.name);
+    return B200_SUCCESS;
+}
+
+int b200_device_sm_count(int device, int *sm_count)
+{
+    B200_REQUIRE(sm_count, "null sm_count");
+    B200_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
+    return B200_SUCCESS;
+}
+
+static int ctx_create_impl(int device, cudaStream_t stream, bool own, b200_ctx **out)
+{
+    B200_REQUIRE(out, "null ctx out");
+    *out = nullptr;
+    int n = 0;
+    int rc = b200_get_device_count(&n);
+    if (rc) return rc;
+    if (device < 0 || device >= n) {
+        b200_set_error("device %d out of range (have %d)", device, n);
+        return B200_ERR_NO_DEVICE;
+    }
+    B200_CUDA(cudaSetDevice(device));
+    int major = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major < 10) {
+        b200_set_error("device %d is sm_%d0; libb200spmv carries sm_100a code only", device, major);
+        return B200_ERR_UNSUPPORTED;
+    }
+    b200_ctx *c = new b200_ctx();
+    c->device = device;
+    c->owns_stream = own;
+    c->stream = stream;
+    c->scratch = nullptr;
+    c->host_scratch = nullptr;
+    if (own) {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return b200_cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+        }
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device);
+    cudaDeviceGetAttribute(&c->max_persist_l2, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaError_t e = cudaMalloc(&c->scratch, 4096);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->host_scratch, 4096);
+    if (e != cudaSuccess) {
+        if (c->scratch) cudaFree(c->scratch);
+        if (own) cudaStreamDestroy(c->stream);
+        delete c;
+        return b200_cuda_fail(e, "scratch allocation", __FILE__, __LINE__);
+    }
+    *out = c;
+    return B200_SUCCESS;
+}
+
+int b200_ctx_create(int device, b200_ctx **ctx) { return ctx_create_impl(device, nullptr, true, ctx); }
+
+int b200_ctx_create_on_stream(int device, void *cuda_stream, b200_ctx **ctx)
+{
+    return ctx_create_impl(device, reinterpret_cast<cudaStream_t>(cuda_stream), false, ctx);
+}
+
+int b200_ctx_destroy(b200_ctx *ctx)
+{
+    if (!ctx) return B200_SUCCESS;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return B200_SUCCESS;
+}
+
+int b200_ctx_device(const b200_ctx *ctx, int *device)
+{
+    B200_REQUIRE(ctx && device, "null argument");
+    *device = ctx->device;
+    return B200_SUCCESS;
+}
+
+int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes)
+{
+    B200_ENTER(ctx);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (bytes == 0 || !dptr) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        B200_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        return B200_SUCCESS;
+    }
+    if (ctx->max_persist_l2 <= 0) return B200_SUCCESS;  // nothing to set aside: best effort
+    size_t carve = bytes < (size_t)ctx->max_persist_l2 ? bytes : (size_t)ctx->max_persist_l2;
+    B200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    int max_window = 0;
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    size_t win = bytes;
+    if (max_window > 0 && win > (size_t)max_window) win = (size_t)max_window;
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(dptr);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)carve / (float)win;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    B200_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return B200_SUCCESS;
+}
+
+int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(dptr, "null dptr");
+    *dptr = nullptr;
+    // 16 spare bytes: the vector kernels read whole aligned 16-byte groups
+    B200_CUDA(cudaMalloc(dptr, (bytes ? bytes : 1) + 16));
+    return B200_SUCCESS;
+}
+
+int b200_free(b200_ctx *ctx, void *dptr)
+{
+    B200_ENTER(ctx);
+    if (dptr) B200_CUDA(cudaFree(dptr));
+    return B200_SUCCESS;
+}
+
+int b200_memcpy_h2d_async(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    B200_ENTER(ctx);
+    if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    B200_ENTER(ctx);
+    if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_memcpy_d2h_async(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    B200_ENTER(ctx);
+    if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_memcpy_d2d_async(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    B200_ENTER(ctx);
+    if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_memset_async(b200_ctx *ctx, void *dst, int byte_value, size_t bytes)
+{
+    B200_ENTER(ctx);
+    if (bytes) B200_CUDA(cudaMemsetAsync(dst, byte_value, bytes, ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_sync(b200_ctx *ctx)
+{
+    B200_ENTER(ctx);
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_host_alloc_pinned(size_t bytes, void **hptr)
+{
+    B200_REQUIRE(hptr, "null hptr");
+    *hptr = nullptr;
+    B200_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
+    return B200_SUCCESS;
+}
+
+int b200_host_free_pinned(void *hptr)
+{
+    if (hptr) B200_CUDA(cudaFreeHost(hptr));
+    return B200_SUCCESS;
+}
+
+int b200_event_create(b200_ctx *ctx, b200_event **ev)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(ev, "null event out");
+    b200_event *e = new b200_event();
+    e->device = ctx->device;
+    cudaError_t ce = cudaEventCreate(&e->ev);
+    if (ce != cudaSuccess) {
+        delete e;
+        return b200_cuda_fail(ce, "cudaEventCreate", __FILE__, __LINE__);
+    }
+    *ev = e;
+    return B200_SUCCESS;
+}
+
+int b200_event_record(b200_ctx *ctx, b200_event *ev)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(ev, "null event");
+    B200_CUDA(cudaEventRecord(ev->ev, ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_event_elapsed_ms(b200_event *start, b200_event *stop, float *ms)
+{
+    B200_REQUIRE(start && stop && ms, "null argument");
+    B200_CUDA(cudaSetDevice(stop->device));
+    B200_CUDA(cudaEventSynchronize(stop->ev));
+    B200_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    return B200_SUCCESS;
+}
+
+int b200_event_destroy(b200_event *ev)
+{
+    if (!ev) return B200_SUCCESS;
+    cudaSetDevice(ev->device);
+    cudaEventDestroy(ev->ev);
+    delete ev;
+    return B200_SUCCESS;
+}
+
+}  // extern "C"

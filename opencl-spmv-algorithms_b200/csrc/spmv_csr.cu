@@ -1,0 +1,384 @@
+// spmv_csr.cu -- CSR and row-major ELL SpMV for sm_100a.
+//
+// Replaces kernels/Csr.cl:1-17 (scalar thread-per-row, 32 work-groups) and kernels/Ell.cl:1-39
+// (16-lane work-group per row with a local-memory tree).  B200 design:
+//   * LPR (2..32) lanes cooperate on one row; LPR is picked from the row-length statistics so
+//     that a row is covered by about one 128-bit load per lane (vector / warp-per-row family);
+//   * indices and values are fetched as 128-bit loads on 16-byte ADDRESS-aligned groups of four
+//     entries; the ragged first/last group of a row is masked, never re-read;
+//   * matrix data streams with evict-first, x goes through the read-only path;
+//   * rows far longer than the mean (power-law inputs) are skipped by the vector kernel and
+//     handled by a block-per-row kernel that splits very long rows across blocks (one atomic
+//     per block);
+//   * reduction is __shfl_xor_sync only -- no shared memory, no barriers.
+// HBM-bound: algorithmic bytes = nnz*(4+V) + (R+1)*4 + Cn*V + R*V.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// dot product of entries [s, e) of (col, data) with x, cooperatively by LPR lanes.
+template <typename T, int LPR>
+__device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *__restrict__ data,
+                                         const T *__restrict__ x, long long s, long long e, int lane)
+{
+    T acc = 0;
+    const long long g_end = (e + 3) >> 2;
+#pragma unroll 2
+    for (long long g = (s >> 2) + lane; g < g_end; g += LPR) {
+        const long long j = g << 2;
+        IVec4 c;
+        Vec4<T> v;
+        c.load(col + j);
+        v.load(data + j);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (j + k >= s && j + k < e) acc += v.v[k] * ld_x(x, c.v[k]);
+    }
+    return acc;
+}
+
+// same, scalar loads: used only when an array is not 16-byte aligned
+template <typename T, int LPR>
+__device__ __forceinline__ T row_dot_scalar(const int *__restrict__ col, const T *__restrict__ data,
+                                            const T *__restrict__ x, long long s, long long e, int lane)
+{
+    T acc = 0;
+    for (long long j = s + lane; j < e; j += LPR) acc += ld_stream(data + j) * ld_x(x, ld_stream(col + j));
+    return acc;
+}
+
+template <typename T, int LPR, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+csr_vector_kernel(const int *__restrict__ ptr, const int *__restrict__ col, const T *__restrict__ data,
+                  const T *__restrict__ x, T *__restrict__ y, int n_rows, int long_threshold)
+{
+    const int lane = threadIdx.x & (LPR - 1);
+    const long long row = ((long long)blockIdx.x * kBlock + threadIdx.x) / LPR;
+    int s = 0, e = 0;
+    if (row < n_rows) {
+        s = __ldg(ptr + row);
+        e = __ldg(ptr + row + 1);
+    }
+    const bool is_long = (e - s) > long_threshold;
+    T acc = 0;
+    if (!is_long)
+        acc = VEC ? row_dot_vec<T, LPR>(col, data, x, s, e, lane)
+                  : row_dot_scalar<T, LPR>(col, data, x, s, e, lane);
+    acc = subwarp_sum<LPR>(acc);
+    // long rows: publish 0 here; csr_long_rows_kernel accumulates into it afterwards
+    if (lane == 0 && row < n_rows) y[row] = is_long ? T(0) : acc;
+}
+
+// one (row, split) pair per block; gridDim = (n_long, n_split)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+csr_long_rows_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
+                     const T *__restrict__ data, const T *__restrict__ x, T *__restrict__ y,
+                     const int *__restrict__ long_rows)
+{
+    __shared__ T warp_part[kBlock / 32];
+    const int row = long_rows[blockIdx.x];
+    const long long s0 = ptr[row], e0 = ptr[row + 1];
+    // split [s0,e0) into gridDim.y pieces on 4-entry boundaries
+    long long per = ((e0 - s0 + gridDim.y - 1) / gridDim.y + 3) & ~3ll;
+    long long s = s0 + per * blockIdx.y;
+    long long e = s + per < e0 ? s + per : e0;
+    T acc = 0;
+    if (s < e) {
+        if (VEC) {
+            const long long g_end = (e + 3) >> 2;
+#pragma unroll 2
+            for (long long g = (s >> 2) + threadIdx.x; g < g_end; g += kBlock) {
+                const long long j = g << 2;
+                IVec4 c;
+                Vec4<T> v;
+                c.load(col + j);
+                v.load(data + j);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (j + k >= s && j + k < e) acc += v.v[k] * ld_x(x, c.v[k]);
+            }
+        } else {
+            for (long long j = s + threadIdx.x; j < e; j += kBlock)
+                acc += ld_stream(data + j) * ld_x(x, ld_stream(col + j));
+        }
+    }
+    acc = subwarp_sum<32>(acc);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T t = threadIdx.x < kBlock / 32 ? warp_part[threadIdx.x] : T(0);
+        t = subwarp_sum<32>(t);
+        if (threadIdx.x == 0 && s < e) atomicAdd(y + row, t);
+    }
+}
+
+// row-major ELL (the reference's arrays): row r owns entries [r*K, (r+1)*K)
+template <typename T, int LPR, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+ell_rowmajor_kernel(const T *__restrict__ data, const int *__restrict__ col, const T *__restrict__ x,
+                    T *__restrict__ y, int n_rows, int row_size)
+{
+    const int lane = threadIdx.x & (LPR - 1);
+    const long long row = ((long long)blockIdx.x * kBlock + threadIdx.x) / LPR;
+    long long s = 0, e = 0;
+    if (row < n_rows) {
+        s = row * row_size;
+        e = s + row_size;
+    }
+    T acc = VEC ? row_dot_vec<T, LPR>(col, data, x, s, e, lane)
+                : row_dot_scalar<T, LPR>(col, data, x, s, e, lane);
+    acc = subwarp_sum<LPR>(acc);
+    if (lane == 0 && row < n_rows) y[row] = acc;
+}
+
+// ---- plan: row-length statistics on the device --------------------------------------------
+struct PlanStats {
+    int min_len, max_len, n_long, pad;
+};
+
+__global__ void csr_stats_kernel(const int *__restrict__ ptr, int n_rows, int long_threshold,
+                                 PlanStats *out)
+{
+    int lo = 0x7fffffff, hi = 0, cnt = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        int len = ptr[r + 1] - ptr[r];
+        lo = min(lo, len);
+        hi = max(hi, len);
+        cnt += len > long_threshold;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out->min_len, lo);
+        atomicMax(&out->max_len, hi);
+        if (cnt) atomicAdd(&out->n_long, cnt);
+    }
+}
+
+__global__ void csr_collect_long_kernel(const int *__restrict__ ptr, int n_rows, int long_threshold,
+                                        int *counter, int *list)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        if (ptr[r + 1] - ptr[r] > long_threshold) list[atomicAdd(counter, 1)] = (int)r;
+    }
+}
+
+int pick_lanes(double mean_len)
+{
+    // one 128-bit load (4 entries) per lane covers the mean row
+    int lanes = 2;
+    while (lanes < 32 && lanes * 4 < mean_len) lanes <<= 1;
+    return lanes;
+}
+
+}  // namespace
+
+struct b200_csr_plan {
+    b200_csr_plan_info info;
+    int device;
+    int n_split;      // blocks per long row
+    int *long_rows;   // device list, n_long_rows entries
+};
+
+extern "C" {
+
+int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_plan **plan)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(ptr && plan && n_rows >= 0, "bad argument");
+    *plan = nullptr;
+    int first_last[2] = {0, 0};
+    if (n_rows > 0) {
+        B200_CUDA(cudaMemcpyAsync(&first_last[0], ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaMemcpyAsync(&first_last[1], ptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    b200_csr_plan *p = new b200_csr_plan();
+    p->device = ctx->device;
+    p->long_rows = nullptr;
+    p->n_split = 1;
+    b200_csr_plan_info &in = p->info;
+    in.n_rows = n_rows;
+    in.nnz = (long long)first_last[1] - first_last[0];
+    in.mean_len = n_rows > 0 ? (double)in.nnz / n_rows : 0.0;
+    in.lanes_per_row = pick_lanes(in.mean_len);
+    // a row is "long" when it would keep its lanes busy for more than 16 vector iterations
+    in.long_threshold = in.lanes_per_row * 4 * 16;
+    in.min_len = in.max_len = 0;
+    in.n_long_rows = 0;
+    if (n_rows > 0) {
+        PlanStats init = {0x7fffffff, 0, 0, 0};
+        PlanStats *d = reinterpret_cast<PlanStats *>(ctx->scratch);
+        B200_CUDA(cudaMemcpyAsync(d, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+        int blocks = (int)min((long long)ctx->sm_count * 8, ((long long)n_rows + 255) / 256);
+        csr_stats_kernel<<<blocks, 256, 0, ctx->stream>>>(ptr, n_rows, in.long_threshold, d);
+        B200_LAUNCH_CHECK();
+        PlanStats got;
+        B200_CUDA(cudaMemcpyAsync(&got, d, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        in.min_len = got.min_len;
+        in.max_len = got.max_len;
+        in.n_long_rows = got.n_long;
+        if (got.n_long > 0) {
+            cudaError_t e = cudaMalloc(&p->long_rows, sizeof(int) * (size_t)got.n_long);
+            if (e != cudaSuccess) {
+                delete p;
+                return b200_cuda_fail(e, "cudaMalloc(long_rows)", __FILE__, __LINE__);
+            }
+            int *counter = ctx->scratch + 16;
+            B200_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+            csr_collect_long_kernel<<<blocks, 256, 0, ctx->stream>>>(ptr, n_rows, in.long_threshold,
+                                                                    counter, p->long_rows);
+            B200_LAUNCH_CHECK();
+            B200_CUDA(cudaStreamSynchronize(ctx->stream));
+            // one block streams ~64 Ki entries; longer rows are split (capped)
+            long long split = ((long long)in.max_len + 65535) / 65536;
+            p->n_split = (int)(split < 1 ? 1 : (split > 128 ? 128 : split));
+        }
+    }
+    *plan = p;
+    return B200_SUCCESS;
+}
+
+int b200_csr_plan_get_info(const b200_csr_plan *plan, b200_csr_plan_info *info)
+{
+    B200_REQUIRE(plan && info, "null argument");
+    *info = plan->info;
+    return B200_SUCCESS;
+}
+
+int b200_csr_plan_destroy(b200_csr_plan *plan)
+{
+    if (!plan) return B200_SUCCESS;
+    cudaSetDevice(plan->device);
+    if (plan->long_rows) cudaFree(plan->long_rows);
+    delete plan;
+    return B200_SUCCESS;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T, int LPR>
+int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data, const T *x, T *y,
+                   int n_rows, int long_threshold, bool vec)
+{
+    unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
+    if (vec)
+        csr_vector_kernel<T, LPR, true><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+    else
+        csr_vector_kernel<T, LPR, false><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+template <typename T>
+int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, const T *x, T *y,
+                  int n_rows, const b200_csr_plan *plan)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(ptr && x && y && n_rows >= 0, "bad argument");
+    if (n_rows == 0) return B200_SUCCESS;
+    b200_csr_plan *tmp = nullptr;
+    if (!plan) {
+        int rc = b200_csr_plan_create(ctx, ptr, n_rows, &tmp);
+        if (rc) return rc;
+        plan = tmp;
+    }
+    B200_REQUIRE(plan->info.n_rows == n_rows, "plan was built for a different matrix");
+    B200_REQUIRE(plan->info.nnz == 0 || (col && data), "null col/data");
+    const bool vec = aligned16(col) && aligned16(data);
+    const int thr = plan->info.long_threshold;
+    int rc;
+    switch (plan->info.lanes_per_row) {
+    case 2: rc = launch_csr_lpr<T, 2>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    case 4: rc = launch_csr_lpr<T, 4>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    case 8: rc = launch_csr_lpr<T, 8>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    case 16: rc = launch_csr_lpr<T, 16>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    default: rc = launch_csr_lpr<T, 32>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    }
+    if (rc == B200_SUCCESS && plan->info.n_long_rows > 0) {
+        dim3 grid(plan->info.n_long_rows, plan->n_split);
+        if (vec)
+            csr_long_rows_kernel<T, true><<<grid, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, plan->long_rows);
+        else
+            csr_long_rows_kernel<T, false><<<grid, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, plan->long_rows);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = b200_cuda_fail(e, "csr_long_rows_kernel", __FILE__, __LINE__);
+    }
+    if (tmp) {
+        cudaStreamSynchronize(ctx->stream);
+        b200_csr_plan_destroy(tmp);
+    }
+    return rc;
+}
+
+template <typename T, int LPR>
+int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *y, int n_rows,
+                   int row_size, bool vec)
+{
+    unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
+    if (vec)
+        ell_rowmajor_kernel<T, LPR, true><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+    else
+        ell_rowmajor_kernel<T, LPR, false><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+template <typename T>
+int spmv_ell_impl(b200_ctx *ctx, const T *data, const int *col, const T *x, T *y, int n_rows,
+                  int row_size)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(x && y && n_rows >= 0 && row_size >= 0, "bad argument");
+    if (n_rows == 0) return B200_SUCCESS;
+    B200_REQUIRE(row_size == 0 || (data && col), "null data/indices");
+    const bool vec = aligned16(col) && aligned16(data);
+    switch (pick_lanes((double)row_size)) {
+    case 2: return launch_ell_lpr<T, 2>(ctx, data, col, x, y, n_rows, row_size, vec);
+    case 4: return launch_ell_lpr<T, 4>(ctx, data, col, x, y, n_rows, row_size, vec);
+    case 8: return launch_ell_lpr<T, 8>(ctx, data, col, x, y, n_rows, row_size, vec);
+    case 16: return launch_ell_lpr<T, 16>(ctx, data, col, x, y, n_rows, row_size, vec);
+    default: return launch_ell_lpr<T, 32>(ctx, data, col, x, y, n_rows, row_size, vec);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_spmv_csr_f64(b200_ctx *ctx, const int *ptr, const int *col, const double *data,
+                      const double *vect, double *output, int n_rows, const b200_csr_plan *plan)
+{
+    return spmv_csr_impl<double>(ctx, ptr, col, data, vect, output, n_rows, plan);
+}
+
+int b200_spmv_csr_f32(b200_ctx *ctx, const int *ptr, const int *col, const float *data,
+                      const float *vect, float *output, int n_rows, const b200_csr_plan *plan)
+{
+    return spmv_csr_impl<float>(ctx, ptr, col, data, vect, output, n_rows, plan);
+}
+
+int b200_spmv_ell_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                      double *output, int n_rows, int row_size)
+{
+    return spmv_ell_impl<double>(ctx, data, indices, vect, output, n_rows, row_size);
+}
+
+int b200_spmv_ell_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
+                      float *output, int n_rows, int row_size)
+{
+    return spmv_ell_impl<float>(ctx, data, indices, vect, output, n_rows, row_size);
+}
+
+}  // extern "C"

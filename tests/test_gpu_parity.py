@@ -1,0 +1,316 @@
+"""GPU parity tests proper: every call goes through the C ABI (libb200spmv.so) and is compared with
+the CPU oracle on the same seeded inputs.  Integer/index arrays: bit-exact.  y: relative max-norm
+<= 1e-12 (fp64) / 1e-5 (fp32) against the serial fp64 COO reference (check_result semantics,
+inc/helper_functions.h:207-219) -- the tolerances BASELINE.json states."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from __graft_entry__ import load_package
+from conftest import random_sorted_matrix
+from oracle import binding as O
+
+pytestmark = pytest.mark.gpu
+pkg = load_package()
+TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def check_y(name, y, y_ref, dtype):
+    err = O.rel_maxnorm(y, y_ref)
+    assert err <= TOL[np.dtype(dtype)], f"{name} {np.dtype(dtype).name}: rel max-norm {err:g}"
+
+
+def run_all_formats(ctx, n_rows, n_cols, rows, cols, vals, dtype, x=None, coo_order=None,
+                    on_domain=True):
+    """Build the five formats on the GPU, compare every array with the oracle, run every kernel."""
+    x = np.arange(n_cols, dtype=np.float64) if x is None else x   # csr.c:95-99
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    coo_any = None
+    if coo_order is not None:
+        coo_any = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows[coo_order], cols[coo_order],
+                                          vals[coo_order])
+    m = pkg.build_all(coo, dtype, coo_any=coo_any)
+    xd = ctx.array(x.astype(dtype))
+    lens = np.bincount(rows, minlength=n_rows)
+
+    # ---- builds: bit-exact against the oracle (which is pinned to the reference) ----
+    ptr_ref = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    np.testing.assert_array_equal(m["csr"].ptr.download(), ptr_ref)
+    if on_domain:
+        ptr_o, changes = O.build_csr(n_rows, rows)
+        assert changes == n_rows - 1
+        np.testing.assert_array_equal(ptr_o, ptr_ref)
+        K = int(lens.max())
+        hi, lo, tot, last = O.ell_stats(n_rows, rows)
+        st = m["csr"].row_stats()
+        assert (st.max_len, st.min_len, st.sum_len) == (K, int(lens.min()), int(lens.sum()))
+        if n_rows > 1:
+            assert (st.max_len_excl_last, st.min_len_excl_last, st.sum_len_excl_last, st.last_len) \
+                == (hi, lo, tot, last)
+        assert m["ell"].row_size == K
+        if last <= hi and n_rows > 1:  # the reference's well-defined ELL domain (quirk q3)
+            ec, ed = O.build_ell(n_rows, hi, rows, cols, vals)
+            np.testing.assert_array_equal(m["ell"].cols.download(), ec)
+            assert m["ell"].data.download().tobytes() == ed.astype(dtype).tobytes()
+            cc, cd = O.ell_to_colmajor(n_rows, hi, m["ellcm"].pitch, ec, ed)
+            np.testing.assert_array_equal(m["ellcm"].cols.download(), cc)
+            assert m["ellcm"].data.download().tobytes() == cd.astype(dtype).tobytes()
+        ri, sc, sd = O.build_sell(n_rows, rows, cols, vals)
+        np.testing.assert_array_equal(m["sell"].row_indices.download(), ri)
+        np.testing.assert_array_equal(m["sell"].slice_ptr.download(), ri.astype(np.int64))
+        np.testing.assert_array_equal(m["sell"].cols.download(), sc)
+        assert m["sell"].data.download().tobytes() == sd.astype(dtype).tobytes()
+        sp, ris = O.build_cmrs(n_rows, rows)
+        np.testing.assert_array_equal(m["cmrs"].strip_ptr.download(), sp)
+        np.testing.assert_array_equal(m["cmrs"].row_in_strip.download(), ris)
+
+    # ---- SpMV: every kernel, y poisoned first so unwritten rows are caught ----
+    for name, mat in m.items():
+        yd = ctx.array(np.full(n_rows, np.nan, dtype))
+        mat.spmv(xd, yd)
+        check_y(name, yd.download(), y_ref, dtype)
+    # CSR without a plan (analysed on the fly) gives the same bits as with one
+    y1, y2 = ctx.zeros(n_rows, dtype), ctx.zeros(n_rows, dtype)
+    m["csr"].spmv(xd, y1, use_plan=True)
+    m["csr"].spmv(xd, y2, use_plan=False)
+    assert y1.download().tobytes() == y2.download().tobytes()
+    # SELL writing the reference's padded output (n_slices*32, sigma_c.c:212): padding rows = 0
+    ns = m["sell"].n_slices
+    yp = ctx.array(np.full(ns * 32, np.nan, dtype))
+    m["sell"].spmv(xd, yp, n_out=ns * 32)
+    got = yp.download()
+    check_y("sell-padded", got[:n_rows], y_ref, dtype)
+    assert np.all(got[n_rows:] == 0)
+    return m, y_ref
+
+
+SHAPES = [  # n_rows, n_cols, min_len, max_len, seed, long_rows
+    (1, 40, 3, 3, 0, ()),
+    (2, 9, 1, 4, 1, ()),
+    (31, 64, 1, 9, 2, ()),
+    (32, 64, 1, 9, 3, ()),
+    (33, 64, 1, 9, 4, ()),
+    (257, 300, 1, 70, 5, ()),
+    (1000, 1500, 1, 3, 6, ()),
+    (1000, 5000, 20, 120, 7, ()),
+    (4099, 6000, 1, 40, 8, ((0, 40), (4098, 1))),
+    (3000, 60000, 1, 12, 9, ((5, 50000), (1777, 9000), (2999, 700))),   # long-row kernel, splits
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"r{s[0]}-l{s[2]}-{s[3]}" for s in SHAPES])
+def test_formats_random(ctx, shape, dtype):
+    n_rows, n_cols, lo, hi, seed, long_rows = shape
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, lo, hi, seed, long_rows)
+    order = np.lexsort((rows, cols))  # column-major file order, as cant.mtx for coo.c
+    run_all_formats(ctx, n_rows, n_cols, rows, cols, vals, dtype, coo_order=order)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_random_x_and_unsorted_coo(ctx, dtype):
+    rows, cols, vals = random_sorted_matrix(2000, 2000, 1, 60, 11)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, 2000)
+    run_all_formats(ctx, 2000, 2000, rows, cols, vals, dtype, x=x, coo_order=rng.permutation(rows.size))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_empty_rows_are_handled(ctx, dtype):
+    """Off the reference's domain (quirk q4: its builders shift everything on an empty row); the
+    GPU builders give the mathematically right arrays."""
+    rows, cols, vals = random_sorted_matrix(500, 700, 1, 20, 12)
+    keep = ~np.isin(rows, [0, 17, 18, 19, 255, 499])
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    m, y_ref = run_all_formats(ctx, 500, 700, rows, cols, vals, dtype, on_domain=False)
+    assert y_ref[17] == 0 and y_ref[499] == 0
+
+
+def test_degenerate_sizes(ctx):
+    for dtype in (np.float64, np.float32):
+        # no rows at all
+        coo = pkg.CooMatrix.from_host(ctx, 0, 5, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
+        csr = pkg.CsrMatrix(coo)
+        assert list(csr.ptr.download()) == [0]
+        x, y = ctx.array(np.ones(5, dtype)), ctx.zeros(1, dtype)
+        csr.spmv(x, y)
+        coo.spmv(x, y)
+        # rows but no entries
+        coo = pkg.CooMatrix.from_host(ctx, 70, 5, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
+        m = pkg.build_all(coo, dtype)
+        for name, mat in m.items():
+            yd = ctx.array(np.full(70, np.nan, dtype))
+            mat.spmv(x, yd)
+            assert np.all(yd.download() == 0), name
+
+
+def test_unsorted_rows_rejected(ctx):
+    coo = pkg.CooMatrix.from_host(ctx, 4, 4, np.array([0, 2, 1, 3], np.int32),
+                                  np.array([0, 1, 2, 3], np.int32), np.ones(4))
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.CsrMatrix(coo)
+    assert e.value.status == pkg.ERR_DOMAIN
+    coo = pkg.CooMatrix.from_host(ctx, 4, 4, np.array([0, 1, 2, 4], np.int32),
+                                  np.array([0, 1, 2, 3], np.int32), np.ones(4))
+    with pytest.raises(pkg.B200Error):
+        pkg.CsrMatrix(coo)
+
+
+def test_bad_arguments_fail_loudly(ctx):
+    L = pkg.lib()
+    x = ctx.zeros(8, np.float64)
+    assert L.b200_spmv_sell_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 16, 1, 8, None) == pkg.ERR_UNSUPPORTED
+    assert L.b200_spmv_cmrs_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, 64, 8) == pkg.ERR_UNSUPPORTED
+    assert L.b200_spmv_ellcm_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, 8, 1, 8) == pkg.ERR_INVALID_VALUE
+    assert L.b200_spmv_csr_f64(None, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, None) == pkg.ERR_INVALID_VALUE
+    assert b"null context" in L.b200_last_error()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_unaligned_arrays_take_the_scalar_kernels(ctx, dtype):
+    """Arrays that are not 16-byte aligned (e.g. a shard view into a larger allocation) must still
+    give the right answer through the scalar-load kernel variants."""
+    n_rows, n_cols = 777, 900
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 50, 21)
+    x = np.arange(n_cols, dtype=np.float64)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    nnz = rows.size
+    L, suf, V = pkg.lib(), pkg.suffix(dtype), np.dtype(dtype).itemsize
+    pad = lambda a, dt: np.concatenate([np.zeros(1, dt), a.astype(dt)])   # shift by one element
+    rows_d, cols_d, vals_d = ctx.array(pad(rows, np.int32)), ctx.array(pad(cols, np.int32)), ctx.array(pad(vals, dtype))
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n_rows))]).astype(np.int32)
+    ptr_d, xd = ctx.array(ptr), ctx.array(x.astype(dtype))
+    yd = ctx.array(np.full(n_rows, np.nan, dtype))
+    pkg.check(getattr(L, "b200_spmv_csr_" + suf)(ctx.h, ptr_d.ptr, cols_d.ptr + 4, vals_d.ptr + V, xd.ptr,
+                                                 yd.ptr, n_rows, None), "csr")
+    check_y("csr-unaligned", yd.download(), y_ref, dtype)
+    yd = ctx.array(np.full(n_rows, np.nan, dtype))
+    pkg.check(getattr(L, "b200_spmv_coo_" + suf)(ctx.h, rows_d.ptr + 4, cols_d.ptr + 4, vals_d.ptr + V,
+                                                 xd.ptr, yd.ptr, nnz, n_rows), "coo")
+    check_y("coo-unaligned", yd.download(), y_ref, dtype)
+    sp, ris = O.build_cmrs(n_rows, rows)
+    sp_d, ris_d = ctx.array(sp), ctx.array(pad(ris, np.int32))
+    yd = ctx.array(np.full(n_rows, np.nan, dtype))
+    pkg.check(getattr(L, "b200_spmv_cmrs_" + suf)(ctx.h, vals_d.ptr + V, cols_d.ptr + 4, sp_d.ptr, ris_d.ptr + 4,
+                                                  xd.ptr, yd.ptr, len(sp) - 1, 8, n_rows), "cmrs")
+    check_y("cmrs-unaligned", yd.download(), y_ref, dtype)
+    ri, sc, sd = O.build_sell(n_rows, rows, cols, vals)
+    sc_d, sd_d, ri_d = ctx.array(pad(sc, np.int32)), ctx.array(pad(sd, dtype)), ctx.array(ri)
+    yd = ctx.array(np.full(n_rows, np.nan, dtype))
+    pkg.check(getattr(L, "b200_spmv_sell_" + suf)(ctx.h, sd_d.ptr + V, sc_d.ptr + 4, xd.ptr, yd.ptr, ri_d.ptr,
+                                                  32, len(ri) - 1, n_rows, None), "sell")
+    check_y("sell-unaligned", yd.download(), y_ref, dtype)
+
+
+@pytest.mark.parametrize("height", [1, 2, 5, 8, 16, 32])
+def test_cmrs_heights(ctx, height):
+    n_rows, n_cols = 1234, 1500
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 30, 31)
+    x = np.arange(n_cols, dtype=np.float64)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    m = pkg.CmrsMatrix(pkg.CsrMatrix(coo), height=height)
+    sp, ris = O.build_cmrs(n_rows, rows, height=height)
+    np.testing.assert_array_equal(m.strip_ptr.download(), sp)
+    np.testing.assert_array_equal(m.row_in_strip.download(), ris)
+    for dtype in (np.float64, np.float32):
+        yd = ctx.array(np.full(n_rows, np.nan, dtype))
+        m.spmv(ctx.array(x.astype(dtype)), yd)
+        check_y(f"cmrs-h{height}", yd.download(), y_ref, dtype)
+
+
+@pytest.mark.parametrize("sigma", [1, 2, 32, 64, 100, 256, 1000, 4096, 5000, 1 << 20])
+def test_sell_sigma(ctx, sigma):
+    """SELL-C-sigma is new (the reference has no sigma): the GPU window sort must equal the oracle's
+    specification -- stable, descending length inside each sigma window, perm[new] = old -- and the
+    layout must reduce to the reference's at sigma = 1."""
+    n_rows, n_cols = 5000, 5000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 60, 41, long_rows=((77, 900), (4000, 400)))
+    x = np.random.default_rng(5).uniform(-1, 1, n_cols)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    perm, sp, sc, sd = O.build_sell_sigma(n_rows, rows, cols, vals, sigma)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo)
+    for dtype in (np.float64, np.float32):
+        for wide in (False, True):
+            m = pkg.SellMatrix(csr, dtype, sigma=sigma, wide=wide)
+            if sigma > 1:
+                np.testing.assert_array_equal(m.perm.download(), perm)
+            np.testing.assert_array_equal(m.slice_ptr.download(), sp)
+            np.testing.assert_array_equal(m.cols.download(), sc)
+            assert m.data.download().tobytes() == sd.astype(dtype).tobytes()
+            yd = ctx.array(np.full(n_rows, np.nan, dtype))
+            m.spmv(ctx.array(x.astype(dtype)), yd)
+            check_y(f"sell-sigma{sigma}", yd.download(), y_ref, dtype)
+    if sigma == 1:
+        ri, _, _ = O.build_sell(n_rows, rows, cols, vals)
+        np.testing.assert_array_equal(sp, ri.astype(np.int64))
+    else:
+        # sorting can only shrink the padded size
+        assert sp[-1] <= O.build_sell_sigma(n_rows, rows, cols, vals, 1)[1][-1]
+
+
+def test_full_cant_shape(ctx, cant_dir):
+    """BASELINE config 2: all five formats on the 62 451-row cant-shaped stand-in, x = ramp; COO from
+    the column-major file (coo.c:43), the others from the row-sorted one (csr.c:43)."""
+    n_rows, n_cols, rows, cols, vals = O.read_mtx(cant_dir / "databases" / "cant-sorted.mtx")
+    n2, c2, rows_c, cols_c, vals_c = O.read_mtx(cant_dir / "databases" / "cant.mtx")
+    assert (n_rows, rows.size) == (62451, 4325625)
+    for dtype in (np.float64, np.float32):
+        coo_s = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+        order = np.lexsort((rows, cols))
+        assert np.array_equal(rows[order], rows_c) and np.array_equal(cols[order], cols_c)
+        m, y_ref = run_all_formats(ctx, n_rows, n_cols, rows, cols, vals, dtype, coo_order=order)
+        info = m["csr"].plan_info()
+        assert info.lanes_per_row == 32 and info.n_long_rows == 0 and info.max_len == 81
+
+
+def test_row_sharded_equals_unsharded(ctx):
+    """G row blocks run one after the other on one GPU give, row for row, the same bits
+    as the unsharded run (row-local kernels), with cut points aligned to lcm(32, 8)."""
+    n_rows, n_cols = 20000, 20000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 80, 51)
+    x = np.random.default_rng(9).uniform(-1, 1, n_cols)
+    lens = np.bincount(rows, minlength=n_rows)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    for dtype in (np.float64, np.float32):
+        xd = ctx.array(x.astype(dtype))
+        full = pkg.build_all(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals), dtype)
+        y_full = {}
+        for name, mat in full.items():
+            yd = ctx.zeros(n_rows, dtype)
+            mat.spmv(xd, yd)
+            y_full[name] = yd.download()
+        for G in (2, 4, 8):
+            cuts = pkg.partition_rows(ptr, G, align=32)
+            assert cuts[0] == 0 and cuts[-1] == n_rows and np.all(np.diff(cuts) > 0) and np.all(cuts[:-1] % 32 == 0)
+            nnz_per = np.diff(ptr[cuts])
+            assert nnz_per.max() <= 1.10 * nnz_per.mean()
+            parts = {k: [] for k in full}
+            for g in range(G):
+                r0, r1 = cuts[g], cuts[g + 1]
+                sel = slice(ptr[r0], ptr[r1])
+                shard = pkg.build_all(pkg.CooMatrix.from_host(ctx, r1 - r0, n_cols, rows[sel] - r0, cols[sel], vals[sel]), dtype,
+                                      ell=False)
+                # same global width for ELL so that rows see identical padding
+                shard["ell"] = pkg.EllMatrix(shard["csr"], dtype, row_size=full["ell"].row_size)
+                shard["ellcm"] = pkg.EllCmMatrix(shard["csr"], dtype, row_size=full["ell"].row_size)
+                for name, mat in shard.items():
+                    yd = ctx.zeros(r1 - r0, dtype)
+                    mat.spmv(xd, yd)
+                    parts[name].append(yd.download())
+            for name in full:
+                got = np.concatenate(parts[name])
+                if name == "coo":
+                    assert O.rel_maxnorm(got, y_full[name].astype(np.float64)) <= TOL[np.dtype(dtype)]
+                else:
+                    assert got.tobytes() == y_full[name].tobytes(), (name, G)
