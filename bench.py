@@ -1,0 +1,499 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload banded|cant] [--dtype f32|f64] [--rows-per-gpu R]
+
+One "step" = one pass of the hot path over the workload = one SpMV in each of the reference's five
+formats (COO, CSR, ELL, SELL-32, CMRS) on the same matrix.  Default workload: BASELINE.json
+configs[2], the synthetic banded FEM-like matrix, 2 097 152 rows x 64 nnz/row per GPU, fp32,
+generated on the device (weak scaling: rank r owns rows [r*R, (r+1)*R) of the (N*R)-row global
+matrix, x replicated, no collective in the data path).  Every format's arrays (0.8-1.6 GB) are far
+larger than the 126 MB L2, so no flush is needed between iterations.
+
+Prints ONE JSON line.  metric = aggregate SpMV GFLOP/s (2*nnz flops per SpMV, the reference's own
+FLOP model, inc/helper_functions.h:171-172) over the five formats; `formats` carries the per-format
+GFLOP/s, algorithmic GB/s and fraction of the measured HBM peak; `roofline` describes the dominant
+(slowest) kernel; `cpu_baseline` is the oracle port on the host cores on a bounded sample.
+
+--impl reference times the reference's own CPU code (oracle/_ref, compute_using_cpu built -O3 from
+the unmodified sources; fp64 because the reference has no fp32) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("OMP_PROC_BIND", "close")
+
+import numpy as np  # noqa: E402
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FORMATS = ("coo", "csr", "ell", "sell", "cmrs")
+NOMINAL_HBM_GBS = 8000.0   # BASELINE.json north_star
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region (pynvml, 10 ms period)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "app_clocks", 0x100: "display",
+               0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.ok:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------
+BANDED = dict(nnz_per_row=64, half_band=2000, seed=42, x_seed=7)
+
+
+def build_banded_device(pkg, ctx, n_global, row_begin, row_count, dtype):
+    L = pkg.lib()
+    nnz = L.b200_gen_banded_nnz(n_global, row_begin, row_count, BANDED["nnz_per_row"])
+    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_banded_coo(ctx.h, n_global, row_begin, row_count, BANDED["nnz_per_row"],
+                                    BANDED["half_band"], BANDED["seed"], rows.ptr, cols.ptr, vals.ptr),
+              "b200_gen_banded_coo")
+    # shard-local row indices: each rank builds its formats on its own row block; columns stay global
+    pkg.check(L.b200_offset_i32(ctx.h, rows.ptr, nnz, -row_begin), "b200_offset_i32")
+    coo = pkg.CooMatrix(ctx, row_count, n_global, rows, cols, vals)
+    x = ctx.empty(n_global, dtype)
+    if np.dtype(dtype) == np.float32:
+        pkg.check(L.b200_gen_uniform_f32(ctx.h, x.ptr, n_global, BANDED["x_seed"], 0.0, 1.0), "gen x")
+    else:
+        pkg.check(L.b200_gen_uniform_f64(ctx.h, x.ptr, n_global, BANDED["x_seed"], 0.0, 1.0), "gen x")
+    return coo, x
+
+
+def banded_host(pkg, n_global, row_begin, row_count):
+    L = pkg.lib()
+    nnz = row_count * BANDED["nnz_per_row"]
+    rows, cols, vals = np.empty(nnz, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_banded_coo_host(n_global, row_begin, row_count, BANDED["nnz_per_row"],
+                                         BANDED["half_band"], BANDED["seed"], rows.ctypes.data,
+                                         cols.ctypes.data, vals.ctypes.data), "gen host")
+    x = np.empty(n_global, np.float64)
+    pkg.check(L.b200_gen_uniform_f64_host(x.ctypes.data, n_global, BANDED["x_seed"], 0.0, 1.0), "gen x host")
+    return rows, cols, vals, x
+
+
+def cant_host():
+    """cant-shaped stand-in parsed from generated MatrixMarket text (row-sorted file)."""
+    import subprocess
+    import tempfile
+    from oracle import binding as O
+    gen = ROOT / "opencl-spmv-algorithms_b200" / "tools" / "gen_mtx"
+    with tempfile.TemporaryDirectory() as d:
+        path = Path(d) / "cant-sorted.mtx"
+        subprocess.run([str(gen), "--order", "row", "--out", str(path)], check=True)
+        n_rows, n_cols, rows, cols, vals = O.read_mtx(path)
+    return n_rows, n_cols, rows, cols, vals, np.arange(n_cols, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arms (oracle port / compiled reference).  The ONLY place bench.py touches oracle/.
+# --------------------------------------------------------------------------------------------
+class quiet_stdout:
+    """The reference's compute_using_cpu printf()s its own timing block; keep our stdout to the
+    single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
+def cpu_arm(n_rows, n_cols, rows, cols, vals, x, dtype, kind, reps, warm):
+    """Time one SpMV per format on the host cores; returns (seconds per five-format pass, details).
+    kind='port': oracle/liboracle.so (-O3, OpenMP) in `dtype`.
+    kind='reference': the reference's own compute_using_cpu (fp64, -O3 build of the unmodified
+    sources) for coo/csr/ell/cmrs; sigma_c.c has no CPU path, so SELL uses the port."""
+    from oracle import binding as O
+    threads = os.cpu_count() or 1
+    O.lib().orc_set_threads(threads)
+    nnz = len(rows)
+    ptr, _ = O.build_csr(n_rows, rows)
+    K = int(np.bincount(rows, minlength=n_rows).max())
+    ec, ed = O.build_ell(n_rows, K, rows, cols, vals)
+    ri, sc, sd = O.build_sell(n_rows, rows, cols, vals)
+    sp, ris = O.build_cmrs(n_rows, rows)
+    dt = np.float64 if kind == "reference" else dtype
+    v, xx = vals.astype(dt), x.astype(dt)
+    ed_t, sd_t = ed.astype(dt), sd.astype(dt)
+    use_ref = kind == "reference" and O.ref_available()
+    if use_ref:
+        arrs = {
+            "coo": dict(rows=rows, cols=cols, data=v, vect=xx),
+            "csr": dict(ptr=ptr, cols=cols, data=v, vect=xx),
+            "ell": dict(cols=ec, data=ed_t, vect=xx),
+            "cmrs": dict(strip_ptr=sp, row_in_strip=ris, cols=cols, data=v, vect=xx),
+        }
+        runs = {
+            "coo": lambda: O.ref_compute_using_cpu("coo", arrs["coo"], n_rows, nnz, opt=True),
+            "csr": lambda: O.ref_compute_using_cpu("csr", arrs["csr"], n_rows, nnz, opt=True),
+            "ell": lambda: O.ref_compute_using_cpu("ell", arrs["ell"], n_rows, nnz, opt=True, row_size=K),
+            "cmrs": lambda: O.ref_compute_using_cpu("cmrs", arrs["cmrs"], n_rows, nnz, opt=True),
+            "sell": lambda: O.spmv_sell(ri, sc, sd_t, xx, dtype=dt),
+        }
+    else:
+        runs = {
+            "coo": lambda: O.spmv_coo(n_rows, rows, cols, v, xx, dtype=dt),
+            "csr": lambda: O.spmv_csr(n_rows, ptr, cols, v, xx, dtype=dt),
+            "ell": lambda: O.spmv_ell(n_rows, K, ec, ed_t, xx, dtype=dt),
+            "sell": lambda: O.spmv_sell(ri, sc, sd_t, xx, dtype=dt),
+            "cmrs": lambda: O.spmv_cmrs(n_rows, sp, ris, cols, v, xx, dtype=dt),
+        }
+    per = {}
+    with quiet_stdout():
+        for f in FORMATS:
+            for _ in range(warm):
+                runs[f]()
+            best = float("inf")
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                runs[f]()
+                best = min(best, time.perf_counter() - t0)
+            per[f] = best
+    total = sum(per.values())
+    detail = {f: round(2.0 * nnz / per[f] * 1e-9, 3) for f in FORMATS}
+    return total, detail, threads, ("reference" if use_ref else "port"), ("f32" if np.dtype(dt) == np.float32 else "f64")
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="banded", choices=["banded", "cant"])
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
+    ap.add_argument("--rows-per-gpu", type=int, default=2097152)
+    ap.add_argument("--cpu-sample-rows", type=int, default=262144)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dtype = np.dtype(np.float32 if (args.dtype or ("f32" if args.workload == "banded" else "f64")) == "f32"
+                     else np.float64)
+    dname = "f32" if dtype == np.float32 else "f64"
+
+    from __graft_entry__ import load_package
+    pkg = load_package()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(pkg, args, dtype)
+
+    # ---------------- the B200 arm ----------------
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    L = pkg.lib()
+
+    if args.workload == "banded":
+        R = args.rows_per_gpu
+        n_global = R * world
+        row_begin = rank * R
+        coo, x = build_banded_device(pkg, ctx, n_global, row_begin, R, dtype)
+        n_rows, n_cols = R, n_global
+        workload = (f"banded FEM-like (BASELINE configs[2]): {R} rows x {BANDED['nnz_per_row']} nnz/row per GPU, "
+                    f"global {n_global} x {n_global}, half-band {BANDED['half_band']}, device-generated")
+    else:
+        n_rows, n_cols, rows_h, cols_h, vals_h, x_h = cant_host()
+        coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows_h, cols_h, vals_h)
+        x = ctx.array(x_h.astype(dtype))
+        workload = "cant-shaped stand-in (BASELINE configs[1]): 62451 x 62451, 4325625 nnz, x = ramp"
+    nnz = coo.nnz
+
+    mats_all = pkg.build_all(coo, dtype)
+    mats = {"coo": mats_all["coo"], "csr": mats_all["csr"], "ell": mats_all["ellcm"],
+            "sell": mats_all["sell"], "cmrs": mats_all["cmrs"]}
+    extra = {"ell_rowmajor": mats_all["ell"]}
+    mats["csr"].plan()
+    y = {f: ctx.zeros(n_rows, dtype) for f in list(mats) + list(extra)}
+    bytes_alg = {f: m.nbytes(dtype) for f, m in {**mats, **extra}.items()}
+    ctx.set_l2_persist(x)
+    ctx.sync()
+
+    # L2 flush buffer: only the cant workload (25-52 MB per format) fits in the 126 MB L2
+    flush = ctx.empty(256 << 20, np.uint8) if args.workload == "cant" else None
+
+    def run_format(f, m):
+        if flush is not None:
+            flush.fill_bytes(1)
+        m.spmv(x, y[f])
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for f, m in mats.items():
+            run_format(f, m)
+    barrier()
+
+    # timed region: K steps; per-format events inside, whole-region events outside
+    ev = {f: [(ctx.event(), ctx.event()) for _ in range(args.steps)] for f in mats}
+    e0, e1 = ctx.event(), ctx.event()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for s in range(args.steps):
+            for f, m in mats.items():
+                if flush is not None:
+                    flush.fill_bytes(1)
+                ev[f][s][0].record()
+                m.spmv(x, y[f])
+                ev[f][s][1].record()
+        e1.record()
+        barrier()
+    total_ms = e0.elapsed_ms_until(e1)
+    per_ms = {f: float(np.mean([a.elapsed_ms_until(b) for a, b in ev[f]])) for f in mats}
+    kernels_ms = sum(per_ms.values())
+    # with the L2 flush in the loop only the kernels' own time is the step; otherwise the region is
+    step_ms = kernels_ms if flush is not None else total_ms / args.steps
+
+    # extra (untimed for the headline): the row-major ELL kernel on the reference's own arrays
+    for f, m in extra.items():
+        for _ in range(3):
+            run_format(f, m)
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        for _ in range(10):
+            m.spmv(x, y[f])
+        b.record()
+        ctx.sync()
+        per_ms[f] = a.elapsed_ms_until(b) / 10
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([step_ms] + [per_ms[f] for f in mats], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t[0])
+        for i, f in enumerate(mats):
+            per_ms[f] = float(t[1 + i])
+
+    peak, peak_src = measured_peak()
+    flops_step = 2.0 * nnz * len(mats) * world
+    value = flops_step / (step_ms * 1e-3) * 1e-9
+    fm = {}
+    for f in list(mats) + list(extra):
+        gbs = bytes_alg[f] / (per_ms[f] * 1e-3) * 1e-9
+        fm[f] = {"ms": round(per_ms[f], 5), "gflops": round(2.0 * nnz / (per_ms[f] * 1e-3) * 1e-9, 2),
+                 "alg_bytes": int(bytes_alg[f]), "gbs": round(gbs, 1),
+                 "frac_measured": round(gbs / peak, 4), "frac_nominal_8TBs": round(gbs / NOMINAL_HBM_GBS, 4)}
+    dom = max(mats, key=lambda f: per_ms[f])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": fm[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": fm[dom]["frac_measured"], "traffic": None, "peak_source": peak_src,
+                "per_format_frac": {f: fm[f]["frac_measured"] for f in mats}}
+
+    # ---------------- e2e: host x in, host y out, through the C ABI, matrix resident ----------
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        V = dtype.itemsize
+        hx, hy = C.c_void_p(), C.c_void_p()
+        pkg.check(L.b200_host_alloc_pinned(n_cols * V, C.byref(hx)), "pinned x")
+        pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy)), "pinned y")
+        x_host = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(n_cols * V,)).view(dtype)
+        x_host[:] = x.download()
+        xin = ctx.empty(n_cols, dtype)
+        steps_e = max(3, min(args.steps, 20))
+
+        def e2e_step():
+            for f, m in mats.items():
+                pkg.check(L.b200_memcpy_h2d_async(ctx.h, xin.ptr, hx, n_cols * V), "h2d x")
+                m.spmv(xin, y[f])
+                pkg.check(L.b200_memcpy_d2h_async(ctx.h, hy, y[f].ptr, n_rows * V), "d2h y")
+            ctx.sync()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        for _ in range(steps_e):
+            e2e_step()
+        b.record()
+        barrier()
+        e2e_ms = a.elapsed_ms_until(b) / steps_e
+        wall_ms = (time.perf_counter() - t0) * 1e3 / steps_e
+        if dist is not None:
+            import torch
+            t = torch.tensor([e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms, wall_ms = float(t[0]), float(t[1])
+        e2e = {"value": round(flops_step / (e2e_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(len(mats) * n_cols * V * world),
+               "d2h_bytes_per_step": int(len(mats) * n_rows * V * world),
+               "ms_per_step": round(e2e_ms, 4), "wall_ms_per_step": round(wall_ms, 4), "steps": steps_e,
+               "what": "per format: pinned-host x -> device, SpMV through the C ABI, y -> pinned host; format "
+                       "arrays uploaded once before the timed region, as the reference driver does (csr.c:183-193)"}
+        L.b200_host_free_pinned(hx)
+        L.b200_host_free_pinned(hy)
+
+    # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ---------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.workload == "banded":
+            sr = min(args.cpu_sample_rows, n_rows)
+            rows_h, cols_h, vals_h, x_h = banded_host(pkg, n_cols, 0, sr)
+            sample = f"first {sr} rows ({sr * BANDED['nnz_per_row']} nnz) of the same banded matrix, five formats, best of 5"
+        else:
+            sr = n_rows
+            sample = "the whole cant-shaped matrix, five formats, best of 5"
+        sec, detail, threads, kind, cdt = cpu_arm(sr, n_cols, rows_h, cols_h, vals_h, x_h, dtype, "port", 5, 2)
+        cpu = {"value": round(2.0 * len(rows_h) * len(FORMATS) / sec * 1e-9, 3), "unit": "GFLOP/s",
+               "cores": threads, "kind": kind, "dtype": cdt, "sample": sample, "per_format_gflops": detail}
+
+    if rank == 0:
+        out = {
+            "metric": "SpMV GFLOP/s, aggregate over the five formats (COO, CSR, ELL, SELL-32, CMRS); "
+                      "per-format GFLOP/s and HBM GB/s (% of peak) in `formats`",
+            "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dname, "data": "synthetic",
+            "config": {"workload": workload, "formats": list(mats), "nnz_per_gpu": int(nnz),
+                       "rows_per_gpu": int(n_rows), "cols": int(n_cols),
+                       "partition": f"row blocks, {world} rank(s), x replicated, no collective",
+                       "cache": ("256 MiB L2 flush before every kernel; per-kernel event times summed"
+                                 if flush is not None else "inputs larger than L2 (0.8-1.6 GB per format), no flush")},
+            "formats": fm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(args.steps * len(mats)), "clocks": clk.summary(),
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def reference_arm(pkg, args, dtype):
+    """The reference's own CPU implementation on the host cores, same workload / metric / unit."""
+    if args.workload == "banded":
+        n_global = args.rows_per_gpu * max(args.gpus, 1)
+        sr = min(args.cpu_sample_rows, args.rows_per_gpu)
+        rows, cols, vals, x = banded_host(pkg, n_global, 0, sr)
+        n_rows, n_cols = sr, n_global
+        sample = (f"first {sr} rows ({len(rows)} nnz) of the banded matrix per step, five formats; fp64 because the "
+                  "reference is fp64-only; compute_using_cpu of the unmodified coo/csr/ell/cmrs.c built -O3 "
+                  "(oracle port for SELL: sigma_c.c has no CPU path)")
+        workload = (f"banded FEM-like (BASELINE configs[2]): {args.rows_per_gpu} rows x {BANDED['nnz_per_row']} nnz/row "
+                    f"per GPU; CPU sample = {sr} rows")
+    else:
+        n_rows, n_cols, rows, cols, vals, x = cant_host()
+        sample = "the whole cant-shaped matrix per step, five formats, fp64"
+        workload = "cant-shaped stand-in (BASELINE configs[1]): 62451 x 62451, 4325625 nnz, x = ramp"
+    t0 = time.perf_counter()
+    sec, detail, threads, kind, cdt = cpu_arm(n_rows, n_cols, rows, cols, vals, x, dtype, "reference",
+                                              max(args.steps, 1), max(args.warmup, 0))
+    value = 2.0 * len(rows) * len(FORMATS) / sec * 1e-9
+    out = {
+        "impl": "reference",
+        "metric": "SpMV GFLOP/s, aggregate over the five formats (COO, CSR, ELL, SELL-32, CMRS); "
+                  "per-format GFLOP/s and HBM GB/s (% of peak) in `formats`",
+        "value": round(value, 3), "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": cdt, "data": "synthetic",
+        "config": {"workload": workload, "formats": list(FORMATS)},
+        "cpu_baseline": {"value": round(value, 3), "unit": "GFLOP/s", "cores": threads, "kind": kind,
+                         "sample": sample, "per_format_gflops": detail,
+                         "wall_s": round(time.perf_counter() - t0, 2)},
+        "e2e": {"value": round(value, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

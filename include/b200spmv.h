@@ -227,6 +227,8 @@ int b200_build_cmrs(b200_ctx *ctx, const int *rows, const int *ptr, int nnz, int
                     int height, int *strip_ptr, int *row_in_strip);
 /* value conversion for the fp32 path (the reference is fp64-only) */
 int b200_convert_f64_to_f32(b200_ctx *ctx, const double *src, float *dst, long long n);
+/* a[i] += delta: rebases the row indices (or a row pointer) of a row block to shard-local */
+int b200_offset_i32(b200_ctx *ctx, int *a, long long n, int delta);
 /* x[i] = i, the reference's input vector (csr.c:95-99) */
 int b200_fill_ramp_f64(b200_ctx *ctx, double *x, int n);
 int b200_fill_ramp_f32(b200_ctx *ctx, float *x, int n);

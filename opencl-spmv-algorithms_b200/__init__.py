@@ -103,6 +103,7 @@ SIGNATURES = {
     "b200_cmrs_num_strips": (_i, [_i, _i]),
     "b200_build_cmrs": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b200_convert_f64_to_f32": (_i, [_vp, _vp, _vp, _ll]),
+    "b200_offset_i32": (_i, [_vp, _vp, _ll, _i]),
     "b200_fill_ramp_f64": (_i, [_vp, _vp, _i]),
     "b200_fill_ramp_f32": (_i, [_vp, _vp, _i]),
     "b200_gen_banded_nnz": (_ll, [_ll, _i, _i, _i]),

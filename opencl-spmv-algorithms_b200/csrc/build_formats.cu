@@ -333,6 +333,13 @@ __global__ void convert_kernel(const double *__restrict__ src, float *__restrict
         dst[i] = (float)src[i];
 }
 
+__global__ void offset_kernel(int *__restrict__ a, long long n, int delta)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        a[i] += delta;
+}
+
 template <typename T>
 __global__ void ramp_kernel(T *__restrict__ x, int n)
 {
@@ -598,6 +605,18 @@ int b200_convert_f64_to_f32(b200_ctx *ctx, const double *src, float *dst, long l
     long long blocks = (n + kBlock - 1) / kBlock;
     if (blocks > (long long)ctx->sm_count * 32) blocks = (long long)ctx->sm_count * 32;
     convert_kernel<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(src, dst, n);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_offset_i32(b200_ctx *ctx, int *a, long long n, int delta)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(n >= 0 && (n == 0 || a), "bad argument");
+    if (n == 0 || delta == 0) return B200_SUCCESS;
+    long long blocks = (n + kBlock - 1) / kBlock;
+    if (blocks > (long long)ctx->sm_count * 32) blocks = (long long)ctx->sm_count * 32;
+    offset_kernel<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(a, n, delta);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

@@ -275,8 +275,8 @@ def test_full_cant_shape(ctx, cant_dir):
 
 
 def test_row_sharded_equals_unsharded(ctx):
-    """G row blocks run one after the other on one GPU give, row for row, the same bits
-    as the unsharded run (row-local kernels), with cut points aligned to lcm(32, 8)."""
+    """G row blocks run one after the other on one GPU reproduce the unsharded run row for
+    row (bit-identical for the alignment-independent kernels), cut points aligned to lcm(32, 8)."""
     n_rows, n_cols = 20000, 20000
     rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 80, 51)
     x = np.random.default_rng(9).uniform(-1, 1, n_cols)
@@ -310,7 +310,10 @@ def test_row_sharded_equals_unsharded(ctx):
                     parts[name].append(yd.download())
             for name in full:
                 got = np.concatenate(parts[name])
-                if name == "coo":
-                    assert O.rel_maxnorm(got, y_full[name].astype(np.float64)) <= TOL[np.dtype(dtype)]
-                else:
+                if name in ("ell", "ellcm", "sell"):
+                    # row-local AND alignment-independent (r0 % 32 == 0): identical bits
                     assert got.tobytes() == y_full[name].tobytes(), (name, G)
+                else:
+                    # csr/cmrs group entries by 16-byte alignment of the (rebased) entry index and
+                    # coo uses atomics: same values up to summation order
+                    assert O.rel_maxnorm(got, y_full[name].astype(np.float64)) <= TOL[np.dtype(dtype)]
