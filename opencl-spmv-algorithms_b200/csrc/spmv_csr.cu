@@ -12,6 +12,8 @@
 //     per block);
 //   * reduction is __shfl_xor_sync only -- no shared memory, no barriers.
 // HBM-bound: algorithmic bytes = nnz*(4+V) + (R+1)*4 + Cn*V + R*V.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -171,11 +173,21 @@ __global__ void csr_collect_long_kernel(const int *__restrict__ ptr, int n_rows,
     }
 }
 
-int pick_lanes(double mean_len)
+int pick_lanes(double mean_len, const char *override_env)
 {
-    // one 128-bit load (4 entries) per lane covers the mean row
+    // Measured on B200 (profiles/r1_lanes_sweep.md): the kernel is bound by L1 wavefronts of the x
+    // gather, not by the matrix loads.  Fewer lanes per row put more ADJACENT rows in one warp, and
+    // adjacent rows gather neighbouring x entries, so the sweet spot is ~4 vector iterations
+    // (16 entries) per lane -- but never 2 lanes on multi-iteration rows, whose 32-byte row
+    // segments would uncoalesce the matrix loads themselves.
     int lanes = 2;
-    while (lanes < 32 && lanes * 4 < mean_len) lanes <<= 1;
+    while (lanes < 32 && lanes * 16 < mean_len) lanes <<= 1;
+    if (lanes == 2 && mean_len > 8.0) lanes = 4;
+    // tuning hook: B200_CSR_LANES / B200_ELL_LANES = 2,4,8,16,32 overrides the heuristic
+    if (const char *e = getenv(override_env)) {
+        const int v = atoi(e);
+        if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
+    }
     return lanes;
 }
 
@@ -209,9 +221,10 @@ int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
     in.n_rows = n_rows;
     in.nnz = (long long)first_last[1] - first_last[0];
     in.mean_len = n_rows > 0 ? (double)in.nnz / n_rows : 0.0;
-    in.lanes_per_row = pick_lanes(in.mean_len);
-    // a row is "long" when it would keep its lanes busy for more than 16 vector iterations
-    in.long_threshold = in.lanes_per_row * 4 * 16;
+    in.lanes_per_row = pick_lanes(in.mean_len, "B200_CSR_LANES");
+    // a row is "long" when it would keep its lanes busy for more than 64 vector iterations
+    // (and is worth a whole block): it goes to the block-per-row kernel instead
+    in.long_threshold = in.lanes_per_row * 4 * 64 > 1024 ? in.lanes_per_row * 4 * 64 : 1024;
     in.min_len = in.max_len = 0;
     in.n_long_rows = 0;
     if (n_rows > 0) {
@@ -344,7 +357,7 @@ int spmv_ell_impl(b200_ctx *ctx, const T *data, const int *col, const T *x, T *y
     if (n_rows == 0) return B200_SUCCESS;
     B200_REQUIRE(row_size == 0 || (data && col), "null data/indices");
     const bool vec = aligned16(col) && aligned16(data);
-    switch (pick_lanes((double)row_size)) {
+    switch (pick_lanes((double)row_size, "B200_ELL_LANES")) {
     case 2: return launch_ell_lpr<T, 2>(ctx, data, col, x, y, n_rows, row_size, vec);
     case 4: return launch_ell_lpr<T, 4>(ctx, data, col, x, y, n_rows, row_size, vec);
     case 8: return launch_ell_lpr<T, 8>(ctx, data, col, x, y, n_rows, row_size, vec);

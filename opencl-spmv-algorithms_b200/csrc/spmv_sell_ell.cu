@@ -77,14 +77,14 @@ sell32_scalar_kernel(const T *__restrict__ data, const int *__restrict__ idx, co
     if (r < n_out) y[perm ? perm[r] : r] = acc;
 }
 
-// column-major ELL: blockDim = (64 row-quads, KS column slices)
-template <typename T, int KS>
-__global__ void __launch_bounds__(64 * KS)
+// column-major ELL: blockDim = (BX row-quads, KS column slices)
+template <typename T, int KS, int BX>
+__global__ void __launch_bounds__(BX * KS)
 ellcm_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
              T *__restrict__ y, int n_rows, int row_size, int pitch)
 {
-    __shared__ T red[KS > 1 ? KS : 1][64][4];
-    const long long r0 = ((long long)blockIdx.x * 64 + threadIdx.x) * 4;
+    __shared__ T red[KS > 1 ? KS : 1][KS > 1 ? BX : 1][4];
+    const long long r0 = ((long long)blockIdx.x * BX + threadIdx.x) * 4;
     T acc[4] = {0, 0, 0, 0};
     if (r0 < pitch) {
 #pragma unroll 4
@@ -137,9 +137,11 @@ template <typename T, int KS>
 int launch_ellcm(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *y, int n_rows,
                  int row_size, int pitch)
 {
-    dim3 block(64, KS);
-    unsigned blocks = ceil_div_u(pitch / 4, 64);
-    ellcm_kernel<T, KS><<<blocks, block, 0, ctx->stream>>>(data, idx, x, y, n_rows, row_size, pitch);
+    // KS == 1 (enough rows): 256 row-quads per block = 4 KiB contiguous per column and array
+    constexpr int BX = KS == 1 ? 256 : 64;
+    dim3 block(BX, KS);
+    unsigned blocks = ceil_div_u(pitch / 4, BX);
+    ellcm_kernel<T, KS, BX><<<blocks, block, 0, ctx->stream>>>(data, idx, x, y, n_rows, row_size, pitch);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

@@ -1,0 +1,166 @@
+/*
+ * csr -- drop-in for the reference's ./bin/csr (csr.c): same flow, same stdout, same exit codes.
+ *
+ *   load databases/cant-sorted.mtx (MatrixMarket, via mmio)   csr.c:54-66
+ *   parse the triples                                         csr.c:77-83
+ *   x = ramp                                                  csr.c:95-99
+ *   context + buffers + uploads                               csr.c:107-193  -> b200_* C ABI
+ *   FORMAT BUILD on the GPU (row pointer)                     csr.c:72-91    -> b200_build_csr_ptr
+ *   timed launch                                              csr.c:198-209  -> b200_spmv_csr_*
+ *   read back, check_result                                   csr.c:220-236
+ *   "CPU calculations" block (OpenMP, as the reference)       csr.c:246-255,285-309
+ * With no arguments it behaves like the reference; optional flags are listed by --help.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "helper_functions.h"
+
+void compute_using_cpu(double *data, double *vect, int *ptr, int *cols, int number_of_rows,
+                       int number_of_nonzeroes, double **result);
+
+int main(int argc, char *argv[])
+{
+    driver_options opt;
+    if (driver_parse_args(argc, argv, "databases/cant-sorted.mtx", &opt)) return OtherError;
+
+    int number_of_devices = 0;
+    if (b200_get_device_count(&number_of_devices) != B200_SUCCESS) {
+        printf("No CUDA devices found\n");
+        return OpenCLDeviceError;
+    }
+    if (number_of_devices > DEVICES_DEFAULT_SIZE) number_of_devices = DEVICES_DEFAULT_SIZE;
+    if (opt.device >= number_of_devices) return OpenCLDeviceError;
+
+    int number_of_rows, number_of_columns, number_of_nonzeroes, i;
+    const char *filename = opt.matrix;
+
+    /* prepare data for calculations */
+    FILE *file = fopen(filename, "r");
+    if (file == NULL) {
+        perror(filename);
+        return FileError;
+    }
+    if (read_size_of_matrices_from_file(file, &number_of_rows, &number_of_columns, &number_of_nonzeroes) == false) {
+        fclose(file);
+        return FileError;
+    }
+    int *rows = (int *)malloc((size_t)number_of_nonzeroes * sizeof(int));
+    int *cols = (int *)malloc((size_t)number_of_nonzeroes * sizeof(int));
+    double *data = (double *)malloc((size_t)number_of_nonzeroes * sizeof(double));
+    int *ptr = (int *)malloc(((size_t)number_of_rows + 1) * sizeof(int));
+    if (!read_entries(file, number_of_nonzeroes, rows, cols, data)) {
+        fclose(file);
+        return FileError;
+    }
+    fclose(file);
+
+    double *vect = (double *)malloc(sizeof(double) * (size_t)number_of_columns);
+    for (i = 0; i < number_of_columns; ++i) vect[i] = i;
+    double *output = (double *)malloc(sizeof(double) * (size_t)number_of_rows);
+    double *output_cpu = (double *)calloc((size_t)number_of_rows, sizeof(double));
+
+    /* prepare the device: context, buffers, uploads, format build */
+    const size_t V = opt.use_f32 ? sizeof(float) : sizeof(double);
+    b200_ctx *ctx = NULL;
+    B200_TRY(b200_ctx_create(opt.device, &ctx));
+    void *buffer_row, *buffer_ptr, *buffer_col, *buffer_data64, *buffer_data, *buffer_vect, *buffer_output;
+    B200_TRY(b200_malloc(ctx, sizeof(int) * (size_t)number_of_nonzeroes, &buffer_row));
+    B200_TRY(b200_malloc(ctx, sizeof(int) * ((size_t)number_of_rows + 1), &buffer_ptr));
+    B200_TRY(b200_malloc(ctx, sizeof(int) * (size_t)number_of_nonzeroes, &buffer_col));
+    B200_TRY(b200_malloc(ctx, sizeof(double) * (size_t)number_of_nonzeroes, &buffer_data64));
+    B200_TRY(b200_malloc(ctx, V * (size_t)number_of_columns, &buffer_vect));
+    B200_TRY(b200_malloc(ctx, V * (size_t)number_of_rows, &buffer_output));
+    B200_TRY(b200_memcpy_h2d_async(ctx, buffer_row, rows, sizeof(int) * (size_t)number_of_nonzeroes));
+    B200_TRY(b200_memcpy_h2d_async(ctx, buffer_col, cols, sizeof(int) * (size_t)number_of_nonzeroes));
+    B200_TRY(b200_memcpy_h2d_async(ctx, buffer_data64, data, sizeof(double) * (size_t)number_of_nonzeroes));
+    buffer_data = buffer_data64;
+    if (opt.use_f32) {
+        B200_TRY(b200_malloc(ctx, sizeof(float) * (size_t)number_of_nonzeroes, &buffer_data));
+        B200_TRY(b200_convert_f64_to_f32(ctx, (const double *)buffer_data64, (float *)buffer_data, number_of_nonzeroes));
+        B200_TRY(b200_fill_ramp_f32(ctx, (float *)buffer_vect, number_of_columns));
+    } else {
+        B200_TRY(b200_memcpy_h2d_async(ctx, buffer_vect, vect, sizeof(double) * (size_t)number_of_columns));
+    }
+    B200_TRY(b200_check_sorted_rows(ctx, (const int *)buffer_row, number_of_nonzeroes, number_of_rows));
+    B200_TRY(b200_build_csr_ptr(ctx, (const int *)buffer_row, number_of_nonzeroes, number_of_rows, (int *)buffer_ptr));
+    b200_csr_plan *plan = NULL;
+    B200_TRY(b200_csr_plan_create(ctx, (const int *)buffer_ptr, number_of_rows, &plan));
+    B200_TRY(b200_sync(ctx));
+
+#define LAUNCH()                                                                                          \
+    (opt.use_f32 ? b200_spmv_csr_f32(ctx, (const int *)buffer_ptr, (const int *)buffer_col,               \
+                                     (const float *)buffer_data, (const float *)buffer_vect,              \
+                                     (float *)buffer_output, number_of_rows, plan)                        \
+                 : b200_spmv_csr_f64(ctx, (const int *)buffer_ptr, (const int *)buffer_col,               \
+                                     (const double *)buffer_data, (const double *)buffer_vect,            \
+                                     (double *)buffer_output, number_of_rows, plan))
+
+    /* run program: one untimed launch loads the module, then `reps` timed launches */
+    B200_TRY(LAUNCH());
+    B200_TRY(b200_sync(ctx));
+    double start = now_ms();
+    int error = B200_SUCCESS;
+    for (i = 0; i < opt.reps && error == B200_SUCCESS; ++i) error = LAUNCH();
+    if (error == B200_SUCCESS) error = b200_sync(ctx);
+    double ms = (now_ms() - start) / opt.reps;
+
+    calculate_and_print_performance(ms, number_of_nonzeroes);
+    calculate_and_print_speed(ms, number_of_nonzeroes);
+    if (error != B200_SUCCESS) return report_b200_error("b200_spmv_csr", error);
+
+    /* read output */
+    if (opt.use_f32) {
+        float *tmp = (float *)malloc(sizeof(float) * (size_t)number_of_rows);
+        B200_TRY(b200_memcpy_d2h(ctx, tmp, buffer_output, sizeof(float) * (size_t)number_of_rows));
+        for (i = 0; i < number_of_rows; ++i) output[i] = tmp[i];
+        free(tmp);
+    } else {
+        B200_TRY(b200_memcpy_d2h(ctx, output, buffer_output, sizeof(double) * (size_t)number_of_rows));
+    }
+    if (check_result(filename, vect, output) == true) printf("result is ok\n");
+    else printf("result is wrong\n");
+
+    /* CPU (reported baseline, as in the reference; uses the GPU-built row pointer) */
+    if (!opt.no_cpu) {
+        B200_TRY(b200_memcpy_d2h(ctx, ptr, buffer_ptr, sizeof(int) * ((size_t)number_of_rows + 1)));
+        compute_using_cpu(data, vect, ptr, cols, number_of_rows, number_of_nonzeroes, &output_cpu);
+        if (check_result(filename, vect, output_cpu) == true) printf("cpu result is ok\n");
+        else printf("cpu result is wrong\n");
+    }
+
+    /* release memory */
+    b200_csr_plan_destroy(plan);
+    if (buffer_data != buffer_data64) b200_free(ctx, buffer_data);
+    b200_free(ctx, buffer_row);
+    b200_free(ctx, buffer_ptr);
+    b200_free(ctx, buffer_col);
+    b200_free(ctx, buffer_data64);
+    b200_free(ctx, buffer_vect);
+    b200_free(ctx, buffer_output);
+    b200_ctx_destroy(ctx);
+    free(rows);
+    free(ptr);
+    free(cols);
+    free(data);
+    free(vect);
+    free(output);
+    free(output_cpu);
+    return Success;
+}
+
+void compute_using_cpu(double *data, double *vect, int *ptr, int *cols, int number_of_rows,
+                       int number_of_nonzeroes, double **result)
+{
+    double start = now_ms();
+#pragma omp parallel for
+    for (int row = 0; row < number_of_rows; ++row) {
+        double sum = 0.0;
+        for (int j = ptr[row]; j < ptr[row + 1]; ++j) sum += data[j] * vect[cols[j]];
+        (*result)[row] = sum;
+    }
+    double ms = now_ms() - start;
+    printf("\nCPU calculations\n");
+    calculate_and_print_performance(ms, number_of_nonzeroes);
+}

@@ -1,0 +1,269 @@
+/* driver_common.c -- definitions of the helpers declared in inc/helper_functions.h. */
+#define _POSIX_C_SOURCE 200809L
+#include "helper_functions.h"
+
+#include <errno.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static int g_value_bytes = 8;
+static double g_rel_tolerance = 1e-12;
+
+int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt)
+{
+    opt->matrix = default_matrix;
+    opt->use_f32 = 0;
+    opt->sigma = 1;
+    opt->reps = 1;
+    opt->device = 0;
+    opt->no_cpu = 0;
+    opt->rowmajor = 0;
+    for (int i = 1; i < argc; ++i) {
+        const char *a = argv[i];
+        const char *v = i + 1 < argc ? argv[i + 1] : NULL;
+        if (!strcmp(a, "--matrix") && v) opt->matrix = argv[++i];
+        else if (!strcmp(a, "--dtype") && v) {
+            ++i;
+            if (!strcmp(v, "f32")) opt->use_f32 = 1;
+            else if (!strcmp(v, "f64")) opt->use_f32 = 0;
+            else goto bad;
+        } else if (!strcmp(a, "--sigma") && v) opt->sigma = atoi(argv[++i]);
+        else if (!strcmp(a, "--reps") && v) opt->reps = atoi(argv[++i]);
+        else if (!strcmp(a, "--device") && v) opt->device = atoi(argv[++i]);
+        else if (!strcmp(a, "--no-cpu")) opt->no_cpu = 1;
+        else if (!strcmp(a, "--rowmajor")) opt->rowmajor = 1;
+        else goto bad;
+    }
+    if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0) goto bad;
+    set_value_bytes(opt->use_f32 ? 4 : 8);
+    set_check_tolerance(opt->use_f32 ? 1e-5 : 1e-12);
+    return 0;
+bad:
+    fprintf(stderr, "usage: %s [--matrix FILE.mtx] [--dtype f32|f64] [--sigma N] [--reps N] "
+                    "[--device D] [--no-cpu] [--rowmajor]\n", argv[0]);
+    return 1;
+}
+
+bool read_size_of_matrices_from_file(FILE *file, int *number_of_rows, int *number_of_columns,
+                                     int *number_of_nonzeroes)
+{
+    MM_typecode matcode;
+
+    if (file == NULL) return false;
+    if (mm_read_banner(file, &matcode) != 0) {
+        printf("Could not process Matrix Market banner.\n");
+        return false;
+    }
+    /* only complex matrices are refused; symmetry is read and ignored, as in the reference */
+    if (mm_is_complex(matcode) && mm_is_matrix(matcode) && mm_is_sparse(matcode)) {
+        char *name = mm_typecode_to_str(matcode);
+        printf("Sorry, this application does not support ");
+        printf("Market Market type: [%s]\n", name ? name : "?");
+        free(name);
+        return false;
+    }
+    return mm_read_mtx_crd_size(file, number_of_rows, number_of_columns, number_of_nonzeroes) == 0;
+}
+
+/* Entries are parsed from one in-memory copy of the rest of the file with strtol/strtod, which is
+ * what fscanf("%d %d %lg") does underneath, minus the per-call stdio overhead (the text parse is
+ * ~all of the reference's wall-clock). */
+bool read_entries(FILE *file, int number_of_nonzeroes, int *rows, int *cols, double *data)
+{
+    long here = ftell(file);
+    if (here < 0 || fseek(file, 0, SEEK_END) != 0) return false;
+    long end = ftell(file);
+    if (end < here || fseek(file, here, SEEK_SET) != 0) return false;
+    size_t len = (size_t)(end - here);
+    char *buf = (char *)malloc(len + 1);
+    if (!buf) return false;
+    if (fread(buf, 1, len, file) != len) {
+        free(buf);
+        return false;
+    }
+    buf[len] = '\0';
+    char *p = buf;
+    bool ok = true;
+    for (int i = 0; i < number_of_nonzeroes; ++i) {
+        char *q;
+        errno = 0;
+        long r = strtol(p, &q, 10);
+        if (q == p) { ok = false; break; }
+        p = q;
+        long c = strtol(p, &q, 10);
+        if (q == p) { ok = false; break; }
+        p = q;
+        double v = strtod(p, &q);
+        if (q == p) { ok = false; break; }
+        p = q;
+        rows[i] = (int)r - 1; /* adjust from 1-based to 0-based */
+        cols[i] = (int)c - 1;
+        data[i] = v;
+    }
+    free(buf);
+    return ok;
+}
+
+void set_value_bytes(int bytes) { g_value_bytes = bytes; }
+void set_check_tolerance(double relative_max_norm) { g_rel_tolerance = relative_max_norm; }
+
+void calculate_and_print_performance(double ms, int number_of_nonzeroes)
+{
+    printf("Your calculations took %.2lf ms to run.\n", ms);
+    printf("Number of operations %d, PERFORMANCE %lf GFlops\n", 2 * number_of_nonzeroes,
+           (2 * number_of_nonzeroes) / ms * 1e-6);
+}
+
+void calculate_and_print_speed(double ms, int number_of_nonzeroes)
+{
+    const double lo = (double)number_of_nonzeroes * g_value_bytes;
+    const double hi = 2.0 * number_of_nonzeroes * g_value_bytes;
+    printf("GBytes transferred to processor %lf - %lf, speed %lf - %lf GB/s\n", lo * 1e-9, hi * 1e-9,
+           lo / ms * 1e-6, hi / ms * 1e-6);
+}
+
+bool check_result(const char *filename, double *vect, double *result)
+{
+    int number_of_rows, number_of_columns, number_of_nonzeroes;
+    FILE *file = fopen(filename, "r");
+    if (file == NULL) {
+        perror(filename);
+        return false;
+    }
+    if (!read_size_of_matrices_from_file(file, &number_of_rows, &number_of_columns, &number_of_nonzeroes)) {
+        fclose(file);
+        return false;
+    }
+    int *rows = (int *)malloc(sizeof(int) * (size_t)number_of_nonzeroes);
+    int *cols = (int *)malloc(sizeof(int) * (size_t)number_of_nonzeroes);
+    double *vals = (double *)malloc(sizeof(double) * (size_t)number_of_nonzeroes);
+    double *expect = (double *)calloc((size_t)number_of_rows, sizeof(double));
+    bool ok = rows && cols && vals && expect && read_entries(file, number_of_nonzeroes, rows, cols, vals);
+    fclose(file);
+    if (ok) {
+        for (int i = 0; i < number_of_nonzeroes; ++i) expect[rows[i]] += vals[i] * vect[cols[i]];
+        double worst = 0.0, scale = 0.0;
+        int first_bad = -1, nan_seen = 0;
+        for (int i = 0; i < number_of_rows; ++i) {
+            const double d = fabs(expect[i] - result[i]);
+            if (!(d <= EPSILON) && first_bad < 0) first_bad = i;
+            if (d != d) nan_seen = 1;
+            if (d > worst) worst = d;
+            if (fabs(expect[i]) > scale) scale = fabs(expect[i]);
+        }
+        const double rel = scale > 0.0 ? worst / scale : worst;
+        if (first_bad >= 0 && (nan_seen || rel > g_rel_tolerance)) {
+            printf("wrong value at index %d: expected %f - calculated %f\n", first_bad,
+                   expect[first_bad], result[first_bad]);
+            ok = false;
+        }
+    }
+    free(rows);
+    free(cols);
+    free(vals);
+    free(expect);
+    return ok;
+}
+
+double now_ms(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec * 1000.0 + (double)t.tv_nsec / 1000000.0;
+}
+
+int report_b200_error(const char *what, int status)
+{
+    printf("%s error %d\n", what, status);
+    fprintf(stderr, "%s: %s\n", b200_status_string(status), b200_last_error());
+    return status == B200_ERR_NO_DEVICE ? OpenCLDeviceError : OpenCLProgramError;
+}
+
+/* ---- shared prologue / epilogue of the drivers -------------------------------------------- */
+int driver_load_matrix(const driver_options *opt, host_matrix *m)
+{
+    int number_of_devices = 0;
+    memset(m, 0, sizeof *m);
+    if (b200_get_device_count(&number_of_devices) != B200_SUCCESS) {
+        printf("No CUDA devices found\n");
+        return OpenCLDeviceError;
+    }
+    if (number_of_devices > DEVICES_DEFAULT_SIZE) number_of_devices = DEVICES_DEFAULT_SIZE;
+    if (opt->device >= number_of_devices) return OpenCLDeviceError;
+
+    FILE *file = fopen(opt->matrix, "r");
+    if (file == NULL) {
+        perror(opt->matrix);
+        return FileError;
+    }
+    if (read_size_of_matrices_from_file(file, &m->n_rows, &m->n_cols, &m->nnz) == false) {
+        fclose(file);
+        return FileError;
+    }
+    m->rows = (int *)malloc((size_t)m->nnz * sizeof(int) + 16);
+    m->cols = (int *)malloc((size_t)m->nnz * sizeof(int) + 16);
+    m->data = (double *)malloc((size_t)m->nnz * sizeof(double) + 16);
+    m->vect = (double *)malloc((size_t)m->n_cols * sizeof(double) + 16);
+    if (!m->rows || !m->cols || !m->data || !m->vect ||
+        !read_entries(file, m->nnz, m->rows, m->cols, m->data)) {
+        fclose(file);
+        return FileError;
+    }
+    fclose(file);
+    for (int i = 0; i < m->n_cols; ++i) m->vect[i] = i; /* x = ramp, csr.c:95-99 */
+    return Success;
+}
+
+void driver_free_matrix(host_matrix *m)
+{
+    free(m->rows);
+    free(m->cols);
+    free(m->data);
+    free(m->vect);
+    memset(m, 0, sizeof *m);
+}
+
+int driver_upload_triples(b200_ctx *ctx, const host_matrix *m, int use_f32, device_triples *d)
+{
+    const size_t nnz = (size_t)m->nnz, V = use_f32 ? sizeof(float) : sizeof(double);
+    memset(d, 0, sizeof *d);
+    B200_TRY(b200_malloc(ctx, sizeof(int) * nnz, &d->rows));
+    B200_TRY(b200_malloc(ctx, sizeof(int) * nnz, &d->cols));
+    B200_TRY(b200_malloc(ctx, sizeof(double) * nnz, &d->data64));
+    B200_TRY(b200_malloc(ctx, V * (size_t)m->n_cols, &d->vect));
+    B200_TRY(b200_memcpy_h2d_async(ctx, d->rows, m->rows, sizeof(int) * nnz));
+    B200_TRY(b200_memcpy_h2d_async(ctx, d->cols, m->cols, sizeof(int) * nnz));
+    B200_TRY(b200_memcpy_h2d_async(ctx, d->data64, m->data, sizeof(double) * nnz));
+    if (use_f32) B200_TRY(b200_fill_ramp_f32(ctx, (float *)d->vect, m->n_cols));
+    else B200_TRY(b200_memcpy_h2d_async(ctx, d->vect, m->vect, sizeof(double) * (size_t)m->n_cols));
+    return Success;
+}
+
+void driver_free_triples(b200_ctx *ctx, device_triples *d)
+{
+    b200_free(ctx, d->rows);
+    b200_free(ctx, d->cols);
+    b200_free(ctx, d->data64);
+    b200_free(ctx, d->vect);
+    memset(d, 0, sizeof *d);
+}
+
+int driver_read_output(b200_ctx *ctx, const void *buffer_output, int n, int use_f32, double *output)
+{
+    if (use_f32) {
+        float *tmp = (float *)malloc(sizeof(float) * (size_t)n + 16);
+        if (!tmp) return OtherError;
+        int status = b200_memcpy_d2h(ctx, tmp, buffer_output, sizeof(float) * (size_t)n);
+        if (status != B200_SUCCESS) {
+            free(tmp);
+            return report_b200_error("b200_memcpy_d2h", status);
+        }
+        for (int i = 0; i < n; ++i) output[i] = tmp[i];
+        free(tmp);
+        return Success;
+    }
+    B200_TRY(b200_memcpy_d2h(ctx, output, buffer_output, sizeof(double) * (size_t)n));
+    return Success;
+}

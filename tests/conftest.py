@@ -20,6 +20,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests need a device: skip them (loudly) when there is none instead of failing."""
+    try:
+        from __graft_entry__ import load_package
+        import ctypes
+        n = ctypes.c_int(0)
+        have_gpu = load_package().lib().b200_get_device_count(ctypes.byref(n)) == 0 and n.value > 0
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (runs on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def gen_mtx_tool() -> Path:
     if not GEN.exists() or GEN.stat().st_mtime < (PKG / "tools" / "gen_mtx.c").stat().st_mtime:
         subprocess.run(["gcc", "-O2", "-o", str(GEN), str(PKG / "tools" / "gen_mtx.c")], check=True)

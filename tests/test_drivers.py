@@ -1,0 +1,104 @@
+"""The five C drivers (host/*.c -> bin/<format>): exit-code contract without a GPU (CPU test) and,
+on the GPU, the reference's stdout contract line by line next to the unmodified reference binary
+(oracle/_ref/bin/<format>, fake OpenCL) run in the same directory on the same files."""
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from conftest import ROOT
+from oracle import binding as O
+
+HOST = ROOT / "opencl-spmv-algorithms_b200" / "host"
+FORMATS = ("coo", "csr", "ell", "sigma_c", "cmrs")
+
+
+def build_drivers():
+    subprocess.run(["make", "-C", str(HOST), "all"], check=True, capture_output=True)
+    return HOST / "bin"
+
+
+def run(binary, cwd, *args):
+    return subprocess.run([str(binary), *args], cwd=cwd, capture_output=True, text=True, timeout=600)
+
+
+def test_drivers_build_with_reference_warning_flags():
+    bins = build_drivers()
+    for f in FORMATS:
+        assert (bins / f).exists()
+    flags = (HOST / "Makefile").read_text()
+    assert "-Wall -Werror -Wshadow" in flags and "-fopenmp" in flags   # reference Makefile:18
+
+
+def test_no_gpu_exit_code(tmp_path):
+    """Without a device every driver stops with OpenCLDeviceError (1), like the reference when
+    get_device_ids fails (csr.c:25-28) -- never a CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    bins = build_drivers()
+    for f in FORMATS:
+        p = run(bins / f, tmp_path)
+        assert p.returncode == 1, (f, p.stdout, p.stderr)
+        assert "CPU calculations" not in p.stdout
+    assert run(bins / "csr", tmp_path, "--bogus").returncode == 4      # OtherError
+
+
+TIMING = re.compile(r"^(Your calculations took|Number of operations \d+, PERFORMANCE|GBytes transferred)")
+
+
+def shape(stdout):
+    """stdout with the timing numbers blanked: what must match the reference byte for byte."""
+    out = []
+    for line in stdout.splitlines():
+        m = re.match(r"^(Number of operations \d+), PERFORMANCE", line)
+        if m:
+            out.append(m.group(1))
+        elif line.startswith("Your calculations took"):
+            out.append("Your calculations took")
+        elif line.startswith("GBytes transferred to processor"):
+            out.append(" ".join(line.split()[:7]))   # the two byte counts are deterministic
+        else:
+            out.append(line)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_driver_stdout_matches_reference(fem_small_dir, fmt):
+    bins = build_drivers()
+    ours = run(bins / fmt, fem_small_dir)
+    assert ours.returncode == 0, ours.stdout + ours.stderr
+    assert "result is ok" in ours.stdout and "result is wrong" not in ours.stdout
+    if fmt != "sigma_c":
+        assert "cpu result is ok" in ours.stdout
+    if not O.ref_available():
+        pytest.skip("oracle/_ref not built")
+    O.prepare_ref_workdir(fem_small_dir)
+    ref = run(O.REF_DIR / "bin" / fmt, fem_small_dir)
+    assert ref.returncode == 0
+    # the fake OpenCL runtime computes nothing, so the reference's GPU section says "wrong"
+    ref_lines = [l for l in shape(ref.stdout) if not l.startswith("wrong value at index")]
+    ref_lines = ["result is ok" if l == "result is wrong" else l for l in ref_lines]
+    assert shape(ours.stdout) == ref_lines
+
+
+@pytest.mark.gpu
+def test_driver_options_and_errors(fem_small_dir, tmp_path):
+    bins = build_drivers()
+    assert run(bins / "csr", tmp_path).returncode == 3                  # FileError: no databases/
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1 0\n")
+    assert run(bins / "csr", tmp_path, "--matrix", str(bad)).returncode == 3
+    mtx = str(fem_small_dir / "databases" / "cant-sorted.mtx")
+    for fmt in ("csr", "ell", "sigma_c", "cmrs"):
+        p = run(bins / fmt, tmp_path, "--matrix", mtx, "--dtype", "f32", "--reps", "3")
+        assert p.returncode == 0 and "result is ok" in p.stdout, (fmt, p.stdout, p.stderr)
+    p = run(bins / "coo", tmp_path, "--matrix", str(fem_small_dir / "databases" / "cant.mtx"), "--dtype", "f32")
+    assert p.returncode == 0 and "result is ok" in p.stdout
+    for sigma in ("32", "128", "1000"):
+        p = run(bins / "sigma_c", tmp_path, "--matrix", mtx, "--sigma", sigma)
+        assert p.returncode == 0 and "result is ok" in p.stdout, (sigma, p.stdout)
+    p = run(bins / "ell", tmp_path, "--matrix", mtx, "--rowmajor")
+    assert p.returncode == 0 and "result is ok" in p.stdout
