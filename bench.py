@@ -147,12 +147,18 @@ def cant_host():
     """cant-shaped stand-in parsed from generated MatrixMarket text (row-sorted file)."""
     import subprocess
     import tempfile
-    from oracle import binding as O
+    import pandas as pd
     gen = ROOT / "opencl-spmv-algorithms_b200" / "tools" / "gen_mtx"
     with tempfile.TemporaryDirectory() as d:
         path = Path(d) / "cant-sorted.mtx"
         subprocess.run([str(gen), "--order", "row", "--out", str(path)], check=True)
-        n_rows, n_cols, rows, cols, vals = O.read_mtx(path)
+        with open(path) as f:  # banner, one comment line, size line (tools/gen_mtx.c)
+            f.readline()
+            f.readline()
+            n_rows, n_cols, _ = (int(t) for t in f.readline().split())
+        t = pd.read_csv(path, sep=" ", skiprows=3, header=None, names=["r", "c", "v"],
+                        dtype={"r": np.int32, "c": np.int32, "v": np.float64})
+    rows, cols, vals = (t.r.values - 1).astype(np.int32), (t.c.values - 1).astype(np.int32), t.v.values
     return n_rows, n_cols, rows, cols, vals, np.arange(n_cols, dtype=np.float64)
 
 
@@ -240,7 +246,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="banded", choices=["banded", "cant"])
+    ap.add_argument("--workload", default="banded", choices=["banded", "cant", "laplace-iter"])
+    ap.add_argument("--grid", type=int, default=400, help="laplace-iter: nx = ny")
+    ap.add_argument("--nz-per-gpu", type=int, default=50, help="laplace-iter: z planes per rank")
+    ap.add_argument("--iter-format", default="csr", choices=["csr", "sell"])
     ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
     ap.add_argument("--rows-per-gpu", type=int, default=2097152)
     ap.add_argument("--cpu-sample-rows", type=int, default=262144)
@@ -263,6 +272,8 @@ def main():
         if rank != 0:
             return 0
         return reference_arm(pkg, args, dtype)
+    if args.workload == "laplace-iter":
+        return laplace_iter_arm(pkg, args, rank, world, local_rank)
 
     # ---------------- the B200 arm ----------------
     dist = None
@@ -455,6 +466,110 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+    return 0
+
+
+def laplace_iter_arm(pkg, args, rank, world, local_rank):
+    """BASELINE configs[4]: iterated SpMV (power iteration) on the 7-point Laplacian, fp64, rows
+    partitioned over the ranks, NCCL all-gather of x once per step.  Weak scaling: every rank owns
+    grid x grid x nz_per_gpu rows (400 x 400 x 50 = 8 M rows, 55.7 M nnz); 8 ranks = 400^3."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    L = pkg.lib()
+    nx = ny = args.grid
+    nz = args.nz_per_gpu * world
+    n = nx * ny * nz
+    blocks = pkg.equal_row_blocks(n, world, align=32)
+    lo, hi = blocks.bounds(rank)
+    n_local = hi - lo
+    nnz = L.b200_gen_laplace7_nnz(nx, ny, nz, lo, n_local)
+    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_laplace7_coo(ctx.h, nx, ny, nz, lo, n_local, rows.ptr, cols.ptr, vals.ptr), "gen laplace7")
+    pkg.check(L.b200_offset_i32(ctx.h, rows.ptr, nnz, -lo), "rebase rows")
+    coo = pkg.CooMatrix(ctx, n_local, n, rows, cols, vals)
+    fmt = args.iter_format
+    csr = pkg.CsrMatrix(coo)
+    mat = csr if fmt == "csr" else pkg.SellMatrix(csr, np.float64)
+    if fmt == "csr":
+        csr.plan()
+    x_cur = torch.zeros(blocks.padded, dtype=torch.float64, device="cuda")
+    x_next = torch.zeros_like(x_cur)
+    pkg.check(L.b200_gen_uniform_f64(ctx.h, x_cur.data_ptr(), n, 11, 0.0, 1.0), "gen x0")
+    calls = pkg.gpu_callables(pkg, ctx, mat, n_local)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    res = pkg.power_iteration(x_cur=x_cur, x_next=x_next, rank=rank, blocks=blocks, steps=args.warmup, **calls)
+    x_cur, x_next = (res.x, x_next if res.x is x_cur else x_cur)
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        sync_all()
+        t0.record()
+        res = pkg.power_iteration(x_cur=x_cur, x_next=x_next, rank=rank, blocks=blocks, steps=args.steps, **calls)
+        t1.record()
+        sync_all()
+    step_ms = t0.elapsed_time(t1) / args.steps
+
+    # split: SpMV alone and the all-gather alone, same buffers (explains the step time)
+    seg = x_next[rank * blocks.count:(rank + 1) * blocks.count]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        calls["spmv_local"](x_cur, seg)
+    b.record()
+    sync_all()
+    spmv_ms = a.elapsed_time(b) / 10
+    a.record()
+    for _ in range(10):
+        calls["all_gather_inplace"](x_next, seg)
+    b.record()
+    sync_all()
+    gather_ms = a.elapsed_time(b) / 10
+
+    t = torch.tensor([step_ms, spmv_ms, gather_ms, float(nnz)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        step_ms, spmv_ms, gather_ms, nnz_total = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tsum[3])
+    else:
+        nnz_total = float(nnz)
+    peak, peak_src = measured_peak()
+    alg = mat.nbytes(np.float64)
+    gbs = alg / (spmv_ms * 1e-3) * 1e-9
+    if rank == 0:
+        out = {
+            "metric": "SpMV GFLOP/s inside the power iteration (2*nnz flops per step; step = SpMV + "
+                      "norm all-reduce + scale + NCCL all-gather of x)",
+            "value": round(2.0 * nnz_total / (step_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 5),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"iterated SpMV (BASELINE configs[4]): 7-point Laplacian {nx}x{ny}x{nz} = {n} rows, "
+                                   f"{int(nnz_total)} nnz, fp64, {fmt.upper()}, {world} row block(s), NCCL all-gather of x per step",
+                       "rows_per_gpu": int(n_local), "nnz_per_gpu": int(nnz),
+                       "cache": "inputs larger than L2 (0.7 GB matrix + 2 x 64 MB x per GPU per world rank), no flush"},
+            "split_ms": {"spmv": round(spmv_ms, 5), "all_gather": round(gather_ms, 5),
+                         "other (sumsq, all-reduce, scale)": round(max(step_ms - spmv_ms - gather_ms, 0.0), 5)},
+            "eigenvalue_estimate": res.norm,
+            "roofline": {"bound": "hbm", "kernel": fmt, "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src},
+            "cpu_baseline": None, "e2e": None,
+            "gpu_launches": int(args.steps * 3), "clocks": clk.summary(),
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -166,6 +166,14 @@ class DeviceArray:
         self.ptr = p.value or 0
         self._p = p
 
+    @classmethod
+    def from_ptr(cls, ctx: "Context", ptr: int, n: int, dtype) -> "DeviceArray":
+        """Non-owning view of device memory allocated elsewhere (e.g. a torch tensor's data_ptr())."""
+        self = cls.__new__(cls)
+        self.ctx, self.n, self.dtype, self.ptr, self._p = ctx, int(n), np.dtype(dtype), int(ptr), None
+        self._borrowed = True
+        return self
+
     @property
     def nbytes(self) -> int:
         return self.n * self.dtype.itemsize
@@ -190,13 +198,13 @@ class DeviceArray:
         return self
 
     def free(self) -> None:
-        if self.ptr:
+        if self.ptr and not getattr(self, "_borrowed", False):
             check(lib().b200_free(self.ctx.h, self.ptr), "b200_free")
-            self.ptr = 0
+        self.ptr = 0
 
     def __del__(self):
         try:
-            if self.ptr and self.ctx.h:
+            if self.ptr and self.ctx.h and not getattr(self, "_borrowed", False):
                 lib().b200_free(self.ctx.h, self.ptr)
                 self.ptr = 0
         except Exception:
@@ -268,3 +276,4 @@ class Event:
 
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix,  # noqa: E402,F401
                       algorithmic_bytes, build_all, partition_rows)
+from .iterate import (RowBlocks, equal_row_blocks, gpu_callables, power_iteration)  # noqa: E402,F401

@@ -1,0 +1,143 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the N > 1 paths.
+
+(1) row partition + per-shard format builds: the shards of a row-partitioned matrix, each
+    multiplied by the replicated x on its own rank, reassemble to the unsharded result;
+(2) the iterated (power-iteration) mode: the same `power_iteration` step logic the GPU path runs,
+    here wired to numpy/gloo callables, must match a single-process run to rounding.
+
+The local SpMV in these tests is the CPU oracle -- allowed here because this is tests/; the
+product wiring (`gpu_callables`) uses only C-ABI kernels."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def laplace7(nx, ny, nz):
+    """Row-sorted triples of the 7-point Laplacian (x fastest): the host twin of
+    b200_gen_laplace7_coo, diag 6 / off-diag -1, columns ascending."""
+    n = nx * ny * nz
+    idx = np.arange(n)
+    x, y, z = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    parts = []
+    for cond, off in ((z > 0, -nx * ny), (y > 0, -nx), (x > 0, -1), (idx >= 0, 0), (x < nx - 1, 1),
+                      (y < ny - 1, nx), (z < nz - 1, nx * ny)):
+        r = idx[cond]
+        parts.append((r, r + off, np.full(r.size, 6.0 if off == 0 else -1.0)))
+    rows = np.concatenate([p[0] for p in parts])
+    cols = np.concatenate([p[1] for p in parts])
+    vals = np.concatenate([p[2] for p in parts])
+    order = np.lexsort((cols, rows))
+    return n, rows[order].astype(np.int32), cols[order].astype(np.int32), vals[order]
+
+
+def numpy_callables(O, ptr, cols, vals, n_local):
+    def spmv_local(x_full, seg):
+        seg[:n_local] = torch.from_numpy(O.spmv_csr(n_local, ptr, cols, vals, x_full.numpy()))
+
+    def sumsq(seg):
+        return (seg[:n_local] ** 2).sum().reshape(1)
+
+    def scale_inv_sqrt(seg, acc):
+        seg[:n_local] *= 1.0 / torch.sqrt(acc[0])
+
+    def all_reduce_sum(acc):
+        if dist.is_initialized():
+            dist.all_reduce(acc)
+
+    def all_gather_inplace(full, seg):
+        if dist.is_initialized():
+            dist.all_gather_into_tensor(full, seg.clone())
+
+    return dict(spmv_local=spmv_local, sumsq=sumsq, scale_inv_sqrt=scale_inv_sqrt,
+                all_reduce_sum=all_reduce_sum, all_gather_inplace=all_gather_inplace)
+
+
+def run_iteration(rank, world, grid, steps):
+    from __graft_entry__ import load_package
+    from oracle import binding as O
+    pkg = load_package()
+    n, rows, cols, vals = laplace7(*grid)
+    blocks = pkg.equal_row_blocks(n, world, align=32)
+    lo, hi = blocks.bounds(rank)
+    sel = (rows >= lo) & (rows < hi)
+    ptr, _ = O.build_csr(hi - lo, rows[sel] - lo) if hi > lo else (np.zeros(1, np.int32), 0)
+    O.lib().orc_set_threads(1)
+    x0 = np.zeros(blocks.padded)
+    x0[:n] = np.random.default_rng(1).uniform(0.0, 1.0, n)
+    x_cur, x_next = torch.from_numpy(x0.copy()), torch.zeros(blocks.padded, dtype=torch.float64)
+    res = pkg.power_iteration(x_cur=x_cur, x_next=x_next, rank=rank, blocks=blocks, steps=steps,
+                              **numpy_callables(O, ptr, cols[sel], vals[sel], hi - lo))
+    return res.norm, res.x.numpy()[:n].copy()
+
+
+def _worker(rank, world, port, grid, steps, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        norm, x = run_iteration(rank, world, grid, steps)
+        np.save(Path(out_dir) / f"x_{rank}.npy", x)
+        np.save(Path(out_dir) / f"norm_{rank}.npy", np.array([norm]))
+        # (1) single-shot sharded SpMV with replicated x, gathered for checking only
+        from __graft_entry__ import load_package
+        from oracle import binding as O
+        pkg = load_package()
+        from conftest import random_sorted_matrix
+        n_rows, n_cols = 4096, 4096
+        rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 50, 77)
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n_rows))]).astype(np.int32)
+        cuts = pkg.partition_rows(ptr, world, align=32)
+        r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+        sel = slice(ptr[r0], ptr[r1])
+        xv = np.arange(n_cols, dtype=np.float64)
+        lptr, _ = O.build_csr(r1 - r0, rows[sel] - r0)
+        y_local = torch.from_numpy(O.spmv_csr(r1 - r0, lptr, cols[sel], vals[sel], xv))
+        # nnz-balanced blocks have unequal row counts: pad to the largest for the gather
+        sizes = [int(cuts[g + 1] - cuts[g]) for g in range(world)]
+        padded = torch.zeros(max(sizes), dtype=torch.float64)
+        padded[:sizes[rank]] = y_local
+        outs = [torch.empty(max(sizes), dtype=torch.float64) for _ in sizes]
+        dist.all_gather(outs, padded)
+        if rank == 0:
+            y = torch.cat([o[:s] for o, s in zip(outs, sizes)]).numpy()
+            y_ref = O.yref(n_rows, rows, cols, vals, xv)
+            np.save(Path(out_dir) / "shard_err.npy", np.array([O.rel_maxnorm(y, y_ref)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_power_iteration_world2_matches_single_process(tmp_path):
+    grid, steps, world = (12, 10, 9), 25, 2
+    norm1, x1 = run_iteration(0, 1, grid, steps)
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, grid, steps, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        x = np.load(tmp_path / f"x_{r}.npy")
+        norm = float(np.load(tmp_path / f"norm_{r}.npy")[0])
+        assert abs(norm - norm1) <= 1e-12 * norm1
+        assert np.max(np.abs(x - x1)) <= 1e-12
+    assert abs(np.linalg.norm(x1) - 1.0) < 1e-12
+    # the estimate approaches the largest eigenvalue of the 7-point Laplacian from below (< 12)
+    assert 9.0 < norm1 < 12.0
+    assert float(np.load(tmp_path / "shard_err.npy")[0]) <= 1e-12
+
+
+def test_equal_row_blocks():
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    b = pkg.equal_row_blocks(64_000_000, 8)
+    assert b.count == 8_000_000 and b.padded == 64_000_000 and b.bounds(7) == (56_000_000, 64_000_000)
+    b = pkg.equal_row_blocks(1000, 3)
+    assert b.count % 32 == 0 and b.count * 3 >= 1000
+    assert [b.bounds(r) for r in range(3)] == [(0, 352), (352, 704), (704, 1000)]
+    b = pkg.equal_row_blocks(40, 4)       # more ranks than blocks of 32: trailing ranks own nothing
+    assert [b.bounds(r) for r in range(4)] == [(0, 32), (32, 40), (40, 40), (40, 40)]

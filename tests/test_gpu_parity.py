@@ -271,7 +271,8 @@ def test_full_cant_shape(ctx, cant_dir):
         assert np.array_equal(rows[order], rows_c) and np.array_equal(cols[order], cols_c)
         m, y_ref = run_all_formats(ctx, n_rows, n_cols, rows, cols, vals, dtype, coo_order=order)
         info = m["csr"].plan_info()
-        assert info.lanes_per_row == 32 and info.n_long_rows == 0 and info.max_len == 81
+        # mean row length 69.3 -> 8 lanes per row (~ 4 vector iterations per lane), no long rows
+        assert info.lanes_per_row == 8 and info.n_long_rows == 0 and info.max_len == 81
 
 
 def test_row_sharded_equals_unsharded(ctx):

@@ -1,0 +1,126 @@
+"""GPU: device generators against their host twins, the iterated mode on one GPU against a CPU
+power iteration, and -- at BASELINE.json's full banded size -- size-independent properties
+(cross-format agreement, linearity, sampled rows against the oracle)."""
+import numpy as np
+import pytest
+
+from __graft_entry__ import load_package
+from oracle import binding as O
+from test_distributed_cpu import laplace7
+
+pytestmark = pytest.mark.gpu
+pkg = load_package()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def test_banded_generator_device_equals_host(ctx):
+    L = pkg.lib()
+    n, npr, hb, seed = 50000, 64, 2000, 42
+    for r0, cnt in ((0, 3000), (20000, 4096), (47000, 3000)):
+        nnz = cnt * npr
+        rd, cd, vd = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+        pkg.check(L.b200_gen_banded_coo(ctx.h, n, r0, cnt, npr, hb, seed, rd.ptr, cd.ptr, vd.ptr), "gen")
+        rh, ch, vh = np.empty(nnz, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float64)
+        pkg.check(L.b200_gen_banded_coo_host(n, r0, cnt, npr, hb, seed, rh.ctypes.data, ch.ctypes.data,
+                                             vh.ctypes.data), "gen host")
+        assert np.array_equal(rd.download(), rh) and np.array_equal(cd.download(), ch)
+        assert vd.download().tobytes() == vh.tobytes()
+    xd = ctx.empty(100001, np.float64)
+    pkg.check(L.b200_gen_uniform_f64(ctx.h, xd.ptr, 100001, 7, 0.0, 1.0), "gen x")
+    xh = np.empty(100001)
+    pkg.check(L.b200_gen_uniform_f64_host(xh.ctypes.data, 100001, 7, 0.0, 1.0), "gen x host")
+    assert xd.download().tobytes() == xh.tobytes()
+    assert 0.0 <= xh.min() and xh.max() < 1.0 and abs(xh.mean() - 0.5) < 0.01
+
+
+def test_laplace7_generator(ctx):
+    L = pkg.lib()
+    nx, ny, nz = 13, 7, 9
+    n, rows, cols, vals = laplace7(nx, ny, nz)
+    assert L.b200_gen_laplace7_nnz(nx, ny, nz, 0, n) == rows.size == 7 * n - 2 * (nx * ny + ny * nz + nx * nz)
+    for r0, cnt in ((0, n), (100, 333), (n - 50, 50)):
+        sel = (rows >= r0) & (rows < r0 + cnt)
+        nnz = L.b200_gen_laplace7_nnz(nx, ny, nz, r0, cnt)
+        assert nnz == sel.sum()
+        rd, cd, vd = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+        pkg.check(L.b200_gen_laplace7_coo(ctx.h, nx, ny, nz, r0, cnt, rd.ptr, cd.ptr, vd.ptr), "gen")
+        assert np.array_equal(rd.download(), rows[sel]) and np.array_equal(cd.download(), cols[sel])
+        assert np.array_equal(vd.download(), vals[sel])
+
+
+def test_power_iteration_one_gpu_matches_cpu(ctx):
+    import torch
+    nx, ny, nz, steps = 24, 20, 18, 40
+    n, rows, cols, vals = laplace7(nx, ny, nz)
+    blocks = pkg.equal_row_blocks(n, 1)
+    x0 = np.zeros(blocks.padded)
+    x0[:n] = np.random.default_rng(1).uniform(0, 1, n)
+    # CPU power iteration with the oracle
+    ptr, _ = O.build_csr(n, rows)
+    x = x0[:n].copy()
+    for _ in range(steps):
+        y = O.spmv_csr(n, ptr, cols, vals, x)
+        nrm = np.linalg.norm(y)
+        x = y / nrm
+    tctx = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    coo = pkg.CooMatrix.from_host(tctx, n, n, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo)
+    for mat in (csr, pkg.SellMatrix(csr, np.float64)):
+        x_cur = torch.from_numpy(x0.copy()).cuda()
+        x_next = torch.zeros_like(x_cur)
+        res = pkg.power_iteration(x_cur=x_cur, x_next=x_next, rank=0, blocks=blocks, steps=steps,
+                                  **pkg.gpu_callables(pkg, tctx, mat, n))
+        torch.cuda.synchronize()
+        assert abs(res.norm - nrm) <= 1e-12 * nrm
+        assert np.max(np.abs(res.x.cpu().numpy()[:n] - x)) <= 1e-12
+    tctx.close()
+
+
+def test_full_size_banded_properties(ctx):
+    """BASELINE configs[2] at full size (2 097 152 rows x 64 nnz/row, fp32): too big for the CPU
+    oracle in seconds, so check (a) all six kernels agree with each other, (b) linearity
+    A(ax + bz) = aAx + bAz, (c) 4096 sampled rows against the oracle on the host twin."""
+    L = pkg.lib()
+    n, npr, hb, seed = 2097152, 64, 2000, 42
+    nnz = n * npr
+    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_banded_coo(ctx.h, n, 0, n, npr, hb, seed, rows.ptr, cols.ptr, vals.ptr), "gen")
+    coo = pkg.CooMatrix(ctx, n, n, rows, cols, vals)
+    dtype = np.float32
+    m = pkg.build_all(coo, dtype)
+    assert m["csr"].plan_info().lanes_per_row == 4 and m["ell"].row_size == 64
+    assert m["sell"].total == nnz and m["sell"].n_slices == n // 32
+    rng = np.random.default_rng(0)
+    xh, zh = rng.uniform(0, 1, n).astype(dtype), rng.uniform(-1, 1, n).astype(dtype)
+    x, z = ctx.array(xh), ctx.array(zh)
+    ys = {}
+    for name, mat in m.items():
+        yd = ctx.array(np.full(n, np.nan, dtype))
+        mat.spmv(x, yd)
+        ys[name] = yd.download().astype(np.float64)
+    scale = np.abs(ys["csr"]).max()
+    for name in ys:
+        assert np.max(np.abs(ys[name] - ys["csr"])) / scale <= 1e-5, name
+    # linearity on the SELL kernel
+    a, b = 0.75, -1.5
+    w = ctx.array((a * xh + b * zh).astype(dtype))
+    yz, yw = ctx.zeros(n, dtype), ctx.zeros(n, dtype)
+    m["sell"].spmv(z, yz)
+    m["sell"].spmv(w, yw)
+    lin = a * ys["sell"] + b * yz.download().astype(np.float64)
+    assert np.max(np.abs(yw.download() - lin)) / max(np.abs(lin).max(), 1e-30) <= 1e-5
+    # sampled row blocks against the oracle (host twin of the generator)
+    for r0 in (0, 1048576 - 512, n - 1024):
+        cnt = 1024
+        rh, ch, vh = np.empty(cnt * npr, np.int32), np.empty(cnt * npr, np.int32), np.empty(cnt * npr)
+        pkg.check(L.b200_gen_banded_coo_host(n, r0, cnt, npr, hb, seed, rh.ctypes.data, ch.ctypes.data,
+                                             vh.ctypes.data), "gen host")
+        y_ref = O.yref(cnt, rh - r0, ch, vh, xh.astype(np.float64))
+        for name in ys:
+            assert O.rel_maxnorm(ys[name][r0:r0 + cnt], y_ref) <= 1e-5, (name, r0)
