@@ -301,9 +301,11 @@ def main():
     nnz = coo.nnz
 
     mats_all = pkg.build_all(coo, dtype)
-    mats = {"coo": mats_all["coo"], "csr": mats_all["csr"], "ell": mats_all["ellcm"],
+    mats = {"coo": mats_all["coo"], "csr": mats_all["csr"], "ell": mats_all["ell"],
             "sell": mats_all["sell"], "cmrs": mats_all["cmrs"]}
-    extra = {"ell_rowmajor": mats_all["ell"]}
+    # "ell" = the kernel on the reference's row-major arrays (fastest ELL kernel on B200); the
+    # column-major thread-per-row kernel is measured next to it
+    extra = {"ell_colmajor": mats_all["ellcm"]}
     mats["csr"].plan()
     y = {f: ctx.zeros(n_rows, dtype) for f in list(mats) + list(extra)}
     bytes_alg = {f: m.nbytes(dtype) for f, m in {**mats, **extra}.items()}

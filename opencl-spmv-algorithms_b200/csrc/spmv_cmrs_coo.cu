@@ -1,72 +1,127 @@
 // spmv_cmrs_coo.cu -- CMRS and COO SpMV for sm_100a.
 //
-// CMRS replaces kernels/Cmrs.cl:1-46 (32-lane group per strip, a read-modify-write of local
-// memory per non-zero, 3 barriers per strip).  B200 design: one warp owns one strip (`height`
-// consecutive rows = one contiguous run of non-zeros).  Lanes stream the run with 128-bit loads
-// of values, column indices and row_in_strip; each lane keeps `height` private accumulators in
-// REGISTERS (selected by compare, no indexing), a transposing butterfly of __shfl_xor_sync folds
-// the 32 x height partials, and the strip's results are staged in shared memory so that a block
-// (8 strips = 64 rows at height 8) writes y as one coalesced run.
+// Both formats are "entries + a row key per entry" and share one structure, chosen from the B200
+// measurements in profiles/ (the x gather is bound by L1 wavefronts, so a warp should work on
+// ADJACENT rows, and every per-entry instruction counts):
 //
-// COO replaces kernels/Coo.cl:4-32 (one CAS-loop atomic per non-zero).  B200 design: each thread
-// takes four consecutive entries (128-bit loads of row, col, value), folds equal-row neighbours
-// locally, then a ballot-delimited segmented scan across the warp merges runs that span lanes;
-// only the last lane of each run issues a (native fp32/fp64) atomicAdd.  Row-sorted input costs
-// about one atomic per (warp, row); arbitrary order degrades gracefully to one per entry.
+//   * a warp owns one contiguous run of entries (CMRS: one strip of `height` rows; COO: 512
+//     entries) and splits it into 8 contiguous spans, one per 4-lane sub-warp.  A sub-warp reads
+//     its span with 128-bit loads (64 contiguous bytes per instruction and array), so a warp
+//     instruction covers 8 adjacent pieces of the matrix -- typically 8 adjacent rows, whose x
+//     entries are neighbours;
+//   * a lane keeps ONE running (row key, partial sum) pair in registers.  A group of four
+//     entries whose keys all equal the running key costs 4 FMAs (the common case on row-sorted
+//     data); only a key change flushes the pair;
+//   * CMRS flushes into `height` per-lane REGISTER accumulators selected by compare (the
+//     reference's per-entry read-modify-write of local memory, kernels/Cmrs.cl:18, was its
+//     bottleneck); a transposing butterfly of __shfl_xor_sync (7 + 2 shuffles for height 8)
+//     folds the 32 x height partials and lanes 0..height-1 store the strip's rows;
+//   * COO flushes interior runs with one native atomicAdd and merges the lanes' final runs with a
+//     ballot-delimited segmented warp scan, so row-sorted input costs about one atomic per
+//     (warp, row) and arbitrary order (the column-major cant.mtx of coo.c:43) degrades to one per
+//     entry.  Replaces the CAS-loop atomic per entry of kernels/Coo.cl:4-32.
 //
+// Any entry order inside a strip / the COO arrays is accepted; order only affects speed.
 // Bytes: nnz*(8+V) + (T+1)*4 + Cn*V + R*V (CMRS), nnz*(8+V) + Cn*V + R*V (COO); HBM-bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
+constexpr int kSubWarps = 8;      // 4-lane sub-warps per warp
+constexpr int kCooPerWarp = 512;  // COO entries per warp (64 per sub-warp, 4 groups per lane)
+
+template <typename T, int HMAX>
+__device__ __forceinline__ void cmrs_flush(T (&acc)[HMAX], int key, T sum)
+{
+#pragma unroll
+    for (int h = 0; h < HMAX; ++h) acc[h] += (key == h) ? sum : T(0);
+}
 
 // HMAX = accumulator registers per lane (8 or 32); height <= HMAX at run time
-template <typename T, int HMAX, bool VEC>
+template <typename T, int HMAX, bool VEC, int U>
 __global__ void __launch_bounds__(kBlock)
 cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *__restrict__ strip_ptr,
             const int *__restrict__ row_in_strip, const T *__restrict__ x, T *__restrict__ y,
             int n_strips, int height, int n_rows)
 {
-    __shared__ T stage[kWarps][HMAX];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long strip = (long long)blockIdx.x * kWarps + warp;
+    if (strip >= n_strips) return;  // whole warps leave together
     T acc[HMAX];
 #pragma unroll
     for (int h = 0; h < HMAX; ++h) acc[h] = 0;
-    if (strip < n_strips) {
-        const int s = __ldg(strip_ptr + strip), e = __ldg(strip_ptr + strip + 1);
-        if (VEC) {
-            const int g_end = (e + 3) >> 2;
-#pragma unroll 2
-            for (int g = (s >> 2) + lane; g < g_end; g += 32) {
-                const int j = g << 2;
-                IVec4 c, r;
-                Vec4<T> v;
-                c.load(idx + j);
-                r.load(row_in_strip + j);
-                v.load(data + j);
+
+    const int s = __ldg(strip_ptr + strip), e = __ldg(strip_ptr + strip + 1);
+    const int span = ((e - s + kSubWarps - 1) / kSubWarps + 3) & ~3;  // multiple of 4 entries
+    const int ss = min(s + (lane >> 2) * span, e), ee = min(ss + span, e);
+    int cur = -1;
+    T sum = 0;
+    if (VEC) {
+        // U groups per lane are loaded (3U independent 128-bit loads), then gathered (4U independent
+        // loads), then folded: two memory round trips per 16*U entries of the sub-warp
+        const int g_end = ss < ee ? (ee + 3) >> 2 : 0;
+        for (int g0 = (ss >> 2) + (lane & 3); g0 < g_end; g0 += 4 * U) {
+            IVec4 c[U], r[U];
+            Vec4<T> v[U];
+            T xv[U][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (j + k >= s && j + k < e) {
-                        const T p = v.v[k] * ld_x(x, c.v[k]);
+            for (int u = 0; u < U; ++u) {
+                const int j = (g0 + 4 * u) << 2;
+                if (g0 + 4 * u < g_end) {
+                    c[u].load(idx + j);
+                    r[u].load(row_in_strip + j);
+                    v[u].load(data + j);
+                }
+            }
 #pragma unroll
-                        for (int h = 0; h < HMAX; ++h) acc[h] += (r.v[k] == h) ? p : T(0);
+            for (int u = 0; u < U; ++u) {
+                const int j = (g0 + 4 * u) << 2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    xv[u][k] = (g0 + 4 * u < g_end && j + k >= ss && j + k < ee) ? ld_x(x, c[u].v[k]) : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = (g0 + 4 * u) << 2;
+                if (g0 + 4 * u >= g_end) break;
+                const bool whole = j >= ss && j + 3 < ee;
+                if (whole && r[u].v[0] == cur && r[u].v[1] == cur && r[u].v[2] == cur && r[u].v[3] == cur) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sum += v[u].v[k] * xv[u][k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (j + k >= ss && j + k < ee) {
+                            if (r[u].v[k] != cur) {
+                                cmrs_flush<T, HMAX>(acc, cur, sum);
+                                cur = r[u].v[k];
+                                sum = 0;
+                            }
+                            sum += v[u].v[k] * xv[u][k];
+                        }
                     }
                 }
             }
-        } else {
-            for (int j = s + lane; j < e; j += 32) {
-                const T p = ld_stream(data + j) * ld_x(x, ld_stream(idx + j));
-                const int r = ld_stream(row_in_strip + j);
-#pragma unroll
-                for (int h = 0; h < HMAX; ++h) acc[h] += (r == h) ? p : T(0);
+        }
+    } else {
+        for (int j = ss + (lane & 3); j < ee; j += 4) {
+            const int r = ld_stream(row_in_strip + j);
+            if (r != cur) {
+                cmrs_flush<T, HMAX>(acc, cur, sum);
+                cur = r;
+                sum = 0;
             }
+            sum += ld_stream(data + j) * ld_x(x, ld_stream(idx + j));
         }
     }
+    cmrs_flush<T, HMAX>(acc, cur, sum);
+
     // transposing butterfly: after the HMAX-halving steps lane L holds the partial of row
-    // (L % HMAX) over the lanes congruent to it; plain xor steps finish the sum.
+    // (L % HMAX) over the lanes of its HMAX-group; plain xor steps finish the sum.
 #pragma unroll
     for (int w = HMAX / 2; w >= 1; w >>= 1) {
         const bool upper = (lane & w) != 0;
@@ -80,64 +135,78 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
     T total = acc[0];
 #pragma unroll
     for (int off = HMAX; off < 32; off <<= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
-    // lane L (< HMAX) now owns row bitrev-free index: row = L's bits interpreted directly
-    if (lane < HMAX) stage[warp][lane] = total;
-    __syncthreads();
-    // coalesced store of the block's kWarps*height rows
-    const long long row0 = (long long)blockIdx.x * kWarps * height;
-    for (int t = threadIdx.x; t < kWarps * height; t += kBlock) {
-        const int w = t / height, h = t - w * height;
-        const long long row = row0 + t;
-        if ((long long)blockIdx.x * kWarps + w < n_strips && row < n_rows) y[row] = stage[w][h];
-    }
+    const long long row = strip * height + lane;
+    if (lane < height && row < n_rows) y[row] = total;
 }
 
-template <typename T>
+template <typename T, bool VEC, int U>
 __global__ void __launch_bounds__(kBlock)
 coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__restrict__ data,
-           const T *__restrict__ x, T *__restrict__ y, int nnz, bool vec)
+           const T *__restrict__ x, T *__restrict__ y, int nnz)
 {
     const int lane = threadIdx.x & 31;
-    const long long j0 = ((long long)blockIdx.x * kBlock + threadIdx.x) * 4;
-    int r[4], c[4];
-    T v[4];
-    if (vec && j0 < nnz) {
-        IVec4 rr, cc;
-        Vec4<T> vv;
-        rr.load(row + j0);
-        cc.load(col + j0);
-        vv.load(data + j0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            r[k] = rr.v[k];
-            c[k] = cc.v[k];
-            v[k] = vv.v[k];
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool in = j0 + k < nnz;
-            r[k] = in ? ld_stream(row + j0 + k) : -1;
-            c[k] = in ? ld_stream(col + j0 + k) : 0;
-            v[k] = in ? ld_stream(data + j0 + k) : T(0);
-        }
-    }
-    // thread-local fold; completed interior runs go straight to memory
+    const long long warp = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const long long ss = warp * kCooPerWarp + (lane >> 2) * (kCooPerWarp / kSubWarps);
+    const long long ee = min(ss + kCooPerWarp / kSubWarps, (long long)nnz);
     int cur = -1;
     T sum = 0;
+    if (VEC) {
+        // U of the lane's four groups are loaded together (3U independent 128-bit loads), then
+        // gathered (4U independent loads), then folded
+        constexpr int kGroups = kCooPerWarp / kSubWarps / 16;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (j0 + k >= nnz) break;
-        const T p = v[k] * ld_x(x, c[k]);
-        if (r[k] == cur) {
-            sum += p;
-        } else {
-            if (cur >= 0) atomicAdd(y + cur, sum);
-            cur = r[k];
-            sum = p;
+        for (int batch = 0; batch < kGroups / U; ++batch) {
+            const long long j0 = ss + ((lane & 3) << 2) + 16 * U * batch;
+            IVec4 r[U], c[U];
+            Vec4<T> v[U];
+            T xv[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long j = j0 + 16 * u;
+                if (j < ee) {
+                    r[u].load(row + j);
+                    c[u].load(col + j);
+                    v[u].load(data + j);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[u][k] = (j0 + 16 * u + k < ee) ? ld_x(x, c[u].v[k]) : T(0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long j = j0 + 16 * u;
+                if (j >= ee) break;
+                if (j + 3 < ee && r[u].v[0] == cur && r[u].v[1] == cur && r[u].v[2] == cur && r[u].v[3] == cur) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sum += v[u].v[k] * xv[u][k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (j + k < ee) {
+                            if (r[u].v[k] != cur) {
+                                if (cur >= 0) atomicAdd(y + cur, sum);
+                                cur = r[u].v[k];
+                                sum = 0;
+                            }
+                            sum += v[u].v[k] * xv[u][k];
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        for (long long j = ss + (lane & 3); j < ee; j += 4) {
+            const int r = ld_stream(row + j);
+            if (r != cur) {
+                if (cur >= 0) atomicAdd(y + cur, sum);
+                cur = r;
+                sum = 0;
+            }
+            sum += ld_stream(data + j) * ld_x(x, ld_stream(col + j));
         }
     }
-    // warp-level segmented inclusive scan over (cur, sum); heads delimit runs of equal rows
+    // warp-level segmented inclusive scan over the lanes' final (cur, sum); heads delimit runs
     const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
     const bool head = lane == 0 || prev != cur;
     const unsigned heads = __ballot_sync(0xffffffffu, head);
@@ -164,9 +233,21 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     if (n_strips == 0) return B200_SUCCESS;
     const bool vec = aligned16(data) && aligned16(idx) && aligned16(row_in_strip);
     unsigned blocks = ceil_div_u(n_strips, kWarps);
-#define B200_CMRS_LAUNCH(H, V)                                                                   \
-    cmrs_kernel<T, H, V><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, strip_ptr, row_in_strip, \
-                                                             x, y, n_strips, height, n_rows)
+    // U = groups loaded per lane and round trip.  Measured on B200 (profiles/): fp32 wants 2, fp64 1
+    // (register pressure); tuning hook B200_CMRS_U=1|2
+    int u = sizeof(T) == 4 ? 2 : 1;
+    if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
+#define B200_CMRS_LAUNCH(H, V)                                                                        \
+    do {                                                                                              \
+        if (u == 2)                                                                                   \
+            cmrs_kernel<T, H, V, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, strip_ptr,         \
+                                                                        row_in_strip, x, y, n_strips, \
+                                                                        height, n_rows);              \
+        else                                                                                          \
+            cmrs_kernel<T, H, V, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, strip_ptr,         \
+                                                                        row_in_strip, x, y, n_strips, \
+                                                                        height, n_rows);              \
+    } while (0)
     if (height <= 8) {
         if (vec) B200_CMRS_LAUNCH(8, true);
         else B200_CMRS_LAUNCH(8, false);
@@ -189,8 +270,14 @@ int spmv_coo_impl(b200_ctx *ctx, const int *row, const int *col, const T *data, 
     B200_CUDA(cudaMemsetAsync(y, 0, sizeof(T) * (size_t)n_rows, ctx->stream));
     if (nnz == 0) return B200_SUCCESS;
     const bool vec = aligned16(row) && aligned16(col) && aligned16(data);
-    unsigned blocks = ceil_div_u(((long long)nnz + 3) / 4, kBlock);
-    coo_kernel<T><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz, vec);
+    unsigned blocks = ceil_div_u(((long long)nnz + kCooPerWarp - 1) / kCooPerWarp, kWarps);
+    // U = groups loaded per lane and round trip (tuning hook B200_COO_U=1|2|4)
+    int u = 2;
+    if (const char *e = getenv("B200_COO_U")) u = atoi(e) == 4 ? 4 : (atoi(e) == 1 ? 1 : 2);
+    if (!vec) coo_kernel<T, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
+    else if (u == 4) coo_kernel<T, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
+    else if (u == 2) coo_kernel<T, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
+    else coo_kernel<T, true, 1><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

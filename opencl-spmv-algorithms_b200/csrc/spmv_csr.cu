@@ -117,6 +117,112 @@ csr_long_rows_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
     }
 }
 
+// ---- short rows: nnz-split "stream" kernel -------------------------------------------------
+// When the mean row has only a few entries, lanes-per-row kernels waste lanes and re-touch the
+// ragged 16-byte groups of neighbouring rows.  Here a block owns a fixed tile of kTile consecutive
+// ENTRIES instead: every thread loads one aligned group of four (perfectly coalesced, nothing
+// masked but the matrix tail), the products go to shared memory, and then one thread per row sums
+// that row's slice of the tile.  Rows [tile_lo[b], tile_lo[b+1]) START in tile b and are stored by
+// it (a partial sum if the row runs on into later tiles); the piece of a row that started in an
+// earlier tile is a carry, added by csr_stream_fixup_kernel afterwards (same stream, so ordered).
+// tile_lo[] is part of the plan (one binary search per tile, done once).
+constexpr int kTile = 1024;  // entries per 256-thread block
+
+__global__ void csr_tile_rows_kernel(const int *__restrict__ ptr, int n_rows, int n_tiles,
+                                     int *__restrict__ tile_lo)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_tiles) return;
+    if (b == n_tiles) {
+        tile_lo[b] = n_rows;  // the last tile also owns trailing empty rows
+        return;
+    }
+    const int e0 = b * kTile;
+    int lo = 0, hi = n_rows;  // smallest r in [0, n_rows] with ptr[r] >= e0
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (ptr[mid] < e0) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_lo[b] = lo;
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+csr_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ col, const T *__restrict__ data,
+                  const T *__restrict__ x, T *__restrict__ y, int nnz, const int *__restrict__ tile_lo,
+                  int *__restrict__ carry_row, T *__restrict__ carry_val)
+{
+    __shared__ T prod[kTile];
+    const int b = blockIdx.x;
+    const int e0 = b * kTile, e1 = min(e0 + kTile, nnz);
+    const int lo = __ldg(tile_lo + b), r_end = __ldg(tile_lo + b + 1);
+    const int j = e0 + 4 * threadIdx.x;
+    T p[4] = {0, 0, 0, 0};
+    if (j < e1) {
+        if (VEC) {
+            IVec4 c;
+            Vec4<T> v;
+            c.load(col + j);
+            v.load(data + j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (j + k < e1) p[k] = v.v[k] * ld_x(x, c.v[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (j + k < e1) p[k] = ld_stream(data + j + k) * ld_x(x, ld_stream(col + j + k));
+        }
+    }
+    // this thread's first row: pointers fetched before the barrier so the loads overlap the gather
+    int r = lo + threadIdx.x;
+    int s = 0, e = 0;
+    if (r < r_end) {
+        s = __ldg(ptr + r);
+        e = __ldg(ptr + r + 1);
+    }
+    const int first_start = __ldg(ptr + lo);  // lo <= n_rows: ptr has n_rows + 1 entries
+#pragma unroll
+    for (int k = 0; k < 4; ++k) prod[4 * threadIdx.x + k] = p[k];
+    __syncthreads();
+
+    // carry: entries [e0, first_start) belong to row lo-1, which started in an earlier tile
+    if (threadIdx.x < 32) {
+        const int c_end = min(first_start, e1) - e0;
+        if (c_end > 0) {
+            T part = 0;
+            for (int i = threadIdx.x; i < c_end; i += 32) part += prod[i];
+            part = subwarp_sum<32>(part);
+            if (threadIdx.x == 0) {
+                carry_row[b] = lo - 1;
+                carry_val[b] = part;
+            }
+        } else if (threadIdx.x == 0) {
+            carry_row[b] = -1;
+        }
+    }
+    // rows that start in this tile: one thread per row
+    while (r < r_end) {
+        const int stop = min(e, e1) - e0;
+        T acc = 0;
+        for (int i = s - e0; i < stop; ++i) acc += prod[i];
+        y[r] = acc;
+        r += kBlock;
+        if (r < r_end) {
+            s = __ldg(ptr + r);
+            e = __ldg(ptr + r + 1);
+        }
+    }
+}
+
+template <typename T>
+__global__ void csr_stream_fixup_kernel(T *__restrict__ y, int n_tiles, const int *__restrict__ carry_row,
+                                        const T *__restrict__ carry_val)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_tiles && carry_row[b] >= 0) atomicAdd(y + carry_row[b], carry_val[b]);
+}
+
 // row-major ELL (the reference's arrays): row r owns entries [r*K, (r+1)*K)
 template <typename T, int LPR, bool VEC>
 __global__ void __launch_bounds__(kBlock)
@@ -198,6 +304,10 @@ struct b200_csr_plan {
     int device;
     int n_split;      // blocks per long row
     int *long_rows;   // device list, n_long_rows entries
+    // stream (nnz-split) variant for short rows: info.stream_tiles > 0
+    int *tile_lo;     // stream_tiles + 1 entries
+    int *carry_row;   // stream_tiles entries
+    void *carry_val;  // stream_tiles x 8 bytes (T = float or double)
 };
 
 extern "C" {
@@ -216,8 +326,12 @@ int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
     b200_csr_plan *p = new b200_csr_plan();
     p->device = ctx->device;
     p->long_rows = nullptr;
+    p->tile_lo = nullptr;
+    p->carry_row = nullptr;
+    p->carry_val = nullptr;
     p->n_split = 1;
     b200_csr_plan_info &in = p->info;
+    in.stream_tiles = 0;
     in.n_rows = n_rows;
     in.nnz = (long long)first_last[1] - first_last[0];
     in.mean_len = n_rows > 0 ? (double)in.nnz / n_rows : 0.0;
@@ -256,6 +370,25 @@ int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
             long long split = ((long long)in.max_len + 65535) / 65536;
             p->n_split = (int)(split < 1 ? 1 : (split > 128 ? 128 : split));
         }
+        // short rows everywhere: the nnz-split stream kernel (B200_CSR_STREAM=0|1 overrides)
+        bool stream = in.mean_len <= 16.0 && in.max_len <= 256 && first_last[0] == 0 && in.nnz > 0 &&
+                      in.nnz < 0x7fffffffll - kTile;
+        if (const char *e = getenv("B200_CSR_STREAM"))
+            stream = atoi(e) != 0 && first_last[0] == 0 && in.nnz > 0 && in.max_len <= kTile;
+        if (stream) {
+            const int n_tiles = (int)((in.nnz + kTile - 1) / kTile);
+            cudaError_t e = cudaMalloc(&p->tile_lo, sizeof(int) * ((size_t)n_tiles + 1));
+            if (e == cudaSuccess) e = cudaMalloc(&p->carry_row, sizeof(int) * (size_t)n_tiles);
+            if (e == cudaSuccess) e = cudaMalloc(&p->carry_val, sizeof(double) * (size_t)n_tiles);
+            if (e != cudaSuccess) {
+                b200_csr_plan_destroy(p);
+                return b200_cuda_fail(e, "cudaMalloc(stream plan)", __FILE__, __LINE__);
+            }
+            csr_tile_rows_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, ctx->stream>>>(ptr, n_rows, n_tiles, p->tile_lo);
+            B200_LAUNCH_CHECK();
+            B200_CUDA(cudaStreamSynchronize(ctx->stream));
+            in.stream_tiles = n_tiles;
+        }
     }
     *plan = p;
     return B200_SUCCESS;
@@ -273,6 +406,9 @@ int b200_csr_plan_destroy(b200_csr_plan *plan)
     if (!plan) return B200_SUCCESS;
     cudaSetDevice(plan->device);
     if (plan->long_rows) cudaFree(plan->long_rows);
+    if (plan->tile_lo) cudaFree(plan->tile_lo);
+    if (plan->carry_row) cudaFree(plan->carry_row);
+    if (plan->carry_val) cudaFree(plan->carry_val);
     delete plan;
     return B200_SUCCESS;
 }
@@ -312,6 +448,24 @@ int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, 
     const bool vec = aligned16(col) && aligned16(data);
     const int thr = plan->info.long_threshold;
     int rc;
+    if (plan->info.stream_tiles > 0) {
+        const int n_tiles = plan->info.stream_tiles;
+        T *carry_val = static_cast<T *>(plan->carry_val);
+        if (vec)
+            csr_stream_kernel<T, true><<<n_tiles, kBlock, 0, ctx->stream>>>(
+                ptr, col, data, x, y, (int)plan->info.nnz, plan->tile_lo, plan->carry_row, carry_val);
+        else
+            csr_stream_kernel<T, false><<<n_tiles, kBlock, 0, ctx->stream>>>(
+                ptr, col, data, x, y, (int)plan->info.nnz, plan->tile_lo, plan->carry_row, carry_val);
+        csr_stream_fixup_kernel<T><<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(y, n_tiles, plan->carry_row, carry_val);
+        cudaError_t e = cudaGetLastError();
+        rc = e == cudaSuccess ? B200_SUCCESS : b200_cuda_fail(e, "csr_stream_kernel", __FILE__, __LINE__);
+        if (tmp) {
+            cudaStreamSynchronize(ctx->stream);
+            b200_csr_plan_destroy(tmp);
+        }
+        return rc;
+    }
     switch (plan->info.lanes_per_row) {
     case 2: rc = launch_csr_lpr<T, 2>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
     case 4: rc = launch_csr_lpr<T, 4>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;

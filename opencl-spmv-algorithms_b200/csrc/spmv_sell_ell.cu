@@ -12,6 +12,8 @@
 // 4t..4t+3 and walks the K columns (optionally split over KS thread-slices when the matrix has
 // too few rows to fill 148 SMs).  Bytes: P*(4+V) + (S+1)*P_bytes [+R*4 perm] + Cn*V + R*V for
 // SELL, R*K*(4+V) + Cn*V + R*V for ELL; both HBM-bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -77,39 +79,52 @@ sell32_scalar_kernel(const T *__restrict__ data, const int *__restrict__ idx, co
     if (r < n_out) y[perm ? perm[r] : r] = acc;
 }
 
-// column-major ELL: blockDim = (BX row-quads, KS column slices)
-template <typename T, int KS, int BX>
+// column-major ELL: blockDim = (BX threads, KS column slices); a thread owns Q quads of 4 rows,
+// quad q of thread t = rows 4*(q*BX + t) .. +3 of the block's BX*4*Q-row panel, so that a warp
+// instruction still reads 512 contiguous bytes and a block reads BX*16*Q contiguous bytes per
+// column and array (the column stride is pitch*4 bytes: fewer, longer DRAM bursts per column).
+template <typename T, int KS, int BX, int Q>
 __global__ void __launch_bounds__(BX * KS)
 ellcm_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
              T *__restrict__ y, int n_rows, int row_size, int pitch)
 {
-    __shared__ T red[KS > 1 ? KS : 1][KS > 1 ? BX : 1][4];
-    const long long r0 = ((long long)blockIdx.x * BX + threadIdx.x) * 4;
-    T acc[4] = {0, 0, 0, 0};
-    if (r0 < pitch) {
-#pragma unroll 4
-        for (int k = threadIdx.y; k < row_size; k += KS) {
-            IVec4 c;
-            Vec4<T> v;
-            c.load(idx + (long long)k * pitch + r0);
-            v.load(data + (long long)k * pitch + r0);
+    __shared__ T red[KS > 1 ? KS : 1][KS > 1 ? BX : 1][4 * Q];
+    const long long panel = (long long)blockIdx.x * BX * 4 * Q;
+    T acc[4 * Q];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += v.v[i] * ld_x(x, c.v[i]);
+    for (int i = 0; i < 4 * Q; ++i) acc[i] = 0;
+#pragma unroll 4
+    for (int k = threadIdx.y; k < row_size; k += KS) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const long long r0 = panel + ((long long)q * BX + threadIdx.x) * 4;
+            if (r0 < pitch) {
+                IVec4 c;
+                Vec4<T> v;
+                c.load(idx + (long long)k * pitch + r0);
+                v.load(data + (long long)k * pitch + r0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[4 * q + i] += v.v[i] * ld_x(x, c.v[i]);
+            }
         }
     }
     if (KS > 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) red[threadIdx.y][threadIdx.x][i] = acc[i];
+        for (int i = 0; i < 4 * Q; ++i) red[threadIdx.y][threadIdx.x][i] = acc[i];
         __syncthreads();
         if (threadIdx.y != 0) return;
 #pragma unroll
         for (int s = 1; s < KS; ++s)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += red[s][threadIdx.x][i];
+            for (int i = 0; i < 4 * Q; ++i) acc[i] += red[s][threadIdx.x][i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (r0 + i < n_rows) y[r0 + i] = acc[i];
+    for (int q = 0; q < Q; ++q) {
+        const long long r0 = panel + ((long long)q * BX + threadIdx.x) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r0 + i < n_rows) y[r0 + i] = acc[4 * q + i];
+    }
 }
 
 template <typename T, typename P>
@@ -137,11 +152,18 @@ template <typename T, int KS>
 int launch_ellcm(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *y, int n_rows,
                  int row_size, int pitch)
 {
-    // KS == 1 (enough rows): 256 row-quads per block = 4 KiB contiguous per column and array
+    // KS == 1 (enough rows): 256 threads x Q quads of rows.  Q = 2 (8 KiB contiguous per column
+    // and array in fp32) measured no better than Q = 1 on B200 (0.198 vs 0.192 ms on the banded
+    // workload); kept as a tuning hook: B200_ELLCM_Q=1|2
     constexpr int BX = KS == 1 ? 256 : 64;
     dim3 block(BX, KS);
-    unsigned blocks = ceil_div_u(pitch / 4, BX);
-    ellcm_kernel<T, KS, BX><<<blocks, block, 0, ctx->stream>>>(data, idx, x, y, n_rows, row_size, pitch);
+    int q = 1;
+    if (const char *e = getenv("B200_ELLCM_Q")) q = (KS == 1 && atoi(e) == 2) ? 2 : 1;
+    unsigned blocks = ceil_div_u(pitch / 4, BX * q);
+    if (q == 2)
+        ellcm_kernel<T, KS, BX, (KS == 1 ? 2 : 1)><<<blocks, block, 0, ctx->stream>>>(data, idx, x, y, n_rows, row_size, pitch);
+    else
+        ellcm_kernel<T, KS, BX, 1><<<blocks, block, 0, ctx->stream>>>(data, idx, x, y, n_rows, row_size, pitch);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

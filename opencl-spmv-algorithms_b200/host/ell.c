@@ -7,8 +7,9 @@
  *       reproduce that so the line is byte-identical)
  *   FORMAT BUILD on the GPU: K-padded ELL, padding (col 0, 0)   ell.c:118-164 -> b200_build_ell_*
  *   timed launch                                               ell.c:270-280 -> b200_spmv_ellcm_*
- *       default: the column-major coalesced kernel on the transposed device layout;
- *       --rowmajor: the kernel that consumes the reference's row-major arrays as they are
+ *       default (--rowmajor): the sub-warp-per-row kernel that consumes the reference's row-major
+ *       arrays as they are (the fastest ELL kernel measured on B200, profiles/);
+ *       --colmajor: the thread-per-row coalesced kernel on the transposed device layout
  *   read back, check_result, "CPU calculations" block          ell.c:290-330,357-383
  */
 #include <stdio.h>

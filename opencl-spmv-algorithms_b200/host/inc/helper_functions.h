@@ -33,7 +33,7 @@ typedef struct {
     int reps;           /* --reps N        timed launches, the mean is printed (default 1) */
     int device;         /* --device D */
     int no_cpu;         /* --no-cpu        skip the "CPU calculations" block */
-    int rowmajor;       /* --rowmajor      (ell only) run the kernel on the reference's row-major arrays */
+    int rowmajor;       /* --rowmajor (default) | --colmajor   (ell only) which ELL kernel/layout runs */
 } driver_options;
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt);

@@ -19,7 +19,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     opt->reps = 1;
     opt->device = 0;
     opt->no_cpu = 0;
-    opt->rowmajor = 0;
+    opt->rowmajor = 1;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
         const char *v = i + 1 < argc ? argv[i + 1] : NULL;
@@ -34,6 +34,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
         else if (!strcmp(a, "--device") && v) opt->device = atoi(argv[++i]);
         else if (!strcmp(a, "--no-cpu")) opt->no_cpu = 1;
         else if (!strcmp(a, "--rowmajor")) opt->rowmajor = 1;
+        else if (!strcmp(a, "--colmajor")) opt->rowmajor = 0;
         else goto bad;
     }
     if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0) goto bad;
@@ -42,7 +43,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     return 0;
 bad:
     fprintf(stderr, "usage: %s [--matrix FILE.mtx] [--dtype f32|f64] [--sigma N] [--reps N] "
-                    "[--device D] [--no-cpu] [--rowmajor]\n", argv[0]);
+                    "[--device D] [--no-cpu] [--rowmajor|--colmajor]\n", argv[0]);
     return 1;
 }
 

@@ -100,5 +100,6 @@ def test_driver_options_and_errors(fem_small_dir, tmp_path):
     for sigma in ("32", "128", "1000"):
         p = run(bins / "sigma_c", tmp_path, "--matrix", mtx, "--sigma", sigma)
         assert p.returncode == 0 and "result is ok" in p.stdout, (sigma, p.stdout)
-    p = run(bins / "ell", tmp_path, "--matrix", mtx, "--rowmajor")
-    assert p.returncode == 0 and "result is ok" in p.stdout
+    for layout in ("--rowmajor", "--colmajor"):
+        p = run(bins / "ell", tmp_path, "--matrix", mtx, layout)
+        assert p.returncode == 0 and "result is ok" in p.stdout, (layout, p.stdout)

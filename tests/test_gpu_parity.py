@@ -211,6 +211,44 @@ def test_unaligned_arrays_take_the_scalar_kernels(ctx, dtype):
     check_y("sell-unaligned", yd.download(), y_ref, dtype)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_csr_stream_kernel(ctx, dtype, monkeypatch):
+    """The nnz-split CSR kernel (short rows): chosen automatically for mean <= 16 / max <= 256, and
+    forced here on rows that span several 1024-entry tiles, with empty rows sitting exactly on tile
+    boundaries and at the end of the matrix."""
+    rng = np.random.default_rng(61)
+    x = rng.uniform(-1, 1, 3000)
+    # (a) automatic: 7-point-stencil-like rows
+    rows, cols, vals = random_sorted_matrix(20000, 3000, 1, 12, 62)
+    coo = pkg.CooMatrix.from_host(ctx, 20000, 3000, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo)
+    assert csr.plan_info().stream_tiles == -(-rows.size // 1024)
+    yd = ctx.array(np.full(20000, np.nan, dtype))
+    csr.spmv(ctx.array(x.astype(dtype)), yd)
+    check_y("csr-stream", yd.download(), O.yref(20000, rows, cols, vals, x), dtype)
+    # (b) forced: lengths chosen so that rows end exactly on tile boundaries, followed by empty rows,
+    # plus rows of 1000 entries that straddle two or three tiles
+    lens = np.array([1024, 0, 0, 500, 524, 0, 1000, 1000, 1000, 48, 0, 3, 1, 1020, 7, 0, 0])
+    assert np.cumsum(lens)[0] % 1024 == 0 and np.cumsum(lens)[4] % 1024 == 0
+    n_rows, n_cols = lens.size, 3000
+    rows = np.repeat(np.arange(n_rows, dtype=np.int32), lens)
+    cols = np.concatenate([np.sort(rng.choice(n_cols, int(k), replace=False)) for k in lens]).astype(np.int32)
+    vals = rng.uniform(-1, 1, rows.size)
+    monkeypatch.setenv("B200_CSR_STREAM", "1")
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo)
+    assert csr.plan_info().stream_tiles == -(-rows.size // 1024)
+    yd = ctx.array(np.full(n_rows, np.nan, dtype))
+    csr.spmv(ctx.array(x.astype(dtype)), yd)
+    check_y("csr-stream-forced", yd.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+    monkeypatch.setenv("B200_CSR_STREAM", "0")
+    csr2 = pkg.CsrMatrix(coo)
+    assert csr2.plan_info().stream_tiles == 0
+    y2 = ctx.array(np.full(n_rows, np.nan, dtype))
+    csr2.spmv(ctx.array(x.astype(dtype)), y2)
+    check_y("csr-vector", y2.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+
+
 @pytest.mark.parametrize("height", [1, 2, 5, 8, 16, 32])
 def test_cmrs_heights(ctx, height):
     n_rows, n_cols = 1234, 1500
