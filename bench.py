@@ -246,7 +246,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="banded", choices=["banded", "cant", "laplace-iter"])
+    ap.add_argument("--workload", default="banded", choices=["banded", "cant", "laplace-iter", "rmat"])
+    ap.add_argument("--rmat-scale", type=int, default=24)
+    ap.add_argument("--rmat-edge-factor", type=int, default=16)
+    ap.add_argument("--rmat-max-sell-bytes", type=float, default=24e9,
+                    help="rmat: skip running a SELL variant whose padded arrays exceed this")
     ap.add_argument("--grid", type=int, default=400, help="laplace-iter: nx = ny")
     ap.add_argument("--nz-per-gpu", type=int, default=50, help="laplace-iter: z planes per rank")
     ap.add_argument("--iter-format", default="csr", choices=["csr", "sell"])
@@ -274,6 +278,8 @@ def main():
         return reference_arm(pkg, args, dtype)
     if args.workload == "laplace-iter":
         return laplace_iter_arm(pkg, args, rank, world, local_rank)
+    if args.workload == "rmat":
+        return rmat_arm(pkg, args, rank, world, local_rank)
 
     # ---------------- the B200 arm ----------------
     dist = None
@@ -462,6 +468,162 @@ def main():
                                  if flush is not None else "inputs larger than L2 (0.8-1.6 GB per format), no flush")},
             "formats": fm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(args.steps * len(mats)), "clocks": clk.summary(),
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def rmat_arm(pkg, args, rank, world, local_rank):
+    """BASELINE configs[3]: power-law R-MAT (scale 24: 16.8 M rows, ~270 M nnz after duplicate
+    removal), fp32, CSR vs SELL-32-sigma sweep (+ COO, CMRS), rows partitioned nnz-balanced over the
+    ranks (STRONG scaling: the global matrix is fixed), x replicated, no collective."""
+    import ctypes as C
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    L = pkg.lib()
+    scale, ef, abc, seed = args.rmat_scale, args.rmat_edge_factor, (0.57, 0.19, 0.19), 5
+    n = 1 << scale
+    dtype = np.dtype(np.float32 if (args.dtype or "f32") == "f32" else np.float64)
+
+    def candidates(r0, cnt):
+        c = C.c_longlong(0)
+        pkg.check(L.b200_gen_rmat_count(ctx.h, scale, ef, *abc, seed, r0, cnt, C.byref(c)), "rmat count")
+        return c.value
+
+    # nnz-balanced cuts (multiples of 32) by bisection on the candidate count of rows [0, r)
+    cuts = [0]
+    if world > 1:
+        total = candidates(0, n)
+        for k in range(1, world):
+            lo, hi = 0, n // 32
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if candidates(0, mid * 32) < total * k // world:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            cuts.append(max(lo * 32, cuts[-1]))
+    cuts.append(n)
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    cap = candidates(r0, r1 - r0)
+    rows, cols, vals = ctx.empty(cap, np.int32), ctx.empty(cap, np.int32), ctx.empty(cap, np.float64)
+    nnz_c = C.c_longlong(0)
+    pkg.check(L.b200_gen_rmat_coo(ctx.h, scale, ef, *abc, seed, r0, r1 - r0, cap, rows.ptr, cols.ptr, vals.ptr,
+                                  C.byref(nnz_c)), "rmat gen")
+    nnz = nnz_c.value
+    pkg.check(L.b200_offset_i32(ctx.h, rows.ptr, nnz, -r0), "rebase rows")
+    rows.n = cols.n = vals.n = nnz  # views of the first nnz entries
+    n_rows = r1 - r0
+    coo = pkg.CooMatrix(ctx, n_rows, n, rows, cols, vals)
+    x = ctx.empty(n, dtype)
+    gen_x = L.b200_gen_uniform_f32 if dtype == np.float32 else L.b200_gen_uniform_f64
+    pkg.check(gen_x(ctx.h, x.ptr, n, 7, 0.0, 1.0), "gen x")
+    csr = pkg.CsrMatrix(coo, check_sorted=False)
+    info, st = csr.plan_info(), csr.row_stats()
+    y = ctx.zeros(n_rows, dtype)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def time_mat(m):
+        for _ in range(args.warmup):
+            m.spmv(x, y)
+        barrier()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        for _ in range(args.steps):
+            m.spmv(x, y)
+        b.record()
+        barrier()
+        return a.elapsed_ms_until(b) / args.steps
+
+    peak, peak_src = measured_peak()
+    results, order = {}, []
+
+    def record(name, m, extra=None):
+        ms = time_mat(m)
+        alg = m.nbytes(dtype)
+        results[name] = dict(ms=ms, alg_bytes=int(alg), nnz=int(nnz), **(extra or {}))
+        order.append(name)
+
+    with ClockSampler(local_rank) as clk:
+        record("csr", csr)
+        record("coo", coo)
+        record("cmrs", pkg.CmrsMatrix(csr))
+        for sigma in (1, 32, 256, 4096, 65536, n_rows):
+            total = C.c_longlong(0)
+            sp = ctx.empty(L.b200_sell_num_slices(n_rows, 32) + 1, np.int64)
+            perm = ctx.empty(n_rows, np.int32)
+            pkg.check(L.b200_build_sell_ptr(ctx.h, csr.ptr.ptr, n_rows, 32, sigma, perm.ptr, sp.ptr,
+                                            C.byref(total)), "sell ptr")
+            name = f"sell_sigma{sigma if sigma != n_rows else 'R'}"
+            pad = total.value / max(nnz, 1)
+            del sp, perm
+            if total.value * (4 + dtype.itemsize) > args.rmat_max_sell_bytes:
+                results[name] = dict(ms=None, padding_factor=round(pad, 3), skipped="padded arrays exceed --rmat-max-sell-bytes")
+                order.append(name)
+                continue
+            m = pkg.SellMatrix(csr, dtype, sigma=sigma, wide=True)
+            record(name, m, dict(padding_factor=round(pad, 3)))
+            del m
+    # max over ranks per format, sum of nnz (strong scaling: the job is the whole matrix)
+    names = [k for k in order if results[k].get("ms") is not None]
+    ms = np.array([results[k]["ms"] for k in names])
+    tot = np.array([float(nnz)])
+    if dist is not None:
+        import torch
+        t = torch.tensor(ms, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.cpu().numpy()
+        t2 = torch.tensor(tot, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        tot = t2.cpu().numpy()
+    fm = {}
+    for k in order:
+        r = results[k]
+        if r.get("ms") is None:
+            fm[k] = r
+            continue
+        t_ms = float(ms[names.index(k)])
+        gbs = r["alg_bytes"] / (r["ms"] * 1e-3) * 1e-9  # this rank's own bytes / own time
+        fm[k] = {"ms": round(t_ms, 5), "gflops": round(2.0 * tot[0] / (t_ms * 1e-3) * 1e-9, 2),
+                 "alg_bytes_rank0": r["alg_bytes"], "gbs_rank0": round(gbs, 1), "frac_measured_rank0": round(gbs / peak, 4)}
+        if "padding_factor" in r:
+            fm[k]["padding_factor"] = r["padding_factor"]
+    if rank == 0:
+        best_sell = min((k for k in names if k.startswith("sell")), key=lambda k: fm[k]["ms"], default=None)
+        out = {
+            "metric": "SpMV GFLOP/s of CSR on the power-law matrix (2*nnz flops); COO, CMRS and the SELL-32-sigma "
+                      "sweep with padding factors in `formats`",
+            "value": fm["csr"]["gflops"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": fm["csr"]["ms"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
+            "config": {"workload": f"R-MAT power-law (BASELINE configs[3]): scale {scale} = {n} rows, edge factor {ef}, "
+                                   f"(a,b,c,d)=(0.57,0.19,0.19,0.05), diagonal added, duplicates removed: {int(tot[0])} nnz; "
+                                   f"{world} nnz-balanced row block(s), x replicated, no collective",
+                       "rank0": {"rows": int(n_rows), "nnz": int(nnz), "mean_len": round(info.mean_len, 2),
+                                 "max_len": int(st.max_len), "csr_kernel": "nnz-split stream" if info.stream_tiles else
+                                 f"vector, {info.lanes_per_row} lanes/row + {info.n_long_rows} long rows"},
+                       "ell": f"not run: K = longest row = {int(st.max_len)} would need {n_rows * st.max_len * (4 + dtype.itemsize) / 1e12:.1f} TB",
+                       "cache": "inputs larger than L2, no flush"},
+            "formats": fm, "best_sell": best_sell,
+            "roofline": {"bound": "hbm", "kernel": "csr", "achieved": fm["csr"]["gbs_rank0"], "peak": peak, "unit": "GB/s",
+                         "frac": fm["csr"]["frac_measured_rank0"], "traffic": None, "peak_source": peak_src},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(args.steps * len(names)), "clocks": clk.summary(),
         }
         print(json.dumps(out), flush=True)
     if dist is not None:

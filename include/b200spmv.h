@@ -148,21 +148,29 @@ int b200_spmv_ellcm_f32(b200_ctx *ctx, const float *data_cm, const int *indices_
  * sigma_c.c:212); `n_out` says how many leading outputs to write (n_slices*32 for the
  * reference's padded buffer, n_rows otherwise).  `perm` (new; NULL = identity) is the
  * sigma-window permutation perm[new_row] = old_row: row new_row's result goes to
- * output[perm[new_row]].  chunk must be 32 (warp-aligned chunks). */
+ * output[perm[new_row]].  chunk must be 32 (warp-aligned chunks).
+ * `plan` (new; NULL = one warp walks each chunk whole, which is what FEM-like inputs want) lists
+ * the chunks wider than 256 columns -- power-law inputs, where one hub row makes a chunk 10^5
+ * columns wide -- so that their columns are split over many warps (atomics for the extra pieces). */
+typedef struct b200_sell_plan b200_sell_plan;
+int b200_sell_plan_create(b200_ctx *ctx, const int *row_indices, int n_slices, b200_sell_plan **plan);
+int b200_sell64_plan_create(b200_ctx *ctx, const long long *slice_ptr, int n_slices, b200_sell_plan **plan);
+int b200_sell_plan_extra_items(const b200_sell_plan *plan, int *n_items);
+int b200_sell_plan_destroy(b200_sell_plan *plan);
 int b200_spmv_sell_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                        double *output, const int *row_indices, int chunk, int n_slices, int n_out,
-                       const int *perm);
+                       const int *perm, const b200_sell_plan *plan);
 int b200_spmv_sell_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
                        float *output, const int *row_indices, int chunk, int n_slices, int n_out,
-                       const int *perm);
+                       const int *perm, const b200_sell_plan *plan);
 /* same with 64-bit chunk pointers (the reference's cl_int row_indices overflows when the padded
  * size exceeds 2^31, sigma_c.c:41,118-119) */
 int b200_spmv_sell64_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                          double *output, const long long *slice_ptr, int chunk, int n_slices,
-                         int n_out, const int *perm);
+                         int n_out, const int *perm, const b200_sell_plan *plan);
 int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
                          float *output, const long long *slice_ptr, int chunk, int n_slices,
-                         int n_out, const int *perm);
+                         int n_out, const int *perm, const b200_sell_plan *plan);
 
 /* CMRS: kernel cmrs(data,indices,strip_ptr,row_in_strip,vect,output,N=strips,height,local)
  * kernels/Cmrs.cl:1, args cmrs.c:197-205.  `n_rows` bounds the store of the last strip (the
@@ -247,6 +255,15 @@ int b200_gen_banded_coo(b200_ctx *ctx, int n_global, int row_begin, int row_coun
 long long b200_gen_laplace7_nnz(int nx, int ny, int nz, int row_begin, int row_count);
 int b200_gen_laplace7_coo(b200_ctx *ctx, int nx, int ny, int nz, int row_begin, int row_count,
                           int *rows, int *cols, double *vals);
+/* R-MAT power-law matrix, n = 2^scale: n*edge_factor edges with quadrant probabilities
+ * (a, b, c, 1-a-b-c), one diagonal entry per row added (no empty rows), duplicates removed.
+ * b200_gen_rmat_count gives an upper bound (*n_candidates, before duplicate removal) for the
+ * output capacity of the row block; b200_gen_rmat_coo writes *nnz_out entries. */
+int b200_gen_rmat_count(b200_ctx *ctx, int scale, int edge_factor, double a, double b, double c,
+                        uint64_t seed, int row_begin, int row_count, long long *n_candidates);
+int b200_gen_rmat_coo(b200_ctx *ctx, int scale, int edge_factor, double a, double b, double c,
+                      uint64_t seed, int row_begin, int row_count, long long capacity, int *rows,
+                      int *cols, double *vals, long long *nnz_out);
 int b200_gen_uniform_f64(b200_ctx *ctx, double *x, long long n, uint64_t seed, double lo, double hi);
 int b200_gen_uniform_f32(b200_ctx *ctx, float *x, long long n, uint64_t seed, float lo, float hi);
 /* host twins of the generators' per-element functions (same integer hash; bit-identical), so a

@@ -82,10 +82,14 @@ SIGNATURES = {
     "b200_spmv_ell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "b200_spmv_ellcm_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "b200_spmv_ellcm_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
-    "b200_spmv_sell_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "b200_spmv_sell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "b200_spmv_sell64_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "b200_spmv_sell64_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_sell_plan_create": (_i, [_vp, _vp, _i, _vpp]),
+    "b200_sell64_plan_create": (_i, [_vp, _vp, _i, _vpp]),
+    "b200_sell_plan_extra_items": (_i, [_vp, C.POINTER(_i)]),
+    "b200_sell_plan_destroy": (_i, [_vp]),
+    "b200_spmv_sell_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b200_spmv_sell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b200_spmv_sell64_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "b200_spmv_sell64_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b200_spmv_cmrs_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "b200_spmv_cmrs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "b200_check_sorted_rows": (_i, [_vp, _vp, _i, _i]),
@@ -110,6 +114,10 @@ SIGNATURES = {
     "b200_gen_banded_coo": (_i, [_vp, _i, _i, _i, _i, _i, _u64, _vp, _vp, _vp]),
     "b200_gen_laplace7_nnz": (_ll, [_i, _i, _i, _i, _i]),
     "b200_gen_laplace7_coo": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b200_gen_rmat_count": (_i, [_vp, _i, _i, C.c_double, C.c_double, C.c_double, _u64, _i, _i,
+                                 C.POINTER(_ll)]),
+    "b200_gen_rmat_coo": (_i, [_vp, _i, _i, C.c_double, C.c_double, C.c_double, _u64, _i, _i, _ll,
+                               _vp, _vp, _vp, C.POINTER(_ll)]),
     "b200_gen_uniform_f64": (_i, [_vp, _vp, _ll, _u64, C.c_double, C.c_double]),
     "b200_gen_uniform_f32": (_i, [_vp, _vp, _ll, _u64, C.c_float, C.c_float]),
     "b200_gen_banded_coo_host": (_i, [_i, _i, _i, _i, _i, _u64, _vp, _vp, _vp]),

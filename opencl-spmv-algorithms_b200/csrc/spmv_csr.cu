@@ -154,6 +154,9 @@ csr_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ col, cons
                   int *__restrict__ carry_row, T *__restrict__ carry_val)
 {
     __shared__ T prod[kTile];
+    __shared__ int long_list[kTile / 32];  // rows with > 32 entries inside this tile (at most 31)
+    __shared__ int n_long;
+    if (threadIdx.x == 0) n_long = 0;
     const int b = blockIdx.x;
     const int e0 = b * kTile, e1 = min(e0 + kTile, nnz);
     const int lo = __ldg(tile_lo + b), r_end = __ldg(tile_lo + b + 1);
@@ -201,17 +204,31 @@ csr_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ col, cons
             carry_row[b] = -1;
         }
     }
-    // rows that start in this tile: one thread per row
+    // rows that start in this tile: one thread per row; a row with more than 32 entries inside
+    // the tile is left to a whole warp below (keeps skewed, power-law inputs balanced)
     while (r < r_end) {
         const int stop = min(e, e1) - e0;
-        T acc = 0;
-        for (int i = s - e0; i < stop; ++i) acc += prod[i];
-        y[r] = acc;
+        if (stop - (s - e0) > 32) {
+            long_list[atomicAdd(&n_long, 1)] = r;
+        } else {
+            T acc = 0;
+            for (int i = s - e0; i < stop; ++i) acc += prod[i];
+            y[r] = acc;
+        }
         r += kBlock;
         if (r < r_end) {
             s = __ldg(ptr + r);
             e = __ldg(ptr + r + 1);
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x >> 5; i < n_long; i += kBlock / 32) {
+        const int lr = long_list[i];
+        const int ls = __ldg(ptr + lr) - e0, lstop = min(__ldg(ptr + lr + 1), e1) - e0;
+        T part = 0;
+        for (int k = ls + (threadIdx.x & 31); k < lstop; k += 32) part += prod[k];
+        part = subwarp_sum<32>(part);
+        if ((threadIdx.x & 31) == 0) y[lr] = part;
     }
 }
 
@@ -219,8 +236,15 @@ template <typename T>
 __global__ void csr_stream_fixup_kernel(T *__restrict__ y, int n_tiles, const int *__restrict__ carry_row,
                                         const T *__restrict__ carry_val)
 {
+    // A row's carry tiles are consecutive.  The thread of the FIRST of them adds the whole run in
+    // tile order: no atomics, and the result does not depend on scheduling (bit-reproducible).
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_tiles && carry_row[b] >= 0) atomicAdd(y + carry_row[b], carry_val[b]);
+    if (b >= n_tiles) return;
+    const int r = carry_row[b];
+    if (r < 0 || (b > 0 && carry_row[b - 1] == r)) return;
+    T sum = 0;
+    for (int k = b; k < n_tiles && carry_row[k] == r; ++k) sum += carry_val[k];
+    y[r] += sum;
 }
 
 // row-major ELL (the reference's arrays): row r owns entries [r*K, (r+1)*K)
@@ -371,10 +395,15 @@ int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
             p->n_split = (int)(split < 1 ? 1 : (split > 128 ? 128 : split));
         }
         // short rows everywhere: the nnz-split stream kernel (B200_CSR_STREAM=0|1 overrides)
-        bool stream = in.mean_len <= 16.0 && in.max_len <= 256 && first_last[0] == 0 && in.nnz > 0 &&
+        // (any maximum row length: rows longer than 32 entries inside a tile get a whole warp, rows
+        // longer than a tile are stitched by the carries -- the split is by entries, so skewed
+        // power-law inputs stay balanced)
+        const bool short_rows = in.mean_len <= 16.0;
+        const bool skewed = in.mean_len <= 32.0 && (double)in.max_len > 16.0 * in.mean_len;
+        bool stream = (short_rows || skewed) && first_last[0] == 0 && in.nnz > 0 &&
                       in.nnz < 0x7fffffffll - kTile;
         if (const char *e = getenv("B200_CSR_STREAM"))
-            stream = atoi(e) != 0 && first_last[0] == 0 && in.nnz > 0 && in.max_len <= kTile;
+            stream = atoi(e) != 0 && first_last[0] == 0 && in.nnz > 0 && in.nnz < 0x7fffffffll - kTile;
         if (stream) {
             const int n_tiles = (int)((in.nnz + kTile - 1) / kTile);
             cudaError_t e = cudaMalloc(&p->tile_lo, sizeof(int) * ((size_t)n_tiles + 1));

@@ -20,22 +20,38 @@ namespace {
 
 constexpr int kBlock = 256;
 
-template <typename T, typename P>
+// Columns [seg*wmax, (seg+1)*wmax) of one chunk, by one warp.  seg == 0 is the main pass (plain
+// store, wmax = 0 means the whole chunk); seg > 0 are the extra segments of chunks wider than wmax
+// columns (power-law inputs: a hub row makes one chunk 10^5 columns wide), listed by the plan and
+// accumulated with atomics after the main pass.
+template <typename T, typename P, bool EXTRA>
 __global__ void __launch_bounds__(kBlock)
 sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
-              T *__restrict__ y, const P *__restrict__ slice_ptr, int n_slices, int n_out,
-              const int *__restrict__ perm)
+              T *__restrict__ y, const P *__restrict__ slice_ptr, int n_work, int n_out,
+              const int *__restrict__ perm, int wmax, const int2 *__restrict__ items)
 {
     const int lane = threadIdx.x & 31;
-    const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    if (slice >= n_slices) return;  // whole warps leave together
-    const long long base = slice_ptr[slice];
-    const long long n_groups = ((long long)slice_ptr[slice + 1] - base) >> 2;  // 8 per column
-    const int *ip = idx + base;
-    const T *dp = data + base;
+    const long long work = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (work >= n_work) return;  // whole warps leave together
+    long long slice = work;
+    int seg = 0;
+    if (EXTRA) {
+        const int2 it = items[work];
+        slice = it.x;
+        seg = it.y;
+    }
+    const long long chunk_base = slice_ptr[slice];
+    long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;  // 8 per column
+    long long g_begin = 0;
+    if (wmax > 0) {
+        g_begin = (long long)seg * wmax * 8;
+        n_groups = min(n_groups, g_begin + (long long)wmax * 8);
+    }
+    const int *ip = idx + chunk_base;
+    const T *dp = data + chunk_base;
     T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
 #pragma unroll 4
-    for (long long g = lane; g < n_groups; g += 32) {
+    for (long long g = g_begin + lane; g < n_groups; g += 32) {
         IVec4 c;
         Vec4<T> v;
         c.load(ip + (g << 2));
@@ -56,9 +72,31 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
         const long long r = slice * 32 + lane * 4;
         const T a[4] = {acc0, acc1, acc2, acc3};
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (r + k < n_out) y[perm ? perm[r + k] : r + k] = a[k];
+        for (int k = 0; k < 4; ++k) {
+            if (r + k < n_out) {
+                T *dst = y + (perm ? perm[r + k] : r + k);
+                if (EXTRA) atomicAdd(dst, a[k]);
+                else *dst = a[k];
+            }
+        }
     }
+}
+
+// ---- plan: extra (chunk, segment) work items of chunks wider than kSellWmax columns ---------
+constexpr int kSellWmax = 256;
+
+template <typename P>
+__global__ void sell_wide_items_kernel(const P *__restrict__ slice_ptr, int n_slices, int wmax,
+                                       int *counter, int2 *items)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    const long long width = ((long long)slice_ptr[s + 1] - (long long)slice_ptr[s]) >> 5;
+    const int extra = (int)((width + wmax - 1) / wmax) - 1;
+    if (extra <= 0) return;
+    const int at = atomicAdd(counter, extra);
+    if (items)
+        for (int k = 0; k < extra; ++k) items[at + k] = make_int2((int)s, k + 1);
 }
 
 // scalar-load variant for unaligned arrays: lane = row (the reference's mapping)
@@ -127,9 +165,62 @@ ellcm_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *_
     }
 }
 
+}  // namespace
+
+struct b200_sell_plan {
+    int device;
+    int n_slices;
+    int n_items;   // extra (chunk, segment) work items
+    int wmax;      // columns per segment
+    int2 *items;   // device
+};
+
+namespace {
+
+template <typename P>
+int sell_plan_create_impl(b200_ctx *ctx, const P *slice_ptr, int n_slices, b200_sell_plan **plan)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(slice_ptr && plan && n_slices >= 0, "bad argument");
+    *plan = nullptr;
+    b200_sell_plan *p = new b200_sell_plan();
+    p->device = ctx->device;
+    p->n_slices = n_slices;
+    p->n_items = 0;
+    p->wmax = kSellWmax;
+    p->items = nullptr;
+    if (n_slices > 0) {
+        int *counter = ctx->scratch + 192;
+        const unsigned blocks = ceil_div_u(n_slices, 256);
+        int count = 0;
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+        sell_wide_items_kernel<P><<<blocks, 256, 0, ctx->stream>>>(slice_ptr, n_slices, p->wmax, counter, nullptr);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&count, counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess && count > 0) {
+            e = cudaMalloc(&p->items, sizeof(int2) * (size_t)count);
+            if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+            if (e == cudaSuccess) {
+                sell_wide_items_kernel<P><<<blocks, 256, 0, ctx->stream>>>(slice_ptr, n_slices, p->wmax, counter, p->items);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+        if (e != cudaSuccess) {
+            if (p->items) cudaFree(p->items);
+            delete p;
+            return b200_cuda_fail(e, "sell plan", __FILE__, __LINE__);
+        }
+        p->n_items = count;
+    }
+    *plan = p;
+    return B200_SUCCESS;
+}
+
 template <typename T, typename P>
 int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *y, const P *slice_ptr,
-                   int chunk, int n_slices, int n_out, const int *perm)
+                   int chunk, int n_slices, int n_out, const int *perm, const b200_sell_plan *plan)
 {
     B200_ENTER(ctx);
     B200_REQUIRE(x && y && slice_ptr && n_slices >= 0 && n_out >= 0, "bad argument");
@@ -138,12 +229,19 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
         return B200_ERR_UNSUPPORTED;
     }
     B200_REQUIRE((long long)n_out <= (long long)n_slices * 32, "n_out exceeds n_slices*32");
+    B200_REQUIRE(!plan || plan->n_slices == n_slices, "plan was built for a different matrix");
     if (n_slices == 0) return B200_SUCCESS;
     unsigned blocks = ceil_div_u((long long)n_slices * 32, kBlock);
-    if (aligned16(data) && aligned16(idx))
-        sell32_kernel<T, P><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices, n_out, perm);
-    else
+    if (aligned16(data) && aligned16(idx)) {
+        const int wmax = plan && plan->n_items > 0 ? plan->wmax : 0;
+        sell32_kernel<T, P, false><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices,
+                                                                      n_out, perm, wmax, nullptr);
+        if (wmax > 0)
+            sell32_kernel<T, P, true><<<ceil_div_u((long long)plan->n_items * 32, kBlock), kBlock, 0, ctx->stream>>>(
+                data, idx, x, y, slice_ptr, plan->n_items, n_out, perm, wmax, plan->items);
+    } else {
         sell32_scalar_kernel<T, P><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices, n_out, perm);
+    }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -196,29 +294,52 @@ int spmv_ellcm_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T 
 
 extern "C" {
 
+int b200_sell_plan_create(b200_ctx *ctx, const int *row_indices, int n_slices, b200_sell_plan **plan)
+{
+    return sell_plan_create_impl<int>(ctx, row_indices, n_slices, plan);
+}
+int b200_sell64_plan_create(b200_ctx *ctx, const long long *slice_ptr, int n_slices, b200_sell_plan **plan)
+{
+    return sell_plan_create_impl<long long>(ctx, slice_ptr, n_slices, plan);
+}
+int b200_sell_plan_extra_items(const b200_sell_plan *plan, int *n_items)
+{
+    B200_REQUIRE(plan && n_items, "null argument");
+    *n_items = plan->n_items;
+    return B200_SUCCESS;
+}
+int b200_sell_plan_destroy(b200_sell_plan *plan)
+{
+    if (!plan) return B200_SUCCESS;
+    cudaSetDevice(plan->device);
+    if (plan->items) cudaFree(plan->items);
+    delete plan;
+    return B200_SUCCESS;
+}
+
 int b200_spmv_sell_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                        double *output, const int *row_indices, int chunk, int n_slices, int n_out,
-                       const int *perm)
+                       const int *perm, const b200_sell_plan *plan)
 {
-    return spmv_sell_impl<double, int>(ctx, data, indices, vect, output, row_indices, chunk, n_slices, n_out, perm);
+    return spmv_sell_impl<double, int>(ctx, data, indices, vect, output, row_indices, chunk, n_slices, n_out, perm, plan);
 }
 int b200_spmv_sell_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
                        float *output, const int *row_indices, int chunk, int n_slices, int n_out,
-                       const int *perm)
+                       const int *perm, const b200_sell_plan *plan)
 {
-    return spmv_sell_impl<float, int>(ctx, data, indices, vect, output, row_indices, chunk, n_slices, n_out, perm);
+    return spmv_sell_impl<float, int>(ctx, data, indices, vect, output, row_indices, chunk, n_slices, n_out, perm, plan);
 }
 int b200_spmv_sell64_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                          double *output, const long long *slice_ptr, int chunk, int n_slices,
-                         int n_out, const int *perm)
+                         int n_out, const int *perm, const b200_sell_plan *plan)
 {
-    return spmv_sell_impl<double, long long>(ctx, data, indices, vect, output, slice_ptr, chunk, n_slices, n_out, perm);
+    return spmv_sell_impl<double, long long>(ctx, data, indices, vect, output, slice_ptr, chunk, n_slices, n_out, perm, plan);
 }
 int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, const float *vect,
                          float *output, const long long *slice_ptr, int chunk, int n_slices,
-                         int n_out, const int *perm)
+                         int n_out, const int *perm, const b200_sell_plan *plan)
 {
-    return spmv_sell_impl<float, long long>(ctx, data, indices, vect, output, slice_ptr, chunk, n_slices, n_out, perm);
+    return spmv_sell_impl<float, long long>(ctx, data, indices, vect, output, slice_ptr, chunk, n_slices, n_out, perm, plan);
 }
 
 int b200_spmv_ellcm_f64(b200_ctx *ctx, const double *data_cm, const int *indices_cm,

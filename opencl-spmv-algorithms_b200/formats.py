@@ -195,7 +195,26 @@ class SellMatrix:
                  self.perm.ptr if self.perm else None, self.slice_ptr.ptr, self.cols.ptr,
                  self.data.ptr), "b200_build_sell_fill")
 
-    def spmv(self, x: DeviceArray, y: DeviceArray, n_out: int | None = None) -> None:
+    def plan(self):
+        """Wide-chunk work list (only non-trivial on power-law inputs)."""
+        if getattr(self, "_plan", None) is None:
+            p = C.c_void_p()
+            if self.wide:
+                check(lib().b200_sell64_plan_create(self.ctx.h, self.slice_ptr.ptr, self.n_slices,
+                                                    C.byref(p)), "b200_sell64_plan_create")
+            else:
+                check(lib().b200_sell_plan_create(self.ctx.h, self.row_indices.ptr, self.n_slices,
+                                                  C.byref(p)), "b200_sell_plan_create")
+            self._plan = p
+        return self._plan
+
+    def plan_extra_items(self) -> int:
+        n = C.c_int(0)
+        check(lib().b200_sell_plan_extra_items(self.plan(), C.byref(n)), "b200_sell_plan_extra_items")
+        return n.value
+
+    def spmv(self, x: DeviceArray, y: DeviceArray, n_out: int | None = None,
+             use_plan: bool = True) -> None:
         n_out = self.n_rows if n_out is None else n_out
         perm = self.perm.ptr if self.perm else None
         if self.wide:
@@ -205,7 +224,15 @@ class SellMatrix:
             fn = getattr(lib(), "b200_spmv_sell_" + suffix(self.dtype))
             p = self.row_indices.ptr
         check(fn(self.ctx.h, self.data.ptr, self.cols.ptr, x.ptr, y.ptr, p, self.chunk,
-                 self.n_slices, n_out, perm), "b200_spmv_sell")
+                 self.n_slices, n_out, perm, self.plan() if use_plan else None), "b200_spmv_sell")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                lib().b200_sell_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
 
     def nbytes(self, dtype=None) -> int:
         return algorithmic_bytes("sell", self.dtype.itemsize, n_rows=self.n_rows,

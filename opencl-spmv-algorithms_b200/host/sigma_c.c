@@ -70,11 +70,14 @@ int main(int argc, char *argv[])
     (opt.use_f32 ? b200_spmv_sell_f32(ctx, (const float *)buffer_data, (const int *)buffer_indices,         \
                                       (const float *)d.vect, (float *)buffer_output,                        \
                                       (const int *)buffer_row_indices, max_rows_to_check, number_of_slices, \
-                                      n_out, (const int *)buffer_perm)                                      \
+                                      n_out, (const int *)buffer_perm, plan)                                \
                  : b200_spmv_sell_f64(ctx, (const double *)buffer_data, (const int *)buffer_indices,        \
                                       (const double *)d.vect, (double *)buffer_output,                      \
                                       (const int *)buffer_row_indices, max_rows_to_check, number_of_slices, \
-                                      n_out, (const int *)buffer_perm))
+                                      n_out, (const int *)buffer_perm, plan))
+    /* wide-chunk work list (empty for FEM-like inputs; splits hub chunks of power-law inputs) */
+    b200_sell_plan *plan = NULL;
+    B200_TRY(b200_sell_plan_create(ctx, (const int *)buffer_row_indices, number_of_slices, &plan));
 
     /* run program */
     B200_TRY(LAUNCH());
@@ -96,6 +99,7 @@ int main(int argc, char *argv[])
     else printf("result is wrong\n");
 
     /* release memory */
+    b200_sell_plan_destroy(plan);
     b200_free(ctx, buffer_ptr);
     b200_free(ctx, buffer_slice_ptr);
     b200_free(ctx, buffer_row_indices);

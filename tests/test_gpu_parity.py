@@ -168,7 +168,7 @@ def test_unsorted_rows_rejected(ctx):
 def test_bad_arguments_fail_loudly(ctx):
     L = pkg.lib()
     x = ctx.zeros(8, np.float64)
-    assert L.b200_spmv_sell_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 16, 1, 8, None) == pkg.ERR_UNSUPPORTED
+    assert L.b200_spmv_sell_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 16, 1, 8, None, None) == pkg.ERR_UNSUPPORTED
     assert L.b200_spmv_cmrs_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, 64, 8) == pkg.ERR_UNSUPPORTED
     assert L.b200_spmv_ellcm_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, 8, 1, 8) == pkg.ERR_INVALID_VALUE
     assert L.b200_spmv_csr_f64(None, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, None) == pkg.ERR_INVALID_VALUE
@@ -207,7 +207,7 @@ def test_unaligned_arrays_take_the_scalar_kernels(ctx, dtype):
     sc_d, sd_d, ri_d = ctx.array(pad(sc, np.int32)), ctx.array(pad(sd, dtype)), ctx.array(ri)
     yd = ctx.array(np.full(n_rows, np.nan, dtype))
     pkg.check(getattr(L, "b200_spmv_sell_" + suf)(ctx.h, sd_d.ptr + V, sc_d.ptr + 4, xd.ptr, yd.ptr, ri_d.ptr,
-                                                  32, len(ri) - 1, n_rows, None), "sell")
+                                                  32, len(ri) - 1, n_rows, None, None), "sell")
     check_y("sell-unaligned", yd.download(), y_ref, dtype)
 
 

@@ -124,3 +124,64 @@ def test_full_size_banded_properties(ctx):
         y_ref = O.yref(cnt, rh - r0, ch, vh, xh.astype(np.float64))
         for name in ys:
             assert O.rel_maxnorm(ys[name][r0:r0 + cnt], y_ref) <= 1e-5, (name, r0)
+
+
+def gen_rmat(ctx, scale, ef, r0, cnt, seed=3, abc=(0.57, 0.19, 0.19)):
+    import ctypes as C
+    L = pkg.lib()
+    cand = C.c_longlong(0)
+    pkg.check(L.b200_gen_rmat_count(ctx.h, scale, ef, *abc, seed, r0, cnt, C.byref(cand)), "rmat count")
+    rows, cols, vals = ctx.empty(cand.value, np.int32), ctx.empty(cand.value, np.int32), ctx.empty(cand.value, np.float64)
+    nnz = C.c_longlong(0)
+    pkg.check(L.b200_gen_rmat_coo(ctx.h, scale, ef, *abc, seed, r0, cnt, cand.value, rows.ptr, cols.ptr,
+                                  vals.ptr, C.byref(nnz)), "rmat gen")
+    assert 0 < nnz.value <= cand.value
+    return rows.download(nnz.value), cols.download(nnz.value), vals.download(nnz.value)
+
+
+def test_rmat_generator_and_formats(ctx):
+    """BASELINE configs[3] in small: the power-law generator (sorted, duplicate-free, a diagonal in
+    every row, shard blocks concatenate to the whole matrix) and every kernel that is meant to run on
+    it -- the nnz-split CSR kernel with rows spanning many tiles, COO, CMRS, SELL with a sigma sweep."""
+    scale, ef = 13, 8
+    n = 1 << scale
+    rows, cols, vals = gen_rmat(ctx, scale, ef, 0, n)
+    key = rows.astype(np.int64) << 32 | cols
+    assert np.all(np.diff(key) > 0), "not sorted by (row, col) or duplicates left"
+    assert cols.min() >= 0 and cols.max() < n and np.all(np.abs(vals) <= 1.0)
+    assert set(np.flatnonzero(rows == cols)) and np.array_equal(rows[rows == cols], np.arange(n))
+    lens = np.bincount(rows, minlength=n)
+    assert lens.min() >= 1 and lens.max() > 20 * lens.mean()          # skewed
+    parts = [gen_rmat(ctx, scale, ef, r0, cnt) for r0, cnt in ((0, 1000), (1000, 3096), (4096, n - 4096))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), rows)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), cols)
+    assert np.concatenate([p[2] for p in parts]).tobytes() == vals.tobytes()
+
+    x = np.random.default_rng(2).uniform(0, 1, n)
+    y_ref = O.yref(n, rows, cols, vals, x)
+    coo = pkg.CooMatrix.from_host(ctx, n, n, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo)
+    info = csr.plan_info()
+    assert info.stream_tiles > 0 and info.max_len > 512      # skewed: the nnz-split kernel is chosen
+    padded = {}
+    for dtype, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        xd = ctx.array(x.astype(dtype))
+        mats = {"coo": coo, "csr": csr, "cmrs": pkg.CmrsMatrix(csr)}
+        for sigma in (1, 64, 4096, n):
+            mats[f"sell{sigma}"] = pkg.SellMatrix(csr, dtype, sigma=sigma)
+            padded[sigma] = mats[f"sell{sigma}"].total
+        for name, mat in mats.items():
+            yd = ctx.array(np.full(n, np.nan, dtype))
+            mat.spmv(xd, yd)
+            assert O.rel_maxnorm(yd.download(), y_ref) <= tol, (name, dtype)
+        # hub chunks (> 256 columns) are split over many warps by the SELL plan; without the plan
+        # one warp walks the whole chunk -- same answer
+        assert mats["sell1"].plan_extra_items() > 0 and mats[f"sell{n}"].plan_extra_items() > 0
+        yd = ctx.array(np.full(n, np.nan, dtype))
+        mats["sell64"].spmv(xd, yd, use_plan=False)
+        assert O.rel_maxnorm(yd.download(), y_ref) <= tol
+    assert padded[1] > padded[64] > padded[4096] >= padded[n] >= rows.size
+    perm, sp, _, _ = O.build_sell_sigma(n, rows, cols, vals, 4096)
+    m = pkg.SellMatrix(csr, np.float64, sigma=4096)
+    np.testing.assert_array_equal(m.perm.download(), perm)
+    np.testing.assert_array_equal(m.slice_ptr.download(), sp)
