@@ -243,7 +243,7 @@ def cpu_arm(n_rows, n_cols, rows, cols, vals, x, dtype, kind, reps, warm):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="banded", choices=["banded", "cant", "laplace-iter", "rmat"])
@@ -390,8 +390,17 @@ def main():
                  "alg_bytes": int(bytes_alg[f]), "gbs": round(gbs, 1),
                  "frac_measured": round(gbs / peak, 4), "frac_nominal_8TBs": round(gbs / NOMINAL_HBM_GBS, 4)}
     dom = max(mats, key=lambda f: per_ms[f])
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this very
+    # workload (profiles/ncu_traffic.json); null for workloads that were not captured
+    traffic = None
+    try:
+        cap = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        if cap["workload"] == args.workload and cap["dtype"] == dname and world == 1 and n_rows == 2097152:
+            traffic = cap["traffic_bytes"].get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": fm[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": fm[dom]["frac_measured"], "traffic": None, "peak_source": peak_src,
+                "frac": fm[dom]["frac_measured"], "traffic": traffic, "peak_source": peak_src,
                 "per_format_frac": {f: fm[f]["frac_measured"] for f in mats}}
 
     # ---------------- e2e: host x in, host y out, through the C ABI, matrix resident ----------
