@@ -123,6 +123,10 @@ SIGNATURES = {
     "b200_gen_banded_coo_host": (_i, [_i, _i, _i, _i, _i, _u64, _vp, _vp, _vp]),
     "b200_gen_uniform_f64_host": (_i, [_vp, _ll, _u64, C.c_double, C.c_double]),
     "b200_partition_rows": (_i, [_vp, _i, _i, _i, _vp]),
+    "b200_spmv_sell_bcast_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _ll]),
+    "b200_ipc_get_handle": (_i, [_vp, _vp, _vp]),
+    "b200_ipc_open_handle": (_i, [_vp, _vp, _vpp]),
+    "b200_ipc_close_handle": (_i, [_vp, _vp]),
     "b200_scale_f64": (_i, [_vp, _vp, _ll, _vp, _i]),
     "b200_sumsq_f64": (_i, [_vp, _vp, _ll, _vp]),
 }
@@ -284,4 +288,5 @@ class Event:
 
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix,  # noqa: E402,F401
                       algorithmic_bytes, build_all, partition_rows)
-from .iterate import (RowBlocks, equal_row_blocks, gpu_callables, power_iteration)  # noqa: E402,F401
+from .iterate import (PeerBuffers, RowBlocks, equal_row_blocks, gpu_callables, power_iteration,  # noqa: E402,F401
+                      power_iteration_fused)

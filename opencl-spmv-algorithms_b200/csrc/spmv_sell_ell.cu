@@ -13,6 +13,7 @@
 // too few rows to fill 148 SMs).  Bytes: P*(4+V) + (S+1)*P_bytes [+R*4 perm] + Cn*V + R*V for
 // SELL, R*K*(4+V) + Cn*V + R*V for ELL; both HBM-bound.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -97,6 +98,63 @@ __global__ void sell_wide_items_kernel(const P *__restrict__ slice_ptr, int n_sl
     const int at = atomicAdd(counter, extra);
     if (items)
         for (int k = 0; k < extra; ++k) items[at + k] = make_int2((int)s, k + 1);
+}
+
+// ---- fused SpMV + exchange for the iterated (power-iteration) mode -------------------------
+// y = (A_r . x) / sqrt(*scale2) is written STRAIGHT INTO the gather buffers of all ranks: dst.p[d]
+// is the next-x buffer of rank d (its own for d == rank, the others mapped through CUDA IPC, i.e.
+// plain stores over NVLink/NVSwitch), so the all-gather of the reference-style formulation
+// disappears -- the transfer overlaps the SpMV chunk by chunk.  The only synchronisation left per
+// step is the 1-element all-reduce of ||y||^2, which also orders the peer writes.
+constexpr int kMaxPeers = 16;
+template <typename T>
+struct PeerDst {
+    T *p[kMaxPeers];
+};
+
+template <typename T, typename P>
+__global__ void __launch_bounds__(kBlock)
+sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
+                    const P *__restrict__ slice_ptr, int n_slices, int n_rows,
+                    const T *__restrict__ scale2, PeerDst<T> dst, int n_dst, long long dst_offset)
+{
+    const int lane = threadIdx.x & 31;
+    const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (slice >= n_slices) return;
+    const long long chunk_base = slice_ptr[slice];
+    const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
+    const int *ip = idx + chunk_base;
+    const T *dp = data + chunk_base;
+    T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll 4
+    for (long long g = lane; g < n_groups; g += 32) {
+        IVec4 c;
+        Vec4<T> v;
+        c.load(ip + (g << 2));
+        v.load(dp + (g << 2));
+        acc0 += v.v[0] * ld_x(x, c.v[0]);
+        acc1 += v.v[1] * ld_x(x, c.v[1]);
+        acc2 += v.v[2] * ld_x(x, c.v[2]);
+        acc3 += v.v[3] * ld_x(x, c.v[3]);
+    }
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+        acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
+        acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
+    }
+    if (lane < 8) {
+        const T alpha = scale2 ? rsqrt(*scale2) : T(1);
+        const long long r = slice * 32 + lane * 4;
+        const T a[4] = {acc0 * alpha, acc1 * alpha, acc2 * alpha, acc3 * alpha};
+        for (int d = 0; d < n_dst; ++d) {
+            T *out = dst.p[d] + dst_offset + r;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r + k < n_rows) out[k] = a[k];
+        }
+    }
 }
 
 // scalar-load variant for unaligned arrays: lane = row (the reference's mapping)
@@ -340,6 +398,59 @@ int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, c
                          int n_out, const int *perm, const b200_sell_plan *plan)
 {
     return spmv_sell_impl<float, long long>(ctx, data, indices, vect, output, slice_ptr, chunk, n_slices, n_out, perm, plan);
+}
+
+int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                             const int *row_indices, int chunk, int n_slices, int n_rows,
+                             const double *scale_sumsq, double *const *dst, int n_dst,
+                             long long dst_offset)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(vect && row_indices && dst && n_slices >= 0 && n_rows >= 0 && dst_offset >= 0, "bad argument");
+    B200_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers, "n_dst must be in 1..16");
+    B200_REQUIRE((long long)n_rows <= (long long)n_slices * 32, "n_rows exceeds n_slices*32");
+    if (chunk != 32) {
+        b200_set_error("SELL chunk must be 32 (warp-aligned), got %d", chunk);
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_REQUIRE(aligned16(data) && aligned16(indices), "SELL arrays must be 16-byte aligned");
+    if (n_slices == 0) return B200_SUCCESS;
+    PeerDst<double> d;
+    for (int i = 0; i < kMaxPeers; ++i) d.p[i] = i < n_dst ? dst[i] : nullptr;
+    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
+    sell32_bcast_kernel<double, int><<<ceil_div_u((long long)n_slices * 32, kBlock), kBlock, 0, ctx->stream>>>(
+        data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, d, n_dst, dst_offset);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_ipc_get_handle(b200_ctx *ctx, void *dptr, unsigned char handle[64])
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(dptr && handle, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    B200_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, 64);
+    return B200_SUCCESS;
+}
+
+int b200_ipc_open_handle(b200_ctx *ctx, const unsigned char handle[64], void **peer_dptr)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(handle && peer_dptr, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    *peer_dptr = nullptr;
+    B200_CUDA(cudaIpcOpenMemHandle(peer_dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200_SUCCESS;
+}
+
+int b200_ipc_close_handle(b200_ctx *ctx, void *peer_dptr)
+{
+    B200_ENTER(ctx);
+    if (peer_dptr) B200_CUDA(cudaIpcCloseMemHandle(peer_dptr));
+    return B200_SUCCESS;
 }
 
 int b200_spmv_ellcm_f64(b200_ctx *ctx, const double *data_cm, const int *indices_cm,

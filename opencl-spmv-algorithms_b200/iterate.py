@@ -116,3 +116,84 @@ def gpu_callables(pkg, ctx, matrix, n_rows_local: int):
 
     return dict(spmv_local=spmv_local, sumsq=sumsq, scale_inv_sqrt=scale_inv_sqrt,
                 all_reduce_sum=all_reduce_sum, all_gather_inplace=all_gather_inplace)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused variant: the SpMV kernel itself stores its y-block into every rank's next-x buffer over
+# NVLink (peer memory mapped with CUDA IPC) -- no all-gather, no pack, no separate scale pass.
+# ---------------------------------------------------------------------------------------------
+class PeerBuffers:
+    """Two full-length x buffers per rank, allocated through the C ABI and mapped on every rank
+    (b200_ipc_get_handle / b200_ipc_open_handle; handles travel with all_gather_object)."""
+
+    def __init__(self, pkg, ctx, blocks: RowBlocks, rank: int, world: int):
+        import ctypes as C
+        import numpy as np
+        self.pkg, self.ctx, self.rank, self.world = pkg, ctx, rank, world
+        L = pkg.lib()
+        self.local = [ctx.zeros(blocks.padded, np.float64) for _ in range(2)]
+        ctx.sync()
+        handles = []
+        for buf in self.local:
+            h = (C.c_ubyte * 64)()
+            pkg.check(L.b200_ipc_get_handle(ctx.h, buf.ptr, h), "b200_ipc_get_handle")
+            handles.append(bytes(h))
+        gathered = [handles]
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, handles)
+        self._opened = []
+        self.ptrs = []  # ptrs[b][r] = device pointer of buffer b of rank r, valid in THIS process
+        for b in range(2):
+            row = []
+            for r in range(world):
+                if r == rank:
+                    row.append(self.local[b].ptr)
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(gathered[r][b])
+                    pkg.check(L.b200_ipc_open_handle(ctx.h, hb, C.byref(p)), "b200_ipc_open_handle")
+                    self._opened.append(p.value)
+                    row.append(p.value)
+            self.ptrs.append(row)
+        self.dst = [(C.c_void_p * world)(*row) for row in self.ptrs]
+
+    def close(self):
+        L = self.pkg.lib()
+        self.ctx.sync()
+        for p in self._opened:
+            L.b200_ipc_close_handle(self.ctx.h, p)
+        self._opened = []
+
+
+def power_iteration_fused(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: RowBlocks, steps: int,
+                          first_step: int = 0, acc=None) -> IterationResult:
+    """`steps` power-iteration steps with the fused SpMV + exchange kernel.  bufs.local[first_step % 2]
+    holds the current (unnormalised) vector on every rank; `acc` carries the two ||y||^2 scalars
+    between calls (pass the returned result's .acc back in to continue a run)."""
+    import torch
+    import torch.distributed as dist
+    L = pkg.lib()
+    n_local = blocks.bounds(rank)[1] - blocks.bounds(rank)[0]
+    if acc is None:
+        acc = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(2)]
+    assert sell.perm is None and sell.row_indices is not None, "fused path: SELL-32, sigma = 1, int32 pointers"
+    for k in range(first_step, first_step + steps):
+        cur, nxt = k % 2, (k + 1) % 2
+        scale = acc[(k - 1) % 2].data_ptr() if k > 0 else None
+        a = acc[k % 2]
+        a.zero_()
+        pkg.check(L.b200_spmv_sell_bcast_f64(ctx.h, sell.data.ptr, sell.cols.ptr, bufs.local[cur].ptr,
+                                             sell.row_indices.ptr, 32, sell.n_slices, n_local, scale,
+                                             bufs.dst[nxt], bufs.world, rank * blocks.count),
+                  "b200_spmv_sell_bcast_f64")
+        seg_ptr = bufs.local[nxt].ptr + 8 * rank * blocks.count
+        pkg.check(L.b200_sumsq_f64(ctx.h, seg_ptr, n_local, a.data_ptr()), "b200_sumsq_f64")
+        if bufs.world > 1:
+            dist.all_reduce(a, op=dist.ReduceOp.SUM)  # the norm AND the barrier that orders peer writes
+    last = first_step + steps - 1
+    res = IterationResult(steps, float(acc[last % 2][0]) ** 0.5, bufs.local[(last + 1) % 2])
+    res.acc = acc
+    res.next_step = last + 1
+    return res

@@ -185,3 +185,32 @@ def test_rmat_generator_and_formats(ctx):
     m = pkg.SellMatrix(csr, np.float64, sigma=4096)
     np.testing.assert_array_equal(m.perm.download(), perm)
     np.testing.assert_array_equal(m.slice_ptr.download(), sp)
+
+
+def test_fused_power_iteration_one_gpu(ctx):
+    """The fused SpMV + exchange kernel with a single destination (world = 1) must reproduce the
+    NCCL-formulation iteration and the CPU power iteration."""
+    import torch
+    nx, ny, nz, steps = 24, 20, 18, 41
+    n, rows, cols, vals = laplace7(nx, ny, nz)
+    blocks = pkg.equal_row_blocks(n, 1)
+    x0 = np.zeros(blocks.padded)
+    x0[:n] = np.random.default_rng(1).uniform(0, 1, n)
+    ptr, _ = O.build_csr(n, rows)
+    x = x0[:n].copy()
+    for _ in range(steps):
+        y = O.spmv_csr(n, ptr, cols, vals, x)
+        nrm = np.linalg.norm(y)
+        x = y / nrm
+    tctx = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    sell = pkg.SellMatrix(pkg.CsrMatrix(pkg.CooMatrix.from_host(tctx, n, n, rows, cols, vals)), np.float64)
+    bufs = pkg.PeerBuffers(pkg, tctx, blocks, 0, 1)
+    bufs.local[0].upload(x0)
+    r1 = pkg.power_iteration_fused(pkg, tctx, sell, bufs, 0, blocks, 20)
+    r2 = pkg.power_iteration_fused(pkg, tctx, sell, bufs, 0, blocks, steps - 20, first_step=r1.next_step, acc=r1.acc)
+    tctx.sync()
+    assert abs(r2.norm - nrm) <= 1e-12 * nrm
+    y_un = r2.x.download()[:n]                      # unnormalised A x_{k-1}: normalise once at the end
+    assert np.max(np.abs(y_un / np.linalg.norm(y_un) - x)) <= 1e-12
+    bufs.close()
+    tctx.close()
