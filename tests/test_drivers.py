@@ -103,3 +103,47 @@ def test_driver_options_and_errors(fem_small_dir, tmp_path):
     for layout in ("--rowmajor", "--colmajor"):
         p = run(bins / "ell", tmp_path, "--matrix", mtx, layout)
         assert p.returncode == 0 and "result is ok" in p.stdout, (layout, p.stdout)
+
+
+SHIM_BINS = ROOT / "oracle" / "_ref" / "bin_b200"
+
+
+def test_shim_exports_the_opencl_symbols_the_reference_links():
+    """libOpenCL_b200.so must export the 21 OpenCL entry points the reference drivers call."""
+    lib = ROOT / "opencl-spmv-algorithms_b200" / "lib" / "libOpenCL_b200.so"
+    subprocess.run(["make", "-C", str(ROOT / "opencl-spmv-algorithms_b200" / "shim"), "all"], check=True,
+                   capture_output=True)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(lib)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (cl[A-Za-z]+)", out))
+    needed = {"clGetPlatformIDs", "clGetDeviceIDs", "clCreateContext", "clCreateCommandQueueWithProperties",
+              "clCreateBuffer", "clCreateProgramWithSource", "clBuildProgram", "clGetProgramBuildInfo",
+              "clCreateKernel", "clSetKernelArg", "clEnqueueWriteBuffer", "clEnqueueReadBuffer",
+              "clEnqueueNDRangeKernel", "clWaitForEvents", "clFinish", "clFlush", "clReleaseMemObject",
+              "clReleaseCommandQueue", "clReleaseKernel", "clReleaseProgram", "clReleaseContext"}
+    assert needed <= exported, needed - exported
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_unmodified_reference_binary_runs_on_b200(fem_small_dir, fmt):
+    """the reference's own, unmodified driver (built from /root/reference against
+    shim/CL/cl.h, linked with libOpenCL_b200.so instead of libOpenCL.so) runs its SpMV on the B200
+    kernels and its OWN check_result accepts the GPU result: 'result is ok', exit code 0."""
+    if not (SHIM_BINS / fmt).exists():
+        pytest.skip("oracle/_ref/bin_b200 not built (needs the reference sources at build time)")
+    O.prepare_ref_workdir(fem_small_dir)          # kernels/*.cl placeholders: the driver insists on reading them
+    p = run(SHIM_BINS / fmt, fem_small_dir)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert "result is ok" in lines and "result is wrong" not in lines, p.stdout
+    if fmt != "sigma_c":
+        assert "cpu result is ok" in lines
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_csr_on_full_cant_shape(cant_dir):
+    if not (SHIM_BINS / "csr").exists():
+        pytest.skip("oracle/_ref/bin_b200 not built")
+    O.prepare_ref_workdir(cant_dir)
+    p = run(SHIM_BINS / "csr", cant_dir)
+    assert p.returncode == 0 and "result is ok" in p.stdout.splitlines(), p.stdout + p.stderr
