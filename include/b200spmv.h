@@ -280,16 +280,19 @@ int b200_gen_uniform_f64_host(double *x, long long n, uint64_t seed, double lo, 
  * ===================================================================================== */
 int b200_partition_rows(const int *ptr_host, int n_rows, int n_parts, int align, int *cuts);
 /* Fused SpMV + exchange for the iterated mode (new; replaces SpMV -> scale -> all-gather):
- *   y = (A_r . x) / sqrt(*scale_sumsq)        (scale_sumsq: device scalar, NULL = no scaling)
+ *   y = (A_r . x) / sqrt(sum(scale_sumsq[0..32)))     (scale_sumsq: device, NULL = no scaling)
  * is stored at [dst_offset, dst_offset + n_rows) of EVERY buffer in dst[0..n_dst) -- dst is a HOST
  * array of device pointers: this rank's own next-x buffer plus the peers' buffers mapped with
  * b200_ipc_open_handle, so the stores travel over NVLink/NVSwitch while the SpMV is still running.
- * SELL-32, reference chunk pointers, no permutation.  The caller orders steps with one small
- * all-reduce (which it needs anyway for the norm). */
+ * The same kernel accumulates ||y||^2 of its rows into the B200_SUMSQ_SLOTS partial sums of
+ * sumsq_out (device, zeroed by the caller; NULL = skip), one atomic per block.  SELL-32, reference
+ * chunk pointers, no permutation.  The caller orders steps with one small all-reduce of those
+ * slots (which it needs anyway for the norm): no other launch is needed per step. */
+#define B200_SUMSQ_SLOTS 32
 int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                              const int *row_indices, int chunk, int n_slices, int n_rows,
-                             const double *scale_sumsq, double *const *dst, int n_dst,
-                             long long dst_offset);
+                             const double *scale_sumsq, double *sumsq_out, double *const *dst,
+                             int n_dst, long long dst_offset);
 /* CUDA IPC plumbing for the peers' buffers (allocations made with b200_malloc) */
 int b200_ipc_get_handle(b200_ctx *ctx, void *dptr, unsigned char handle[64]);
 int b200_ipc_open_handle(b200_ctx *ctx, const unsigned char handle[64], void **peer_dptr);

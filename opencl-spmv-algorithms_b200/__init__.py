@@ -123,7 +123,7 @@ SIGNATURES = {
     "b200_gen_banded_coo_host": (_i, [_i, _i, _i, _i, _i, _u64, _vp, _vp, _vp]),
     "b200_gen_uniform_f64_host": (_i, [_vp, _ll, _u64, C.c_double, C.c_double]),
     "b200_partition_rows": (_i, [_vp, _i, _i, _i, _vp]),
-    "b200_spmv_sell_bcast_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _ll]),
+    "b200_spmv_sell_bcast_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _ll]),
     "b200_ipc_get_handle": (_i, [_vp, _vp, _vp]),
     "b200_ipc_open_handle": (_i, [_vp, _vp, _vpp]),
     "b200_ipc_close_handle": (_i, [_vp, _vp]),

@@ -112,30 +112,42 @@ struct PeerDst {
     T *p[kMaxPeers];
 };
 
+// ||y||^2 is accumulated by the same kernel into kSumsqSlots partial sums (one atomic per block,
+// spread over the slots so that no single L2 address serialises them); the consumer -- the next
+// step's kernel -- adds the slots up after the ranks' all-reduce.
+constexpr int kSumsqSlots = 32;
+
 template <typename T, typename P>
 __global__ void __launch_bounds__(kBlock)
 sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
                     const P *__restrict__ slice_ptr, int n_slices, int n_rows,
-                    const T *__restrict__ scale2, PeerDst<T> dst, int n_dst, long long dst_offset)
+                    const T *__restrict__ scale2, T *__restrict__ sumsq_out, PeerDst<T> dst, int n_dst,
+                    long long dst_offset)
 {
+    __shared__ T warp_sq[kBlock / 32];
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    if (slice >= n_slices) return;
-    const long long chunk_base = slice_ptr[slice];
-    const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
-    const int *ip = idx + chunk_base;
-    const T *dp = data + chunk_base;
+    const bool active = slice < n_slices;  // no early return: the block reduces ||y||^2 together
+    // 1/||x||: one coalesced load of the 32 partial sums per warp, folded with shuffles
+    T alpha = 1;
+    if (scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
     T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    if (active) {
+        const long long chunk_base = slice_ptr[slice];
+        const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
+        const int *ip = idx + chunk_base;
+        const T *dp = data + chunk_base;
 #pragma unroll 4
-    for (long long g = lane; g < n_groups; g += 32) {
-        IVec4 c;
-        Vec4<T> v;
-        c.load(ip + (g << 2));
-        v.load(dp + (g << 2));
-        acc0 += v.v[0] * ld_x(x, c.v[0]);
-        acc1 += v.v[1] * ld_x(x, c.v[1]);
-        acc2 += v.v[2] * ld_x(x, c.v[2]);
-        acc3 += v.v[3] * ld_x(x, c.v[3]);
+        for (long long g = lane; g < n_groups; g += 32) {
+            IVec4 c;
+            Vec4<T> v;
+            c.load(ip + (g << 2));
+            v.load(dp + (g << 2));
+            acc0 += v.v[0] * ld_x(x, c.v[0]);
+            acc1 += v.v[1] * ld_x(x, c.v[1]);
+            acc2 += v.v[2] * ld_x(x, c.v[2]);
+            acc3 += v.v[3] * ld_x(x, c.v[3]);
+        }
     }
 #pragma unroll
     for (int off = 8; off <= 16; off <<= 1) {
@@ -144,15 +156,41 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
         acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
         acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
     }
-    if (lane < 8) {
-        const T alpha = scale2 ? rsqrt(*scale2) : T(1);
-        const long long r = slice * 32 + lane * 4;
-        const T a[4] = {acc0 * alpha, acc1 * alpha, acc2 * alpha, acc3 * alpha};
-        for (int d = 0; d < n_dst; ++d) {
-            T *out = dst.p[d] + dst_offset + r;
+    // lanes 0-7 hold rows 4L..4L+3; re-deal them so that lane j < 16 holds rows 2j, 2j+1: the warp
+    // then writes its 32 results as ONE contiguous 256-byte store per destination (full NVLink
+    // packets instead of 32 scattered 8-byte writes)
+    const int src = lane >> 1;
+    const T b0 = __shfl_sync(0xffffffffu, acc0, src), b1 = __shfl_sync(0xffffffffu, acc1, src);
+    const T b2 = __shfl_sync(0xffffffffu, acc2, src), b3 = __shfl_sync(0xffffffffu, acc3, src);
+    T sq = 0;
+    if (active && lane < 16) {
+        const T lo = ((lane & 1) ? b2 : b0) * alpha, hi = ((lane & 1) ? b3 : b1) * alpha;
+        const long long r = slice * 32 + lane * 2;
+        if (r < n_rows) sq += lo * lo;
+        if (r + 1 < n_rows) sq += hi * hi;
+        // fully unrolled with a static index: dst lives in the constant bank; a runtime-indexed
+        // loop would copy the whole struct to local memory in every thread (ncu: +70 % instructions)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (r + k < n_rows) out[k] = a[k];
+        for (int d = 0; d < kMaxPeers; ++d) {
+            if (d < n_dst) {
+                T *out = dst.p[d] + dst_offset + r;
+                if (r + 1 < n_rows) {
+                    *reinterpret_cast<double2 *>(out) = make_double2(lo, hi);
+                } else if (r < n_rows) {
+                    out[0] = lo;
+                }
+            }
+        }
+    }
+    if (sumsq_out) {
+        sq = subwarp_sum<32>(sq);
+        if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T total = 0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) total += warp_sq[w];
+            atomicAdd(sumsq_out + (blockIdx.x & (kSumsqSlots - 1)), total);
         }
     }
 }
@@ -402,7 +440,7 @@ int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, c
 
 int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                              const int *row_indices, int chunk, int n_slices, int n_rows,
-                             const double *scale_sumsq, double *const *dst, int n_dst,
+                             const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
                              long long dst_offset)
 {
     B200_ENTER(ctx);
@@ -419,7 +457,7 @@ int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indic
     for (int i = 0; i < kMaxPeers; ++i) d.p[i] = i < n_dst ? dst[i] : nullptr;
     for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
     sell32_bcast_kernel<double, int><<<ceil_div_u((long long)n_slices * 32, kBlock), kBlock, 0, ctx->stream>>>(
-        data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, d, n_dst, dst_offset);
+        data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

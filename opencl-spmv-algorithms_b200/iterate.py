@@ -176,24 +176,30 @@ def power_iteration_fused(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: 
     import torch.distributed as dist
     L = pkg.lib()
     n_local = blocks.bounds(rank)[1] - blocks.bounds(rank)[0]
+    slots = 32  # B200_SUMSQ_SLOTS partial sums of ||y||^2, added up by the consuming kernel
     if acc is None:
-        acc = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(2)]
+        acc = [torch.zeros(slots, dtype=torch.float64, device="cuda") for _ in range(2)]
     assert sell.perm is None and sell.row_indices is not None, "fused path: SELL-32, sigma = 1, int32 pointers"
-    for k in range(first_step, first_step + steps):
+
+    def step(k):
+        """One launch + one tiny all-reduce: memset of the 32 slots, the fused kernel, NCCL."""
         cur, nxt = k % 2, (k + 1) % 2
         scale = acc[(k - 1) % 2].data_ptr() if k > 0 else None
         a = acc[k % 2]
-        a.zero_()
+        pkg.check(L.b200_memset_async(ctx.h, a.data_ptr(), 0, 8 * slots), "b200_memset_async")
         pkg.check(L.b200_spmv_sell_bcast_f64(ctx.h, sell.data.ptr, sell.cols.ptr, bufs.local[cur].ptr,
                                              sell.row_indices.ptr, 32, sell.n_slices, n_local, scale,
-                                             bufs.dst[nxt], bufs.world, rank * blocks.count),
+                                             a.data_ptr(), bufs.dst[nxt], bufs.world, rank * blocks.count),
                   "b200_spmv_sell_bcast_f64")
-        seg_ptr = bufs.local[nxt].ptr + 8 * rank * blocks.count
-        pkg.check(L.b200_sumsq_f64(ctx.h, seg_ptr, n_local, a.data_ptr()), "b200_sumsq_f64")
         if bufs.world > 1:
             dist.all_reduce(a, op=dist.ReduceOp.SUM)  # the norm AND the barrier that orders peer writes
-    last = first_step + steps - 1
-    res = IterationResult(steps, float(acc[last % 2][0]) ** 0.5, bufs.local[(last + 1) % 2])
+
+    k, end = first_step, first_step + steps
+    while k < end:
+        step(k)
+        k += 1
+    last = end - 1
+    res = IterationResult(steps, float(acc[last % 2].sum()) ** 0.5, bufs.local[(last + 1) % 2])
     res.acc = acc
-    res.next_step = last + 1
+    res.next_step = end
     return res
