@@ -21,13 +21,16 @@ namespace {
 constexpr int kBlock = 256;
 
 // dot product of entries [s, e) of (col, data) with x, cooperatively by LPR lanes.
-template <typename T, int LPR>
+template <typename T, int LPR, int U = 2>
 __device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *__restrict__ data,
                                          const T *__restrict__ x, long long s, long long e, int lane)
 {
     T acc = 0;
     const long long g_end = (e + 3) >> 2;
-#pragma unroll 2
+    // U iterations are unrolled so that their 2U vector loads, then their 4U gathers, are in flight
+    // together: U = 2 when many waves of blocks hide latency anyway, U = 4 for small matrices
+    // (at most ~2 waves) where the kernel is a latency chain
+#pragma unroll U
     for (long long g = (s >> 2) + lane; g < g_end; g += LPR) {
         const long long j = g << 2;
         IVec4 c;
@@ -51,7 +54,7 @@ __device__ __forceinline__ T row_dot_scalar(const int *__restrict__ col, const T
     return acc;
 }
 
-template <typename T, int LPR, bool VEC>
+template <typename T, int LPR, bool VEC, int U>
 __global__ void __launch_bounds__(kBlock)
 csr_vector_kernel(const int *__restrict__ ptr, const int *__restrict__ col, const T *__restrict__ data,
                   const T *__restrict__ x, T *__restrict__ y, int n_rows, int long_threshold)
@@ -66,7 +69,7 @@ csr_vector_kernel(const int *__restrict__ ptr, const int *__restrict__ col, cons
     const bool is_long = (e - s) > long_threshold;
     T acc = 0;
     if (!is_long)
-        acc = VEC ? row_dot_vec<T, LPR>(col, data, x, s, e, lane)
+        acc = VEC ? row_dot_vec<T, LPR, U>(col, data, x, s, e, lane)
                   : row_dot_scalar<T, LPR>(col, data, x, s, e, lane);
     acc = subwarp_sum<LPR>(acc);
     // long rows: publish 0 here; csr_long_rows_kernel accumulates into it afterwards
@@ -248,7 +251,7 @@ __global__ void csr_stream_fixup_kernel(T *__restrict__ y, int n_tiles, const in
 }
 
 // row-major ELL (the reference's arrays): row r owns entries [r*K, (r+1)*K)
-template <typename T, int LPR, bool VEC>
+template <typename T, int LPR, bool VEC, int U>
 __global__ void __launch_bounds__(kBlock)
 ell_rowmajor_kernel(const T *__restrict__ data, const int *__restrict__ col, const T *__restrict__ x,
                     T *__restrict__ y, int n_rows, int row_size)
@@ -260,7 +263,7 @@ ell_rowmajor_kernel(const T *__restrict__ data, const int *__restrict__ col, con
         s = row * row_size;
         e = s + row_size;
     }
-    T acc = VEC ? row_dot_vec<T, LPR>(col, data, x, s, e, lane)
+    T acc = VEC ? row_dot_vec<T, LPR, U>(col, data, x, s, e, lane)
                 : row_dot_scalar<T, LPR>(col, data, x, s, e, lane);
     acc = subwarp_sum<LPR>(acc);
     if (lane == 0 && row < n_rows) y[row] = acc;
@@ -451,10 +454,15 @@ int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data,
                    int n_rows, int long_threshold, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    if (vec)
-        csr_vector_kernel<T, LPR, true><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+    // small launch (at most ~2 waves of resident threads): deeper unroll, see row_dot_vec
+    bool deep = (long long)n_rows * LPR <= 2ll * ctx->sm_count * 2048;
+    if (const char *e = getenv("B200_CSR_UNROLL")) deep = atoi(e) >= 4;
+    if (!vec)
+        csr_vector_kernel<T, LPR, false, 2><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+    else if (deep)
+        csr_vector_kernel<T, LPR, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
     else
-        csr_vector_kernel<T, LPR, false><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+        csr_vector_kernel<T, LPR, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -523,10 +531,14 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
                    int row_size, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    if (vec)
-        ell_rowmajor_kernel<T, LPR, true><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+    bool deep = (long long)n_rows * LPR <= 2ll * ctx->sm_count * 2048;
+    if (const char *e = getenv("B200_CSR_UNROLL")) deep = atoi(e) >= 4;
+    if (!vec)
+        ell_rowmajor_kernel<T, LPR, false, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+    else if (deep)
+        ell_rowmajor_kernel<T, LPR, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
     else
-        ell_rowmajor_kernel<T, LPR, false><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+        ell_rowmajor_kernel<T, LPR, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
