@@ -460,14 +460,64 @@ def main():
             t = torch.tensor([e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms, wall_ms = float(t[0]), float(t[1])
-        e2e = {"value": round(flops_step / (e2e_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
+        # the same five calls issued on TWO in-order queues (contexts) of the same device, formats
+        # alternating: PCIe is full duplex, so the y download of one call overlaps the x upload and
+        # kernel of the next.  Wall clock with both queues drained on both sides (events live on one
+        # stream only).
+        ctx2 = pkg.Context(local_rank)
+        hx2, hy2 = C.c_void_p(), C.c_void_p()
+        pkg.check(L.b200_host_alloc_pinned(n_cols * V, C.byref(hx2)), "pinned x2")
+        pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy2)), "pinned y2")
+        C.memmove(hx2, hx, n_cols * V)
+        xin2 = ctx2.empty(n_cols, dtype)
+        queues = [(ctx, xin, hx, hy), (ctx2, xin2, hx2, hy2)]
+        owner = {f: queues[i % 2] for i, f in enumerate(mats)}
+
+        def e2e_step2():
+            for f, m in mats.items():
+                q, xq, hxq, hyq = owner[f]
+                m.ctx = q
+                pkg.check(L.b200_memcpy_h2d_async(q.h, xq.ptr, hxq, n_cols * V), "h2d x")
+                m.spmv(xq, y[f])
+                pkg.check(L.b200_memcpy_d2h_async(q.h, hyq, y[f].ptr, n_rows * V), "d2h y")
+            ctx.sync()
+            ctx2.sync()
+
+        for _ in range(2):
+            e2e_step2()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps_e):
+            e2e_step2()
+        barrier()
+        wall2_ms = (time.perf_counter() - t0) * 1e3 / steps_e
+        for m in mats.values():
+            m.ctx = ctx
+        if dist is not None:
+            import torch
+            t = torch.tensor([wall2_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall2_ms = float(t[0])
+        best_ms = min(e2e_ms, wall2_ms)
+        e2e = {"value": round(flops_step / (best_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
                "h2d_bytes_per_step": int(len(mats) * n_cols * V * world),
                "d2h_bytes_per_step": int(len(mats) * n_rows * V * world),
-               "ms_per_step": round(e2e_ms, 4), "wall_ms_per_step": round(wall_ms, 4), "steps": steps_e,
+               "ms_per_step": round(best_ms, 4), "steps": steps_e,
+               "one_queue": {"ms_per_step": round(e2e_ms, 4), "wall_ms_per_step": round(wall_ms, 4),
+                             "gflops": round(flops_step / (e2e_ms * 1e-3) * 1e-9, 2)},
+               "two_queues": {"wall_ms_per_step": round(wall2_ms, 4),
+                              "gflops": round(flops_step / (wall2_ms * 1e-3) * 1e-9, 2)},
                "what": "per format: pinned-host x -> device, SpMV through the C ABI, y -> pinned host; format "
-                       "arrays uploaded once before the timed region, as the reference driver does (csr.c:183-193)"}
+                       "arrays uploaded once before the timed region, as the reference driver does (csr.c:183-193). "
+                       "value = the better of one in-order queue (CUDA events) and two queues with alternating "
+                       "formats (wall clock, both drained)"}
+        ctx2.sync()
+        del xin2
         L.b200_host_free_pinned(hx)
         L.b200_host_free_pinned(hy)
+        L.b200_host_free_pinned(hx2)
+        L.b200_host_free_pinned(hy2)
+        ctx2.close()
 
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ---------
     cpu = None
