@@ -38,6 +38,27 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FORMATS = ("coo", "csr", "ell", "sell", "cmrs")
+
+# stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version
+# line, the reference's compute_using_cpu printf()s its timing block): everything written to fd 1
+# during the run goes to stderr, and only emit_json() writes to the real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while line:
+        line = line[os.write(fd, line):]
 NOMINAL_HBM_GBS = 8000.0   # BASELINE.json north_star
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -241,6 +262,7 @@ def cpu_arm(n_rows, n_cols, rows, cols, vals, x, dtype, kind, reps, warm):
 
 # --------------------------------------------------------------------------------------------
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -548,7 +570,7 @@ def main():
             "formats": fm, "formats_warm_l2_context_only": warm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(args.steps * len(mats)), "clocks": clk.summary(),
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -704,7 +726,7 @@ def rmat_arm(pkg, args, rank, world, local_rank):
                          "frac": fm["csr"]["frac_measured_rank0"], "traffic": None, "peak_source": peak_src},
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(args.steps * len(names)), "clocks": clk.summary(),
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -839,7 +861,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
             "cpu_baseline": None, "e2e": None,
             "gpu_launches": int(args.steps * 3), "clocks": clk.summary(),
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -879,7 +901,7 @@ def reference_arm(pkg, args, dtype):
                          "wall_s": round(time.perf_counter() - t0, 2)},
         "e2e": {"value": round(value, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
     return 0
 
 
