@@ -1,6 +1,7 @@
 """The five C drivers (host/*.c -> bin/<format>): exit-code contract without a GPU (CPU test) and,
 on the GPU, the reference's stdout contract line by line next to the unmodified reference binary
 (oracle/_ref/bin/<format>, fake OpenCL) run in the same directory on the same files."""
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -43,6 +44,48 @@ def test_no_gpu_exit_code(tmp_path):
         assert p.returncode == 1, (f, p.stdout, p.stderr)
         assert "CPU calculations" not in p.stdout
     assert run(bins / "csr", tmp_path, "--bogus").returncode == 4      # OtherError
+
+
+def test_fast_parallel_parse_equals_fscanf_parse(cant_dir, tmp_path):
+    """The drivers' one-pass, multi-threaded text parse (host/src/driver_common.c: read_entries)
+    must give bit-identical triples to the reference-style fscanf("%d %d %lg") parse -- on a large
+    well-formed file (parallel path) and on files whose entries are NOT one per line (it must notice
+    and fall back to the line-agnostic serial parse)."""
+    import numpy as np
+    bins = build_drivers()
+
+    def parse(path, threads):
+        out = tmp_path / "p.bin"
+        p = subprocess.run([str(bins / "mtx_parse"), str(path), str(out)], capture_output=True, text=True,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+        assert p.returncode == 0, p.stderr
+        n_rows, n_cols, nnz = (int(t) for t in p.stdout.split()[:3])
+        raw = out.read_bytes()
+        rows = np.frombuffer(raw, np.int32, nnz, 0)
+        cols = np.frombuffer(raw, np.int32, nnz, 4 * nnz)
+        vals = np.frombuffer(raw, np.float64, nnz, 8 * nnz)
+        return n_rows, n_cols, rows, cols, vals
+
+    big = cant_dir / "databases" / "cant.mtx"
+    ref = O.read_mtx(big)
+    for threads in (1, 8):
+        got = parse(big, threads)
+        assert got[:2] == ref[:2]
+        for a, b in zip(got[2:], ref[2:]):
+            assert a.tobytes() == b.tobytes()
+    # entries wrapped over lines / several per line: legal for fscanf, so legal here
+    n = 40000
+    rng = np.random.default_rng(0)
+    r, c, v = rng.integers(1, 500, n), rng.integers(1, 500, n), np.round(rng.uniform(-9, 9, n), 7)
+    weird = tmp_path / "weird.mtx"
+    with open(weird, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% odd but scanf-legal layout\n\n500 500 %d\n" % n)
+        for i in range(0, n, 2):
+            f.write(f"{r[i]} {c[i]}\n{v[i]!r} {r[i + 1]} {c[i + 1]} {v[i + 1]!r}\n")
+    ref = O.read_mtx(weird)
+    got = parse(weird, 8)
+    for a, b in zip(got[2:], ref[2:]):
+        assert a.tobytes() == b.tobytes()
 
 
 TIMING = re.compile(r"^(Your calculations took|Number of operations \d+, PERFORMANCE|GBytes transferred)")
