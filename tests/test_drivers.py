@@ -79,7 +79,7 @@ def test_fast_parallel_parse_equals_fscanf_parse(cant_dir, tmp_path):
     r, c, v = rng.integers(1, 500, n), rng.integers(1, 500, n), np.round(rng.uniform(-9, 9, n), 7)
     weird = tmp_path / "weird.mtx"
     with open(weird, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n% odd but scanf-legal layout\n\n500 500 %d\n" % n)
+        f.write("%%MatrixMarket matrix coordinate real general\n% odd but scanf-legal layout\n\n" + f"500 500 {n}\n")
         for i in range(0, n, 2):
             f.write(f"{r[i]} {c[i]}\n{v[i]!r} {r[i + 1]} {c[i + 1]} {v[i + 1]!r}\n")
     ref = O.read_mtx(weird)
