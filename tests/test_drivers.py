@@ -81,7 +81,7 @@ def test_fast_parallel_parse_equals_fscanf_parse(cant_dir, tmp_path):
     with open(weird, "w") as f:
         f.write("%%MatrixMarket matrix coordinate real general\n% odd but scanf-legal layout\n\n" + f"500 500 {n}\n")
         for i in range(0, n, 2):
-            f.write(f"{r[i]} {c[i]}\n{v[i]!r} {r[i + 1]} {c[i + 1]} {v[i + 1]!r}\n")
+            f.write(f"{r[i]} {c[i]}\n{float(v[i])!r} {r[i + 1]} {c[i + 1]} {float(v[i + 1])!r}\n")
     ref = O.read_mtx(weird)
     got = parse(weird, 8)
     for a, b in zip(got[2:], ref[2:]):
