@@ -176,12 +176,17 @@ int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, c
  * kernels/Cmrs.cl:1, args cmrs.c:197-205.  `n_rows` bounds the store of the last strip (the
  * reference writes height outputs per strip unconditionally, Cmrs.cl:38-41, quirk q5).
  * height <= 32. */
+typedef struct b200_cmrs_plan b200_cmrs_plan; /* strips longer than 8192 entries (power-law hubs) are
+                                               * split over several warps; NULL = never split */
+int b200_cmrs_plan_create(b200_ctx *ctx, const int *strip_ptr, int n_strips, b200_cmrs_plan **plan);
+int b200_cmrs_plan_extra_items(const b200_cmrs_plan *plan, int *n_items);
+int b200_cmrs_plan_destroy(b200_cmrs_plan *plan);
 int b200_spmv_cmrs_f64(b200_ctx *ctx, const double *data, const int *indices, const int *strip_ptr,
                        const int *row_in_strip, const double *vect, double *output, int n_strips,
-                       int height, int n_rows);
+                       int height, int n_rows, const b200_cmrs_plan *plan);
 int b200_spmv_cmrs_f32(b200_ctx *ctx, const float *data, const int *indices, const int *strip_ptr,
                        const int *row_in_strip, const float *vect, float *output, int n_strips,
-                       int height, int n_rows);
+                       int height, int n_rows, const b200_cmrs_plan *plan);
 
 /* =====================================================================================
  * Format builds on the GPU (new; in the reference they are host loops inlined in each main()).

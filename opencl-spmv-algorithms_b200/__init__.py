@@ -90,8 +90,11 @@ SIGNATURES = {
     "b200_spmv_sell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b200_spmv_sell64_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b200_spmv_sell64_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "b200_spmv_cmrs_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
-    "b200_spmv_cmrs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "b200_cmrs_plan_create": (_i, [_vp, _vp, _i, _vpp]),
+    "b200_cmrs_plan_extra_items": (_i, [_vp, C.POINTER(_i)]),
+    "b200_cmrs_plan_destroy": (_i, [_vp]),
+    "b200_spmv_cmrs_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_spmv_cmrs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_check_sorted_rows": (_i, [_vp, _vp, _i, _i]),
     "b200_build_csr_ptr": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200_row_length_stats": (_i, [_vp, _vp, _i, C.POINTER(RowStats)]),

@@ -42,20 +42,35 @@ __device__ __forceinline__ void cmrs_flush(T (&acc)[HMAX], int key, T sum)
 }
 
 // HMAX = accumulator registers per lane (8 or 32); height <= HMAX at run time
-template <typename T, int HMAX, bool VEC, int U>
+// cap > 0 (a plan found strips longer than `cap` entries -- power-law inputs, where a strip holding
+// a hub row has 10^5 entries): the main pass (EXTRA = false) walks only the first `cap` entries of
+// each strip and stores; the extra pass (EXTRA = true) has one warp per (strip, segment) work item
+// of the plan and accumulates with atomics.
+template <typename T, int HMAX, bool VEC, int U, bool EXTRA>
 __global__ void __launch_bounds__(kBlock)
 cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *__restrict__ strip_ptr,
             const int *__restrict__ row_in_strip, const T *__restrict__ x, T *__restrict__ y,
-            int n_strips, int height, int n_rows)
+            int n_work, int height, int n_rows, int cap, const int2 *__restrict__ items)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long strip = (long long)blockIdx.x * kWarps + warp;
-    if (strip >= n_strips) return;  // whole warps leave together
+    const long long work = (long long)blockIdx.x * kWarps + warp;
+    if (work >= n_work) return;  // whole warps leave together
+    long long strip = work;
+    int seg = 0;
+    if (EXTRA) {
+        const int2 it = items[work];
+        strip = it.x;
+        seg = it.y;
+    }
     T acc[HMAX];
 #pragma unroll
     for (int h = 0; h < HMAX; ++h) acc[h] = 0;
 
-    const int s = __ldg(strip_ptr + strip), e = __ldg(strip_ptr + strip + 1);
+    int s = __ldg(strip_ptr + strip), e = __ldg(strip_ptr + strip + 1);
+    if (cap > 0) {
+        s = min(s + seg * cap, e);
+        e = min(s + cap, e);
+    }
     const int span = ((e - s + kSubWarps - 1) / kSubWarps + 3) & ~3;  // multiple of 4 entries
     const int ss = min(s + (lane >> 2) * span, e), ee = min(ss + span, e);
     int cur = -1;
@@ -136,7 +151,25 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
 #pragma unroll
     for (int off = HMAX; off < 32; off <<= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
     const long long row = strip * height + lane;
-    if (lane < height && row < n_rows) y[row] = total;
+    if (lane < height && row < n_rows) {
+        if (EXTRA) atomicAdd(y + row, total);
+        else y[row] = total;
+    }
+}
+
+constexpr int kCmrsCap = 8192;  // entries per (strip, segment) work item
+
+__global__ void cmrs_long_items_kernel(const int *__restrict__ strip_ptr, int n_strips, int cap,
+                                       int *counter, int2 *items)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_strips) return;
+    const int len = strip_ptr[t + 1] - strip_ptr[t];
+    const int extra = (len + cap - 1) / cap - 1;
+    if (extra <= 0) return;
+    const int at = atomicAdd(counter, extra);
+    if (items)
+        for (int k = 0; k < extra; ++k) items[at + k] = make_int2((int)t, k + 1);
 }
 
 template <typename T, bool VEC, int U>
@@ -220,9 +253,22 @@ coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__
     if (tail && cur >= 0) atomicAdd(y + cur, sum);
 }
 
+}  // namespace
+
+struct b200_cmrs_plan {
+    int device;
+    int n_strips;
+    int n_items;  // extra (strip, segment) work items
+    int cap;
+    int2 *items;  // device
+};
+
+namespace {
+
 template <typename T>
 int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *strip_ptr,
-                   const int *row_in_strip, const T *x, T *y, int n_strips, int height, int n_rows)
+                   const int *row_in_strip, const T *x, T *y, int n_strips, int height, int n_rows,
+                   const b200_cmrs_plan *plan)
 {
     B200_ENTER(ctx);
     B200_REQUIRE(strip_ptr && x && y && n_strips >= 0 && n_rows >= 0, "bad argument");
@@ -230,23 +276,28 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
         b200_set_error("CMRS height must be in 1..32, got %d", height);
         return B200_ERR_UNSUPPORTED;
     }
+    B200_REQUIRE(!plan || plan->n_strips == n_strips, "plan was built for a different matrix");
     if (n_strips == 0) return B200_SUCCESS;
     const bool vec = aligned16(data) && aligned16(idx) && aligned16(row_in_strip);
-    unsigned blocks = ceil_div_u(n_strips, kWarps);
+    const int n_items = plan ? plan->n_items : 0;
+    const int cap = n_items > 0 ? plan->cap : 0;
+    const int2 *items = n_items > 0 ? plan->items : nullptr;
     // U = groups loaded per lane and round trip.  Measured on B200 (profiles/): fp32 wants 2, fp64 1
     // (register pressure); tuning hook B200_CMRS_U=1|2
     int u = sizeof(T) == 4 ? 2 : 1;
     if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
-#define B200_CMRS_LAUNCH(H, V)                                                                        \
-    do {                                                                                              \
-        if (u == 2)                                                                                   \
-            cmrs_kernel<T, H, V, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, strip_ptr,         \
-                                                                        row_in_strip, x, y, n_strips, \
-                                                                        height, n_rows);              \
-        else                                                                                          \
-            cmrs_kernel<T, H, V, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, strip_ptr,         \
-                                                                        row_in_strip, x, y, n_strips, \
-                                                                        height, n_rows);              \
+#define B200_CMRS_LAUNCH2(H, V, UU)                                                                         \
+    do {                                                                                                    \
+        cmrs_kernel<T, H, V, UU, false><<<ceil_div_u(n_strips, kWarps), kBlock, 0, ctx->stream>>>(           \
+            data, idx, strip_ptr, row_in_strip, x, y, n_strips, height, n_rows, cap, nullptr);              \
+        if (n_items > 0)                                                                                    \
+            cmrs_kernel<T, H, V, UU, true><<<ceil_div_u(n_items, kWarps), kBlock, 0, ctx->stream>>>(         \
+                data, idx, strip_ptr, row_in_strip, x, y, n_items, height, n_rows, cap, items);             \
+    } while (0)
+#define B200_CMRS_LAUNCH(H, V)             \
+    do {                                   \
+        if (u == 2) B200_CMRS_LAUNCH2(H, V, 2); \
+        else B200_CMRS_LAUNCH2(H, V, 1);   \
     } while (0)
     if (height <= 8) {
         if (vec) B200_CMRS_LAUNCH(8, true);
@@ -256,6 +307,7 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
         else B200_CMRS_LAUNCH(32, false);
     }
 #undef B200_CMRS_LAUNCH
+#undef B200_CMRS_LAUNCH2
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -286,17 +338,73 @@ int spmv_coo_impl(b200_ctx *ctx, const int *row, const int *col, const T *data, 
 
 extern "C" {
 
+int b200_cmrs_plan_create(b200_ctx *ctx, const int *strip_ptr, int n_strips, b200_cmrs_plan **plan)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(strip_ptr && plan && n_strips >= 0, "bad argument");
+    *plan = nullptr;
+    b200_cmrs_plan *p = new b200_cmrs_plan();
+    p->device = ctx->device;
+    p->n_strips = n_strips;
+    p->n_items = 0;
+    p->cap = kCmrsCap;
+    p->items = nullptr;
+    if (n_strips > 0) {
+        int *counter = ctx->scratch + 224;
+        const unsigned blocks = ceil_div_u(n_strips, 256);
+        int count = 0;
+        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+        cmrs_long_items_kernel<<<blocks, 256, 0, ctx->stream>>>(strip_ptr, n_strips, p->cap, counter, nullptr);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&count, counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess && count > 0) {
+            e = cudaMalloc(&p->items, sizeof(int2) * (size_t)count);
+            if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+            if (e == cudaSuccess) {
+                cmrs_long_items_kernel<<<blocks, 256, 0, ctx->stream>>>(strip_ptr, n_strips, p->cap, counter, p->items);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+        if (e != cudaSuccess) {
+            if (p->items) cudaFree(p->items);
+            delete p;
+            return b200_cuda_fail(e, "cmrs plan", __FILE__, __LINE__);
+        }
+        p->n_items = count;
+    }
+    *plan = p;
+    return B200_SUCCESS;
+}
+
+int b200_cmrs_plan_extra_items(const b200_cmrs_plan *plan, int *n_items)
+{
+    B200_REQUIRE(plan && n_items, "null argument");
+    *n_items = plan->n_items;
+    return B200_SUCCESS;
+}
+
+int b200_cmrs_plan_destroy(b200_cmrs_plan *plan)
+{
+    if (!plan) return B200_SUCCESS;
+    cudaSetDevice(plan->device);
+    if (plan->items) cudaFree(plan->items);
+    delete plan;
+    return B200_SUCCESS;
+}
+
 int b200_spmv_cmrs_f64(b200_ctx *ctx, const double *data, const int *indices, const int *strip_ptr,
                        const int *row_in_strip, const double *vect, double *output, int n_strips,
-                       int height, int n_rows)
+                       int height, int n_rows, const b200_cmrs_plan *plan)
 {
-    return spmv_cmrs_impl<double>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows);
+    return spmv_cmrs_impl<double>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows, plan);
 }
 int b200_spmv_cmrs_f32(b200_ctx *ctx, const float *data, const int *indices, const int *strip_ptr,
                        const int *row_in_strip, const float *vect, float *output, int n_strips,
-                       int height, int n_rows)
+                       int height, int n_rows, const b200_cmrs_plan *plan)
 {
-    return spmv_cmrs_impl<float>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows);
+    return spmv_cmrs_impl<float>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows, plan);
 }
 int b200_spmv_coo_f64(b200_ctx *ctx, const int *row, const int *col, const double *data,
                       const double *vect, double *output, int nnz, int n_rows)

@@ -253,11 +253,34 @@ class CmrsMatrix:
               "b200_build_cmrs")
         self.cols = csr.cols
 
-    def spmv(self, x: DeviceArray, y: DeviceArray) -> None:
+    def plan(self):
+        """Long-strip work list (only non-trivial on power-law inputs)."""
+        if getattr(self, "_plan", None) is None:
+            p = C.c_void_p()
+            check(lib().b200_cmrs_plan_create(self.ctx.h, self.strip_ptr.ptr, self.n_strips, C.byref(p)),
+                  "b200_cmrs_plan_create")
+            self._plan = p
+        return self._plan
+
+    def plan_extra_items(self) -> int:
+        n = C.c_int(0)
+        check(lib().b200_cmrs_plan_extra_items(self.plan(), C.byref(n)), "b200_cmrs_plan_extra_items")
+        return n.value
+
+    def spmv(self, x: DeviceArray, y: DeviceArray, use_plan: bool = True) -> None:
         v = self.csr.coo.values(x.dtype)
         fn = getattr(lib(), "b200_spmv_cmrs_" + suffix(x.dtype))
         check(fn(self.ctx.h, v.ptr, self.cols.ptr, self.strip_ptr.ptr, self.row_in_strip.ptr,
-                 x.ptr, y.ptr, self.n_strips, self.height, self.n_rows), "b200_spmv_cmrs")
+                 x.ptr, y.ptr, self.n_strips, self.height, self.n_rows,
+                 self.plan() if use_plan else None), "b200_spmv_cmrs")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                lib().b200_cmrs_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
 
     def nbytes(self, dtype) -> int:
         V = np.dtype(dtype).itemsize

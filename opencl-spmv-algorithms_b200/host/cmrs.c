@@ -52,11 +52,14 @@ int main(int argc, char *argv[])
     (opt.use_f32 ? b200_spmv_cmrs_f32(ctx, (const float *)buffer_data, (const int *)d.cols,             \
                                       (const int *)buffer_strip_ptr, (const int *)buffer_row_in_strip,  \
                                       (const float *)d.vect, (float *)buffer_output, number_of_strips,  \
-                                      height, number_of_rows)                                           \
+                                      height, number_of_rows, plan)                                     \
                  : b200_spmv_cmrs_f64(ctx, (const double *)buffer_data, (const int *)d.cols,            \
                                       (const int *)buffer_strip_ptr, (const int *)buffer_row_in_strip,  \
                                       (const double *)d.vect, (double *)buffer_output, number_of_strips, \
-                                      height, number_of_rows))
+                                      height, number_of_rows, plan))
+    /* long-strip work list (empty for FEM-like inputs) */
+    b200_cmrs_plan *plan = NULL;
+    B200_TRY(b200_cmrs_plan_create(ctx, (const int *)buffer_strip_ptr, number_of_strips, &plan));
 
     /* run program */
     B200_TRY(LAUNCH());
@@ -94,6 +97,7 @@ int main(int argc, char *argv[])
     }
 
     /* release memory */
+    b200_cmrs_plan_destroy(plan);
     if (buffer_data != d.data64) b200_free(ctx, buffer_data);
     b200_free(ctx, buffer_ptr);
     b200_free(ctx, buffer_strip_ptr);

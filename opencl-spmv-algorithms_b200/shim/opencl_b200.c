@@ -290,7 +290,7 @@ cl_int clEnqueueNDRangeKernel(cl_command_queue q, cl_kernel k, cl_uint work_dim,
         status = b200_spmv_cmrs_f64(ctx, (const double *)ARG_MEM(0), (const int *)ARG_MEM(1),
                                     (const int *)ARG_MEM(2), (const int *)ARG_MEM(3),
                                     (const double *)ARG_MEM(4), (double *)ARG_MEM(5), k->ival[6],
-                                    k->ival[7], (int)(k->mem[5]->size / sizeof(double)));
+                                    k->ival[7], (int)(k->mem[5]->size / sizeof(double)), NULL);
     } else {
         return CL_INVALID_KERNEL_NAME;
     }

@@ -169,7 +169,7 @@ def test_bad_arguments_fail_loudly(ctx):
     L = pkg.lib()
     x = ctx.zeros(8, np.float64)
     assert L.b200_spmv_sell_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 16, 1, 8, None, None) == pkg.ERR_UNSUPPORTED
-    assert L.b200_spmv_cmrs_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, 64, 8) == pkg.ERR_UNSUPPORTED
+    assert L.b200_spmv_cmrs_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, 64, 8, None) == pkg.ERR_UNSUPPORTED
     assert L.b200_spmv_ellcm_f64(ctx.h, x.ptr, x.ptr, x.ptr, x.ptr, 8, 1, 8) == pkg.ERR_INVALID_VALUE
     assert L.b200_spmv_csr_f64(None, x.ptr, x.ptr, x.ptr, x.ptr, x.ptr, 1, None) == pkg.ERR_INVALID_VALUE
     assert b"null context" in L.b200_last_error()
@@ -201,7 +201,7 @@ def test_unaligned_arrays_take_the_scalar_kernels(ctx, dtype):
     sp_d, ris_d = ctx.array(sp), ctx.array(pad(ris, np.int32))
     yd = ctx.array(np.full(n_rows, np.nan, dtype))
     pkg.check(getattr(L, "b200_spmv_cmrs_" + suf)(ctx.h, vals_d.ptr + V, cols_d.ptr + 4, sp_d.ptr, ris_d.ptr + 4,
-                                                  xd.ptr, yd.ptr, len(sp) - 1, 8, n_rows), "cmrs")
+                                                  xd.ptr, yd.ptr, len(sp) - 1, 8, n_rows, None), "cmrs")
     check_y("cmrs-unaligned", yd.download(), y_ref, dtype)
     ri, sc, sd = O.build_sell(n_rows, rows, cols, vals)
     sc_d, sd_d, ri_d = ctx.array(pad(sc, np.int32)), ctx.array(pad(sd, dtype)), ctx.array(ri)
@@ -247,6 +247,26 @@ def test_csr_stream_kernel(ctx, dtype, monkeypatch):
     y2 = ctx.array(np.full(n_rows, np.nan, dtype))
     csr2.spmv(ctx.array(x.astype(dtype)), y2)
     check_y("csr-vector", y2.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cmrs_long_strips(ctx, dtype):
+    """Strips longer than 8192 entries (a hub row of a power-law matrix) are split over several
+    warps by the CMRS plan; with and without the plan the answer is the oracle's."""
+    n_rows, n_cols = 600, 70000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 10, 71,
+                                            long_rows=((3, 40000), (4, 9000), (333, 20000), (599, 8193)))
+    x = np.random.default_rng(4).uniform(-1, 1, n_cols)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    m = pkg.CmrsMatrix(pkg.CsrMatrix(coo))
+    # strip 0 (~49 000 entries) -> 5 extra segments, strip 41 (~20 000) -> 2, strip 74 (~8 230) -> 1
+    assert m.plan_extra_items() == 8
+    xd = ctx.array(x.astype(dtype))
+    for use_plan in (True, False):
+        yd = ctx.array(np.full(n_rows, np.nan, dtype))
+        m.spmv(xd, yd, use_plan=use_plan)
+        check_y(f"cmrs-long-plan{use_plan}", yd.download(), y_ref, dtype)
 
 
 @pytest.mark.parametrize("height", [1, 2, 5, 8, 16, 32])

@@ -177,6 +177,8 @@ def test_rmat_generator_and_formats(ctx):
         # hub chunks (> 256 columns) are split over many warps by the SELL plan; without the plan
         # one warp walks the whole chunk -- same answer
         assert mats["sell1"].plan_extra_items() > 0 and mats[f"sell{n}"].plan_extra_items() > 0
+        # ... and so are CMRS strips longer than 8192 entries (none at this scale: forced in
+        # test_cmrs_long_strips)
         yd = ctx.array(np.full(n, np.nan, dtype))
         mats["sell64"].spmv(xd, yd, use_plan=False)
         assert O.rel_maxnorm(yd.download(), y_ref) <= tol
