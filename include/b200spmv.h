@@ -89,6 +89,20 @@ int b200_event_record(b200_ctx *ctx, b200_event *ev);
 int b200_event_elapsed_ms(b200_event *start, b200_event *stop, float *ms); /* waits for `stop` */
 int b200_event_destroy(b200_event *ev);
 
+/* ---- launch graphs (new).  The reference issues ONE clEnqueueNDRangeKernel per program run
+ *      (csr.c:201) and never loops; callers that do loop -- the iterated mode, a sweep over several
+ *      matrices -- pay more host time per launch than a cant-sized SpMV lasts on the device (~10 us).
+ *      Every launch / async copy / memset issued on `ctx` between begin and end is recorded into a
+ *      CUDA graph instead of being executed (the nearest OpenCL notion is cl_khr_command_buffer);
+ *      b200_graph_launch replays the whole sequence, in order, with a single call.  Calls that
+ *      synchronise or allocate (SpMV entry points with plan == NULL, *_plan_create, b200_malloc,
+ *      b200_memcpy_d2h, b200_sync) are not allowed while recording and fail with B200_ERR_CUDA. ---- */
+typedef struct b200_graph b200_graph;
+int b200_graph_begin(b200_ctx *ctx);
+int b200_graph_end(b200_ctx *ctx, b200_graph **graph);
+int b200_graph_launch(b200_ctx *ctx, b200_graph *graph);
+int b200_graph_destroy(b200_graph *graph);
+
 /* =====================================================================================
  * SpMV launches.  One entry per format x dtype; argument order = the order the reference
  * driver sets with clSetKernelArg, followed by what the OpenCL kernel took from its launch

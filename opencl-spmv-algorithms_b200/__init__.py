@@ -71,6 +71,10 @@ SIGNATURES = {
     "b200_event_record": (_i, [_vp, _vp]),
     "b200_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
     "b200_event_destroy": (_i, [_vp]),
+    "b200_graph_begin": (_i, [_vp]),
+    "b200_graph_end": (_i, [_vp, _vpp]),
+    "b200_graph_launch": (_i, [_vp, _vp]),
+    "b200_graph_destroy": (_i, [_vp]),
     "b200_csr_plan_create": (_i, [_vp, _vp, _i, _vpp]),
     "b200_csr_plan_get_info": (_i, [_vp, C.POINTER(CsrPlanInfo)]),
     "b200_csr_plan_destroy": (_i, [_vp]),
@@ -259,10 +263,46 @@ class Context:
     def event(self) -> "Event":
         return Event(self)
 
+    def record_graph(self) -> "GraphRecorder":
+        """`with ctx.record_graph() as g: ...launches...` records them instead of running them;
+        afterwards `g.launch()` replays the sequence with one call (b200_graph_*)."""
+        return GraphRecorder(self)
+
     def close(self) -> None:
         if self.h:
             lib().b200_ctx_destroy(self.h)
             self.h = None
+
+
+class GraphRecorder:
+    """A recorded launch sequence (CUDA graph) on one context."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.h = ctx, None
+
+    def __enter__(self) -> "GraphRecorder":
+        check(lib().b200_graph_begin(self.ctx.h), "b200_graph_begin")
+        return self
+
+    def __exit__(self, exc_type, exc, tb) -> None:
+        h = C.c_void_p()
+        status = lib().b200_graph_end(self.ctx.h, C.byref(h))  # always end the capture
+        if exc_type is None:
+            check(status, "b200_graph_end")
+            self.h = h
+        elif status == SUCCESS:
+            lib().b200_graph_destroy(h)
+
+    def launch(self) -> None:
+        check(lib().b200_graph_launch(self.ctx.h, self.h), "b200_graph_launch")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().b200_graph_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 class Event:

@@ -20,7 +20,11 @@ struct b200_ctx {
     int max_persist_l2;
     int *scratch;          // small device scratch (flags / counters), 4 KiB
     void *host_scratch;    // pinned, 4 KiB, for small readbacks
+    bool watch_flag;       // a bulk-copy kernel ran since the last sync: b200_sync reads kWatchFlag
 };
+// scratch[kWatchFlag]: set by a kernel whose mbarrier wait ran into its spin limit (never expected;
+// reported by the next b200_sync / b200_memcpy_d2h instead of hanging the device)
+constexpr int kWatchFlag = 512;
 
 struct b200_event {
     cudaEvent_t ev;
@@ -93,30 +97,74 @@ struct Vec4;
 template <>
 struct Vec4<float> {
     float v[4];
+    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = v[3] = 0.f; }
     __device__ __forceinline__ void load(const float *p)
     {
         float4 t = ld_stream(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void load_shared(const float *p)  // p in shared memory, 16-byte aligned
+    {
+        float4 t = *reinterpret_cast<const float4 *>(p);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 };
 template <>
 struct Vec4<double> {
     double v[4];
+    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = v[3] = 0.0; }
     __device__ __forceinline__ void load(const double *p)
     {
         double2 a = ld_stream(reinterpret_cast<const double2 *>(p));
         double2 b = ld_stream(reinterpret_cast<const double2 *>(p) + 1);
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     }
+    __device__ __forceinline__ void load_shared(const double *p)
+    {
+        double2 a = *reinterpret_cast<const double2 *>(p);
+        double2 b = *(reinterpret_cast<const double2 *>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
 };
 struct IVec4 {
     int v[4];
+    __device__ __forceinline__ void zero() { v[0] = v[1] = v[2] = v[3] = 0; }
     __device__ __forceinline__ void load(const int *p)
     {
         int4 t = ld_stream(reinterpret_cast<const int4 *>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
+    __device__ __forceinline__ void load_shared(const int *p)
+    {
+        int4 t = *reinterpret_cast<const int4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
 };
+
+// Load batching.  The kernels issue U groups of matrix loads, then the x gathers, then the FMAs.
+// ptxas, left alone, sinks the later loads of a batch below the first gathers (fewer live
+// registers), and the in-order warp then sits out a full memory latency before those loads are even
+// issued.  batch_hold() returns a value that is 0 at run time -- column indices are >= 0, so the
+// sign bit of (index & value bits) is clear -- but data-dependent on every load of the batch; adding
+// it to the gather indices pins the schedule to "all loads, then all gathers" (checked with
+// cuobjdump -sass).  Groups that were not loaded must have c zeroed.
+__device__ __forceinline__ int hold_bits(const IVec4 &c, const Vec4<float> &v)
+{
+    return c.v[0] & __float_as_int(v.v[0]);
+}
+__device__ __forceinline__ int hold_bits(const IVec4 &c, const Vec4<double> &v)
+{
+    return c.v[0] & __double2hiint(v.v[0]) & __double2hiint(v.v[2]);
+}
+template <int U, typename T>
+__device__ __forceinline__ int batch_hold(const IVec4 (&c)[U], const Vec4<T> (&v)[U])
+{
+    if (U == 1) return 0;
+    int h = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) h |= hold_bits(c[u], v[u]);
+    return h >> 31;
+}
 
 template <int LANES, typename T>
 __device__ __forceinline__ T subwarp_sum(T v)

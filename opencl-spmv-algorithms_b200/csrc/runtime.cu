@@ -101,6 +101,7 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool own, b200_ctx *
     c->stream = stream;
     c->scratch = nullptr;
     c->host_scratch = nullptr;
+    c->watch_flag = false;
     if (own) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -112,6 +113,7 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool own, b200_ctx *
     cudaDeviceGetAttribute(&c->l2_bytes, cudaDevAttrL2CacheSize, device);
     cudaDeviceGetAttribute(&c->max_persist_l2, cudaDevAttrMaxPersistingL2CacheSize, device);
     cudaError_t e = cudaMalloc(&c->scratch, 4096);
+    if (e == cudaSuccess) e = cudaMemset(c->scratch, 0, 4096);
     if (e == cudaSuccess) e = cudaMallocHost(&c->host_scratch, 4096);
     if (e != cudaSuccess) {
         if (c->scratch) cudaFree(c->scratch);
@@ -175,6 +177,8 @@ int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes)
     return B200_SUCCESS;
 }
 
+static int check_watch_flag(b200_ctx *ctx);
+
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
 {
     B200_ENTER(ctx);
@@ -204,7 +208,7 @@ int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
     B200_ENTER(ctx);
     if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    return B200_SUCCESS;
+    return check_watch_flag(ctx);
 }
 
 int b200_memcpy_d2h_async(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
@@ -228,11 +232,27 @@ int b200_memset_async(b200_ctx *ctx, void *dst, int byte_value, size_t bytes)
     return B200_SUCCESS;
 }
 
+// after a stream sync: did a bulk-copy kernel give up on an mbarrier wait?
+static int check_watch_flag(b200_ctx *ctx)
+{
+    if (!ctx->watch_flag) return B200_SUCCESS;
+    ctx->watch_flag = false;
+    int *h = static_cast<int *>(ctx->host_scratch);
+    B200_CUDA(cudaMemcpyAsync(h, ctx->scratch + kWatchFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*h != 0) {
+        cudaMemsetAsync(ctx->scratch + kWatchFlag, 0, sizeof(int), ctx->stream);
+        b200_set_error("a bulk-copy (TMA) kernel timed out waiting for its data: results are invalid");
+        return B200_ERR_CUDA;
+    }
+    return B200_SUCCESS;
+}
+
 int b200_sync(b200_ctx *ctx)
 {
     B200_ENTER(ctx);
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    return B200_SUCCESS;
+    return check_watch_flag(ctx);
 }
 
 int b200_host_alloc_pinned(size_t bytes, void **hptr)
@@ -278,6 +298,62 @@ int b200_event_elapsed_ms(b200_event *start, b200_event *stop, float *ms)
     B200_CUDA(cudaSetDevice(stop->device));
     B200_CUDA(cudaEventSynchronize(stop->ev));
     B200_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    return B200_SUCCESS;
+}
+
+// ---- launch graphs: record a sequence of launches once, replay it with one call ----------------
+// A cant-sized SpMV lasts ~10 us, less than the host needs to issue it; a solver loop or a
+// rotation over several matrices is therefore captured into a CUDA graph and replayed.
+
+struct b200_graph {
+    int device;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+};
+
+int b200_graph_begin(b200_ctx *ctx)
+{
+    B200_ENTER(ctx);
+    B200_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    return B200_SUCCESS;
+}
+
+int b200_graph_end(b200_ctx *ctx, b200_graph **graph)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(graph, "null graph out");
+    *graph = nullptr;
+    cudaGraph_t g = nullptr;
+    B200_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        return b200_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    }
+    b200_graph *out = new b200_graph();
+    out->device = ctx->device;
+    out->graph = g;
+    out->exec = exec;
+    *graph = out;
+    return B200_SUCCESS;
+}
+
+int b200_graph_launch(b200_ctx *ctx, b200_graph *graph)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(graph && graph->device == ctx->device, "graph was recorded on another device");
+    B200_CUDA(cudaGraphLaunch(graph->exec, ctx->stream));
+    return B200_SUCCESS;
+}
+
+int b200_graph_destroy(b200_graph *graph)
+{
+    if (!graph) return B200_SUCCESS;
+    cudaSetDevice(graph->device);
+    cudaGraphExecDestroy(graph->exec);
+    cudaGraphDestroy(graph->graph);
+    delete graph;
     return B200_SUCCESS;
 }
 

@@ -196,16 +196,27 @@ coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long j = j0 + 16 * u;
+                c[u].zero();
+                r[u].zero();
+                v[u].zero();
                 if (j < ee) {
                     r[u].load(row + j);
                     c[u].load(col + j);
                     v[u].load(data + j);
                 }
             }
+            // 0 at run time; makes the gathers wait for ALL loads of the batch, row keys included
+            // (common.cuh: batch_hold) -- otherwise ptxas sinks most of them below the first gathers
+            int hold = 0;
+            if (U > 1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) hold |= hold_bits(c[u], v[u]) & r[u].v[0];
+                hold >>= 31;
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xv[u][k] = (j0 + 16 * u + k < ee) ? ld_x(x, c[u].v[k]) : T(0);
+                for (int k = 0; k < 4; ++k) xv[u][k] = (j0 + 16 * u + k < ee) ? ld_x(x, c[u].v[k] + hold) : T(0);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long j = j0 + 16 * u;

@@ -21,27 +21,53 @@ namespace {
 constexpr int kBlock = 256;
 
 // dot product of entries [s, e) of (col, data) with x, cooperatively by LPR lanes.
+// One round trip = U aligned groups of four entries per lane: first ALL 2U (fp32) / 3U (fp64)
+// 128-bit matrix loads are issued, then all 4U x gathers, then the FMAs (two accumulators).  Written
+// as three separate phases over register arrays because a plain `#pragma unroll U` loop compiles to
+// load -> gather -> FMA -> load ... (cuobjdump -sass), i.e. one round trip per group: fine when
+// dozens of warps per SM hide it, a latency chain on matrices of one or two waves (cant).
+// U = 1 keeps the register count at 32 (full occupancy); U = 2 / 4 trade occupancy for loads in flight.
 template <typename T, int LPR, int U = 2>
 __device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *__restrict__ data,
                                          const T *__restrict__ x, long long s, long long e, int lane)
 {
-    T acc = 0;
+    T acc0 = 0, acc1 = 0;
     const long long g_end = (e + 3) >> 2;
-    // U iterations are unrolled so that their 2U vector loads, then their 4U gathers, are in flight
-    // together: U = 2 when many waves of blocks hide latency anyway, U = 4 for small matrices
-    // (at most ~2 waves) where the kernel is a latency chain
-#pragma unroll U
-    for (long long g = (s >> 2) + lane; g < g_end; g += LPR) {
-        const long long j = g << 2;
-        IVec4 c;
-        Vec4<T> v;
-        c.load(col + j);
-        v.load(data + j);
+    for (long long g0 = (s >> 2) + lane; g0 < g_end; g0 += (long long)LPR * U) {
+        IVec4 c[U];
+        Vec4<T> v[U];
+        T xv[U][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (j + k >= s && j + k < e) acc += v.v[k] * ld_x(x, c.v[k]);
+        for (int u = 0; u < U; ++u) {
+            const long long g = g0 + (long long)u * LPR;
+            c[u].zero();
+            v[u].zero();
+            if (g < g_end) {
+                c[u].load(col + (g << 2));
+                v[u].load(data + (g << 2));
+            }
+        }
+        const int hold = batch_hold<U, T>(c, v);  // 0; orders the gathers after ALL loads (common.cuh)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long j = (g0 + (long long)u * LPR) << 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // j + k < e implies the group was loaded; masked slots contribute exactly +0
+                const bool ok = j + k >= s && j + k < e;
+                xv[u][k] = ok ? ld_x(x, c[u].v[k] + hold) : T(0);
+                if (!ok) v[u].v[k] = T(0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc0 += v[u].v[0] * xv[u][0];
+            acc1 += v[u].v[1] * xv[u][1];
+            acc0 += v[u].v[2] * xv[u][2];
+            acc1 += v[u].v[3] * xv[u][3];
+        }
     }
-    return acc;
+    return acc0 + acc1;
 }
 
 // same, scalar loads: used only when an array is not 16-byte aligned
@@ -324,6 +350,18 @@ int pick_lanes(double mean_len, const char *override_env)
     return lanes;
 }
 
+// groups loaded per lane and round trip (row_dot_vec).  A launch of at most ~2 waves of resident
+// threads is a latency chain: batch deeper there.  Tuning hook: <env> = 1|2|4.
+int pick_unroll(const b200_ctx *ctx, long long threads, const char *override_env)
+{
+    int u = threads <= 2ll * ctx->sm_count * 2048 ? 4 : 2;
+    if (const char *e = getenv(override_env)) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) u = v;
+    }
+    return u;
+}
+
 }  // namespace
 
 struct b200_csr_plan {
@@ -454,15 +492,15 @@ int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data,
                    int n_rows, int long_threshold, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    // small launch (at most ~2 waves of resident threads): deeper unroll, see row_dot_vec
-    bool deep = (long long)n_rows * LPR <= 2ll * ctx->sm_count * 2048;
-    if (const char *e = getenv("B200_CSR_UNROLL")) deep = atoi(e) >= 4;
+    const int u = pick_unroll(ctx, (long long)n_rows * LPR, "B200_CSR_UNROLL");
     if (!vec)
-        csr_vector_kernel<T, LPR, false, 2><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
-    else if (deep)
+        csr_vector_kernel<T, LPR, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+    else if (u == 4)
         csr_vector_kernel<T, LPR, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
-    else
+    else if (u == 2)
         csr_vector_kernel<T, LPR, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+    else
+        csr_vector_kernel<T, LPR, true, 1><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -531,14 +569,15 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
                    int row_size, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    bool deep = (long long)n_rows * LPR <= 2ll * ctx->sm_count * 2048;
-    if (const char *e = getenv("B200_CSR_UNROLL")) deep = atoi(e) >= 4;
+    const int u = pick_unroll(ctx, (long long)n_rows * LPR, "B200_ELL_UNROLL");
     if (!vec)
-        ell_rowmajor_kernel<T, LPR, false, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
-    else if (deep)
+        ell_rowmajor_kernel<T, LPR, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+    else if (u == 4)
         ell_rowmajor_kernel<T, LPR, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
-    else
+    else if (u == 2)
         ell_rowmajor_kernel<T, LPR, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+    else
+        ell_rowmajor_kernel<T, LPR, true, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

@@ -21,19 +21,30 @@ namespace {
 
 constexpr int kBlock = 256;
 
-// Columns [seg*wmax, (seg+1)*wmax) of one chunk, by one warp.  seg == 0 is the main pass (plain
-// store, wmax = 0 means the whole chunk); seg > 0 are the extra segments of chunks wider than wmax
-// columns (power-law inputs: a hub row makes one chunk 10^5 columns wide), listed by the plan and
+// Columns [seg*wmax, (seg+1)*wmax) of one chunk.  seg == 0 is the main pass (plain store, wmax = 0
+// means the whole chunk); seg > 0 are the extra segments of chunks wider than wmax columns
+// (power-law inputs: a hub row makes one chunk 10^5 columns wide), listed by the plan and
 // accumulated with atomics after the main pass.
-template <typename T, typename P, bool EXTRA>
+//   U   = groups of four entries a lane loads per round trip: all 2U/3U 128-bit loads first, then
+//         the 4U gathers, then the FMAs (see row_dot_vec in spmv_csr.cu for why this is explicit);
+//   WPC = warps that share one chunk (main pass only).  A matrix with few chunks (cant: 1952) gives
+//         one-warp-per-chunk only 13 warps per SM, each walking ~20 dependent round trips; WPC warps
+//         take the chunk's 32-group rounds in turn and their 32 row sums meet in shared memory
+//         (fixed order: deterministic, no atomics).
+template <typename T, typename P, bool EXTRA, int WPC, int U>
 __global__ void __launch_bounds__(kBlock)
 sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
               T *__restrict__ y, const P *__restrict__ slice_ptr, int n_work, int n_out,
               const int *__restrict__ perm, int wmax, const int2 *__restrict__ items)
 {
+    static_assert(!EXTRA || WPC == 1, "extra segments are one warp each");
+    __shared__ T red[WPC > 1 ? kBlock / 32 : 1][32];
     const int lane = threadIdx.x & 31;
-    const long long work = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    if (work >= n_work) return;  // whole warps leave together
+    const int warp = threadIdx.x >> 5;
+    const long long work = ((long long)blockIdx.x * kBlock + threadIdx.x) / (32 * WPC);
+    const int part = warp % WPC;  // which of the chunk's WPC warps this is
+    const bool active = work < n_work;
+    if (WPC == 1 && !active) return;  // whole warps leave together
     long long slice = work;
     int seg = 0;
     if (EXTRA) {
@@ -41,26 +52,46 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
         slice = it.x;
         seg = it.y;
     }
-    const long long chunk_base = slice_ptr[slice];
-    long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;  // 8 per column
-    long long g_begin = 0;
-    if (wmax > 0) {
-        g_begin = (long long)seg * wmax * 8;
-        n_groups = min(n_groups, g_begin + (long long)wmax * 8);
-    }
-    const int *ip = idx + chunk_base;
-    const T *dp = data + chunk_base;
     T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-#pragma unroll 4
-    for (long long g = g_begin + lane; g < n_groups; g += 32) {
-        IVec4 c;
-        Vec4<T> v;
-        c.load(ip + (g << 2));
-        v.load(dp + (g << 2));
-        acc0 += v.v[0] * ld_x(x, c.v[0]);
-        acc1 += v.v[1] * ld_x(x, c.v[1]);
-        acc2 += v.v[2] * ld_x(x, c.v[2]);
-        acc3 += v.v[3] * ld_x(x, c.v[3]);
+    if (active) {
+        const long long chunk_base = slice_ptr[slice];
+        long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;  // 8 per column
+        long long g_begin = 0;
+        if (wmax > 0) {
+            g_begin = (long long)seg * wmax * 8;
+            n_groups = min(n_groups, g_begin + (long long)wmax * 8);
+        }
+        const int *ip = idx + chunk_base;
+        const T *dp = data + chunk_base;
+        for (long long g0 = g_begin + 32 * part + lane; g0 < n_groups; g0 += 32 * WPC * U) {
+            IVec4 c[U];
+            Vec4<T> v[U];
+            T xv[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long g = g0 + 32 * WPC * u;
+                c[u].zero();
+                v[u].zero();
+                if (g < n_groups) {
+                    c[u].load(ip + (g << 2));
+                    v[u].load(dp + (g << 2));
+                }
+            }
+            const int hold = batch_hold<U, T>(c, v);  // 0; orders the gathers after ALL loads (common.cuh)
+            // a group that was not loaded reads x[0] and multiplies it by 0: every group of a chunk
+            // is whole (padding slots are (col 0, value 0) in the format itself)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[u][k] = ld_x(x, c[u].v[k] + hold);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc0 += v[u].v[0] * xv[u][0];
+                acc1 += v[u].v[1] * xv[u][1];
+                acc2 += v[u].v[2] * xv[u][2];
+                acc3 += v[u].v[3] * xv[u][3];
+            }
+        }
     }
 #pragma unroll
     for (int off = 8; off <= 16; off <<= 1) {
@@ -69,16 +100,216 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
         acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
         acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
     }
-    if (lane < 8) {
-        const long long r = slice * 32 + lane * 4;
-        const T a[4] = {acc0, acc1, acc2, acc3};
+    if (WPC == 1) {
+        if (lane < 8) {
+            const long long r = slice * 32 + lane * 4;
+            const T a[4] = {acc0, acc1, acc2, acc3};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (r + k < n_out) {
-                T *dst = y + (perm ? perm[r + k] : r + k);
-                if (EXTRA) atomicAdd(dst, a[k]);
-                else *dst = a[k];
+            for (int k = 0; k < 4; ++k) {
+                if (r + k < n_out) {
+                    T *dst = y + (perm ? perm[r + k] : r + k);
+                    if (EXTRA) atomicAdd(dst, a[k]);
+                    else *dst = a[k];
+                }
             }
+        }
+    } else {
+        if (lane < 8) {
+            red[warp][lane * 4 + 0] = acc0;
+            red[warp][lane * 4 + 1] = acc1;
+            red[warp][lane * 4 + 2] = acc2;
+            red[warp][lane * 4 + 3] = acc3;
+        }
+        __syncthreads();
+        if (part == 0 && active) {
+            T total = red[warp][lane];
+#pragma unroll
+            for (int w = 1; w < WPC; ++w) total += red[warp + w][lane];
+            const long long r = slice * 32 + lane;
+            if (r < n_out) y[perm ? perm[r] : r] = total;
+        }
+    }
+}
+
+// ---- SELL through the TMA engine (bulk asynchronous copies into shared memory) ----------------
+// A chunk is one contiguous run of 32*w entries in both arrays, so the copy engine can stream it:
+// every warp owns a two-stage ring of kPiece-entry buffers in shared memory and one mbarrier per
+// stage.  Lane 0 arms the barrier with the byte count and issues two cp.async.bulk copies (indices,
+// values); the warp waits on the barrier, reads its groups with conflict-free LDS.128, gathers x
+// and accumulates, then re-arms the freed stage with the piece two ahead.  The ring runs ACROSS
+// chunk boundaries (a warp walks chunks gw, gw + W, ...), so a warp always has one or two pieces
+// (4-12 KiB) in flight without holding a single register for them: ~100 KiB in flight per SM at 16
+// resident warps, where the register-staged kernel needs 64 warps x U groups for the same.
+// Persistent grid: blocks = min(chunks / 8, SMs x blocks that fit in 227 KiB of shared memory).
+constexpr int kPiece = 512;   // entries per stage: 16 columns of a chunk
+constexpr int kStages = 2;
+constexpr unsigned long long kWaitLimitNs = 2000000000ull;  // a 2 s wait is a bug: flag it, do not hang
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                         unsigned long long *bar, unsigned long long policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+template <typename T, typename P>
+__global__ void __launch_bounds__(kBlock)
+sell32_tma_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
+                  T *__restrict__ y, const P *__restrict__ slice_ptr, int n_slices, int n_out,
+                  const int *__restrict__ perm, int *__restrict__ err_flag)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kWarps = kBlock / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *s_idx = reinterpret_cast<int *>(smem_raw) + warp * kStages * kPiece;
+    T *s_val = reinterpret_cast<T *>(smem_raw + (size_t)kWarps * kStages * kPiece * sizeof(int)) +
+               warp * kStages * kPiece;
+    unsigned long long *bars =
+        reinterpret_cast<unsigned long long *>(smem_raw + (size_t)kWarps * kStages * kPiece * (sizeof(int) + sizeof(T))) +
+        warp * kStages;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) mbar_init(bars + st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned long long policy;  // matrix data is read once: evict-first in L2, like ld.global.cs
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    const long long n_warps = (long long)gridDim.x * kWarps;
+    const long long gw = (long long)blockIdx.x * kWarps + warp;
+
+    // producer cursor: the next piece to request = entries [p_off, p_off + kPiece) of chunk p_slice
+    long long p_slice = gw, p_base = 0, p_n = 0, p_off = 0;
+    bool p_valid = p_slice < n_slices;
+    if (p_valid) {
+        p_base = slice_ptr[p_slice];
+        p_n = (long long)slice_ptr[p_slice + 1] - p_base;
+    }
+    auto p_normalize = [&]() {  // skip past exhausted (or empty) chunks
+        while (p_valid && p_off >= p_n) {
+            p_slice += n_warps;
+            p_off = 0;
+            p_valid = p_slice < n_slices;
+            if (p_valid) {
+                p_base = slice_ptr[p_slice];
+                p_n = (long long)slice_ptr[p_slice + 1] - p_base;
+            }
+        }
+    };
+    auto p_issue = [&](int stage) {
+        const unsigned cnt = (unsigned)min((long long)kPiece, p_n - p_off);
+        if (lane == 0) {
+            mbar_expect_tx(bars + stage, cnt * (unsigned)(sizeof(int) + sizeof(T)));
+            bulk_g2s(s_idx + stage * kPiece, idx + p_base + p_off, cnt * (unsigned)sizeof(int), bars + stage, policy);
+            bulk_g2s(s_val + stage * kPiece, data + p_base + p_off, cnt * (unsigned)sizeof(T), bars + stage, policy);
+        }
+        p_off += kPiece;
+        p_normalize();
+    };
+    p_normalize();
+#pragma unroll
+    for (int st = 0; st < kStages; ++st)
+        if (p_valid) p_issue(st);
+
+    unsigned consumed = 0;
+    for (long long slice = gw; slice < n_slices; slice += n_warps) {
+        const long long base = slice_ptr[slice];
+        const long long n = (long long)slice_ptr[slice + 1] - base;
+        T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        for (long long off = 0; off < n; off += kPiece) {
+            const int stage = consumed % kStages;
+            const unsigned parity = (consumed / kStages) & 1u;
+            if (!mbar_try_wait(bars + stage, parity)) {
+                const unsigned long long t0 = global_timer_ns();
+                while (!mbar_try_wait(bars + stage, parity)) {
+                    if (global_timer_ns() - t0 > kWaitLimitNs) {
+                        if (lane == 0) atomicExch(err_flag, 1);
+                        return;
+                    }
+                }
+            }
+            const int groups = (int)(min((long long)kPiece, n - off) >> 2);
+            const int *si = s_idx + stage * kPiece;
+            const T *sv = s_val + stage * kPiece;
+            constexpr int G = kPiece / 4 / 32;  // groups per lane and piece
+            IVec4 c[G];
+            Vec4<T> v[G];
+            T xv[G][4];
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const int g = lane + 32 * u;
+                c[u].zero();
+                v[u].zero();
+                if (g < groups) {
+                    c[u].load_shared(si + 4 * g);
+                    v[u].load_shared(sv + 4 * g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[u][k] = ld_x(x, c[u].v[k]);
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                acc0 += v[u].v[0] * xv[u][0];
+                acc1 += v[u].v[1] * xv[u][1];
+                acc2 += v[u].v[2] * xv[u][2];
+                acc3 += v[u].v[3] * xv[u][3];
+            }
+            __syncwarp();  // every lane has read the stage: it may be overwritten
+            ++consumed;
+            if (p_valid) p_issue(stage);
+        }
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+            acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
+            acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
+        }
+        if (lane < 8) {
+            const long long r = slice * 32 + lane * 4;
+            const T a[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (r + k < n_out) y[perm ? perm[r + k] : r + k] = a[k];
         }
     }
 }
@@ -137,16 +368,34 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
         const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
         const int *ip = idx + chunk_base;
         const T *dp = data + chunk_base;
-#pragma unroll 4
-        for (long long g = lane; g < n_groups; g += 32) {
-            IVec4 c;
-            Vec4<T> v;
-            c.load(ip + (g << 2));
-            v.load(dp + (g << 2));
-            acc0 += v.v[0] * ld_x(x, c.v[0]);
-            acc1 += v.v[1] * ld_x(x, c.v[1]);
-            acc2 += v.v[2] * ld_x(x, c.v[2]);
-            acc3 += v.v[3] * ld_x(x, c.v[3]);
+        // two groups per lane and round trip (a 7-point-stencil chunk is 56 groups: one round trip)
+        constexpr int U = 2;
+        for (long long g0 = lane; g0 < n_groups; g0 += 32 * U) {
+            IVec4 c[U];
+            Vec4<T> v[U];
+            T xv[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long g = g0 + 32 * u;
+                c[u].zero();
+                v[u].zero();
+                if (g < n_groups) {
+                    c[u].load(ip + (g << 2));
+                    v[u].load(dp + (g << 2));
+                }
+            }
+            const int hold = batch_hold<U, T>(c, v);  // 0; orders the gathers after ALL loads (common.cuh)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[u][k] = ld_x(x, c[u].v[k] + hold);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc0 += v[u].v[0] * xv[u][0];
+                acc1 += v[u].v[1] * xv[u][1];
+                acc2 += v[u].v[2] * xv[u][2];
+                acc3 += v[u].v[3] * xv[u][3];
+            }
         }
     }
 #pragma unroll
@@ -330,10 +579,64 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
     unsigned blocks = ceil_div_u((long long)n_slices * 32, kBlock);
     if (aligned16(data) && aligned16(idx)) {
         const int wmax = plan && plan->n_items > 0 ? plan->wmax : 0;
-        sell32_kernel<T, P, false><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices,
-                                                                      n_out, perm, wmax, nullptr);
+        // B200_SELL_TMA=1: the bulk-copy (TMA engine) staged kernel, persistent grid
+        bool tma = false;
+        if (const char *e = getenv("B200_SELL_TMA")) tma = atoi(e) != 0;
+        if (tma && wmax == 0) {
+            constexpr size_t smem = (size_t)(kBlock / 32) * kStages * (kPiece * (sizeof(int) + sizeof(T)) + 8);
+            B200_CUDA(cudaFuncSetAttribute(sell32_tma_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // resident blocks per SM (B200_SELL_TMA_BLOCKS=1|2|3): each holds 8 warps x 2 stages in
+            // flight; the shared-memory carve-out is sized for exactly that many, the rest stays L1
+            // for the x gather
+            const long long fit = (227 * 1024) / (long long)(smem + 1024);
+            long long per_sm = fit < 2 ? fit : 2;
+            if (const char *e = getenv("B200_SELL_TMA_BLOCKS")) {
+                const int v = atoi(e);
+                if (v >= 1 && v <= fit) per_sm = v;
+            }
+            const int carve = (int)min(100ll, (per_sm * (long long)(smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            B200_CUDA(cudaFuncSetAttribute(sell32_tma_kernel<T, P>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            const long long want = ((long long)n_slices + kBlock / 32 - 1) / (kBlock / 32);
+            const unsigned grid = (unsigned)min(want, (long long)ctx->sm_count * per_sm);
+            sell32_tma_kernel<T, P><<<grid, kBlock, smem, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices, n_out, perm,
+                                                                        ctx->scratch + kWatchFlag);
+            B200_LAUNCH_CHECK();
+            ctx->watch_flag = true;
+            return B200_SUCCESS;
+        }
+        // warps per chunk: enough warps for ~32 per SM (tuning hook B200_SELL_WPC=1|2|4|8); chunks
+        // that the plan splits by columns anyway stay one warp each
+        int wpc = 1;
+        while (wmax == 0 && wpc < 8 && (long long)n_slices * wpc < (long long)ctx->sm_count * 32) wpc <<= 1;
+        if (const char *e = getenv("B200_SELL_WPC")) {
+            const int v = atoi(e);
+            if (wmax == 0 && (v == 1 || v == 2 || v == 4 || v == 8)) wpc = v;
+        }
+        // groups per lane and round trip (tuning hook B200_SELL_UNROLL=1|2|4)
+        int u = (long long)n_slices * wpc <= 2ll * ctx->sm_count * 64 ? 4 : 2;
+        if (const char *e = getenv("B200_SELL_UNROLL")) {
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4) u = v;
+        }
+#define B200_SELL_MAIN(W, UU)                                                                              \
+    sell32_kernel<T, P, false, W, UU><<<ceil_div_u((long long)n_slices * 32 * W, kBlock), kBlock, 0, ctx->stream>>>( \
+        data, idx, x, y, slice_ptr, n_slices, n_out, perm, wmax, nullptr)
+#define B200_SELL_MAIN_U(W)                  \
+    do {                                     \
+        if (u == 4) B200_SELL_MAIN(W, 4);    \
+        else if (u == 2) B200_SELL_MAIN(W, 2); \
+        else B200_SELL_MAIN(W, 1);           \
+    } while (0)
+        switch (wpc) {
+        case 8: B200_SELL_MAIN_U(8); break;
+        case 4: B200_SELL_MAIN_U(4); break;
+        case 2: B200_SELL_MAIN_U(2); break;
+        default: B200_SELL_MAIN_U(1); break;
+        }
+#undef B200_SELL_MAIN_U
+#undef B200_SELL_MAIN
         if (wmax > 0)
-            sell32_kernel<T, P, true><<<ceil_div_u((long long)plan->n_items * 32, kBlock), kBlock, 0, ctx->stream>>>(
+            sell32_kernel<T, P, true, 1, 2><<<ceil_div_u((long long)plan->n_items * 32, kBlock), kBlock, 0, ctx->stream>>>(
                 data, idx, x, y, slice_ptr, plan->n_items, n_out, perm, wmax, plan->items);
     } else {
         sell32_scalar_kernel<T, P><<<blocks, kBlock, 0, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices, n_out, perm);

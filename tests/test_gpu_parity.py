@@ -376,3 +376,76 @@ def test_row_sharded_equals_unsharded(ctx):
                     # csr/cmrs group entries by 16-byte alignment of the (rebased) entry index and
                     # coo uses atomics: same values up to summation order
                     assert O.rel_maxnorm(got, y_full[name].astype(np.float64)) <= TOL[np.dtype(dtype)]
+
+
+VARIANT_HOOKS = {
+    "csr": [{"B200_CSR_LANES": l, "B200_CSR_UNROLL": u} for l in (2, 4, 8, 16, 32) for u in (1, 2, 4)],
+    "ell": [{"B200_ELL_LANES": l, "B200_ELL_UNROLL": u} for l in (2, 4, 8, 16, 32) for u in (1, 2, 4)],
+    "sell": [{"B200_SELL_WPC": w, "B200_SELL_UNROLL": u} for w in (1, 2, 4, 8) for u in (1, 2, 4)],
+    "coo": [{"B200_COO_U": u} for u in (1, 2, 4)],
+    "cmrs": [{"B200_CMRS_U": u} for u in (1, 2)],
+}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_every_tuning_variant_matches_the_oracle(ctx, dtype, monkeypatch):
+    """Every kernel variant the tuning hooks can select (lanes per row, load-batch depth U, SELL
+    warps per chunk) computes the same y: ragged rows (1..150 entries), a row count that is not a
+    multiple of 32 or 8, and a last SELL chunk / CMRS strip that is partly empty."""
+    n_rows, n_cols = 2333, 4000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 150, 71, long_rows=((7, 900), (2332, 1)))
+    x = np.random.default_rng(72).uniform(-1, 1, n_cols)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    m = pkg.build_all(coo, dtype)
+    xd = ctx.array(x.astype(dtype))
+    for fmt, envs in VARIANT_HOOKS.items():
+        for env in envs:
+            for k, v in env.items():
+                monkeypatch.setenv(k, str(v))
+            mat = pkg.CsrMatrix(coo) if fmt == "csr" else m[fmt]   # the CSR plan caches its lanes
+            if fmt == "csr":
+                assert mat.plan_info().lanes_per_row == env["B200_CSR_LANES"]
+            yd = ctx.array(np.full(n_rows, np.nan, dtype))
+            mat.spmv(xd, yd)
+            check_y(f"{fmt} {env}", yd.download(), y_ref, dtype)
+            for k in env:
+                monkeypatch.delenv(k)
+
+
+def test_launch_graph_replays_recorded_spmvs(ctx):
+    """b200_graph_*: launches recorded on a context replay in order with one call, give the same
+    bits as the direct launches, and calls that synchronise are refused while recording."""
+    n_rows, n_cols = 3000, 3000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 60, 81)
+    x = np.random.default_rng(82).uniform(-1, 1, n_cols)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    m = pkg.build_all(coo, np.float64)
+    xd = ctx.array(x)
+    direct, ys = {}, {}
+    for name, mat in m.items():   # direct launches first: this also creates every plan
+        yd = ctx.zeros(n_rows, np.float64)
+        mat.spmv(xd, yd)
+        direct[name] = yd.download()
+        ys[name] = ctx.array(np.full(n_rows, np.nan))
+    with ctx.record_graph() as g:
+        for name, mat in m.items():
+            mat.spmv(xd, ys[name])
+    ctx.sync()
+    assert all(np.isnan(ys[name].download()).all() for name in m), "recording must not execute"
+    for _ in range(2):
+        g.launch()
+    for name in m:
+        got = ys[name].download()
+        if name == "coo":   # atomics: same values up to summation order
+            assert O.rel_maxnorm(got, direct[name]) <= 1e-12
+        else:
+            assert got.tobytes() == direct[name].tobytes(), name
+    # a call that has to synchronise (no plan -> statistics pass) fails loudly while recording
+    csr = pkg.CsrMatrix(coo)
+    with pytest.raises(pkg.B200Error):
+        with ctx.record_graph():
+            csr.spmv(xd, ys["csr"], use_plan=False)
+    yd = ctx.zeros(n_rows, np.float64)   # and the context is usable afterwards
+    m["csr"].spmv(xd, yd)
+    assert yd.download().tobytes() == direct["csr"].tobytes()
