@@ -202,6 +202,19 @@ int b200_spmv_cmrs_f32(b200_ctx *ctx, const float *data, const int *indices, con
                        const int *row_in_strip, const float *vect, float *output, int n_strips,
                        int height, int n_rows, const b200_cmrs_plan *plan);
 
+/* CMRS, packed device layout (new): packed[i] = (row_in_strip[i] << 27) | indices[i], so
+ * the kernel streams 4 + V bytes per entry instead of the 8 + V of the reference's two index arrays
+ * (cmrs.c:42-45).  The reference arrays stay the bit-exact build product; this is a derived layout
+ * like column-major ELL.  Needs height <= 32 and n_cols <= 2^27 (else B200_ERR_UNSUPPORTED). */
+int b200_cmrs_pack(b200_ctx *ctx, const int *indices, const int *row_in_strip, long long nnz, int n_cols,
+                   int height, int *packed);
+int b200_spmv_cmrs_packed_f64(b200_ctx *ctx, const double *data, const int *packed, const int *strip_ptr,
+                              const double *vect, double *output, int n_strips, int height, int n_rows,
+                              const b200_cmrs_plan *plan);
+int b200_spmv_cmrs_packed_f32(b200_ctx *ctx, const float *data, const int *packed, const int *strip_ptr,
+                              const float *vect, float *output, int n_strips, int height, int n_rows,
+                              const b200_cmrs_plan *plan);
+
 /* =====================================================================================
  * Format builds on the GPU (new; in the reference they are host loops inlined in each main()).
  * Input: device COO triples as the drivers parse them ("%d %d %lg", 1-based -> 0-based,

@@ -99,6 +99,9 @@ SIGNATURES = {
     "b200_cmrs_plan_destroy": (_i, [_vp]),
     "b200_spmv_cmrs_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_spmv_cmrs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_cmrs_pack": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "b200_spmv_cmrs_packed_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_spmv_cmrs_packed_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_check_sorted_rows": (_i, [_vp, _vp, _i, _i]),
     "b200_build_csr_ptr": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200_row_length_stats": (_i, [_vp, _vp, _i, C.POINTER(RowStats)]),
@@ -329,7 +332,7 @@ class Event:
             pass
 
 
-from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix,  # noqa: E402,F401
+from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix, CmrsPackedMatrix,  # noqa: E402,F401
                       algorithmic_bytes, build_all, partition_rows)
 from .iterate import (PeerBuffers, RowBlocks, equal_row_blocks, gpu_callables, power_iteration,  # noqa: E402,F401
                       power_iteration_fused)

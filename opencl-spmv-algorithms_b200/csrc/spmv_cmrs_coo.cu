@@ -46,7 +46,12 @@ __device__ __forceinline__ void cmrs_flush(T (&acc)[HMAX], int key, T sum)
 // a hub row has 10^5 entries): the main pass (EXTRA = false) walks only the first `cap` entries of
 // each strip and stores; the extra pass (EXTRA = true) has one warp per (strip, segment) work item
 // of the plan and accumulates with atomics.
-template <typename T, int HMAX, bool VEC, int U, bool EXTRA>
+// PACKED: `idx` holds (row_in_strip << kPackShift) | column in one word (b200_cmrs_pack) and
+// `row_in_strip` is not read: 4 + V bytes per entry instead of 8 + V.
+constexpr int kPackShift = 27;  // 5 key bits (height <= 32), columns < 2^27
+constexpr int kPackMask = (1 << kPackShift) - 1;
+
+template <typename T, int HMAX, bool VEC, int U, bool EXTRA, bool PACKED = false>
 __global__ void __launch_bounds__(kBlock)
 cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *__restrict__ strip_ptr,
             const int *__restrict__ row_in_strip, const T *__restrict__ x, T *__restrict__ y,
@@ -88,8 +93,15 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
                 const int j = (g0 + 4 * u) << 2;
                 if (g0 + 4 * u < g_end) {
                     c[u].load(idx + j);
-                    r[u].load(row_in_strip + j);
+                    if (!PACKED) r[u].load(row_in_strip + j);
                     v[u].load(data + j);
+                    if (PACKED) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            r[u].v[k] = (int)((unsigned)c[u].v[k] >> kPackShift);
+                            c[u].v[k] &= kPackMask;
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -124,13 +136,15 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
         }
     } else {
         for (int j = ss + (lane & 3); j < ee; j += 4) {
-            const int r = ld_stream(row_in_strip + j);
+            int c = ld_stream(idx + j);
+            const int r = PACKED ? (int)((unsigned)c >> kPackShift) : ld_stream(row_in_strip + j);
+            if (PACKED) c &= kPackMask;
             if (r != cur) {
                 cmrs_flush<T, HMAX>(acc, cur, sum);
                 cur = r;
                 sum = 0;
             }
-            sum += ld_stream(data + j) * ld_x(x, ld_stream(idx + j));
+            sum += ld_stream(data + j) * ld_x(x, c);
         }
     }
     cmrs_flush<T, HMAX>(acc, cur, sum);
@@ -155,6 +169,14 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
         if (EXTRA) atomicAdd(y + row, total);
         else y[row] = total;
     }
+}
+
+__global__ void cmrs_pack_kernel(const int *__restrict__ idx, const int *__restrict__ row_in_strip,
+                                 long long nnz, int *__restrict__ packed)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
+         i += (long long)gridDim.x * blockDim.x)
+        packed[i] = (int)(((unsigned)row_in_strip[i] << kPackShift) | (unsigned)idx[i]);
 }
 
 constexpr int kCmrsCap = 8192;  // entries per (strip, segment) work item
@@ -276,7 +298,7 @@ struct b200_cmrs_plan {
 
 namespace {
 
-template <typename T>
+template <typename T, bool PACKED>
 int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *strip_ptr,
                    const int *row_in_strip, const T *x, T *y, int n_strips, int height, int n_rows,
                    const b200_cmrs_plan *plan)
@@ -289,7 +311,7 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     }
     B200_REQUIRE(!plan || plan->n_strips == n_strips, "plan was built for a different matrix");
     if (n_strips == 0) return B200_SUCCESS;
-    const bool vec = aligned16(data) && aligned16(idx) && aligned16(row_in_strip);
+    const bool vec = aligned16(data) && aligned16(idx) && (PACKED || aligned16(row_in_strip));
     const int n_items = plan ? plan->n_items : 0;
     const int cap = n_items > 0 ? plan->cap : 0;
     const int2 *items = n_items > 0 ? plan->items : nullptr;
@@ -299,10 +321,10 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
 #define B200_CMRS_LAUNCH2(H, V, UU)                                                                         \
     do {                                                                                                    \
-        cmrs_kernel<T, H, V, UU, false><<<ceil_div_u(n_strips, kWarps), kBlock, 0, ctx->stream>>>(           \
+        cmrs_kernel<T, H, V, UU, false, PACKED><<<ceil_div_u(n_strips, kWarps), kBlock, 0, ctx->stream>>>(   \
             data, idx, strip_ptr, row_in_strip, x, y, n_strips, height, n_rows, cap, nullptr);              \
         if (n_items > 0)                                                                                    \
-            cmrs_kernel<T, H, V, UU, true><<<ceil_div_u(n_items, kWarps), kBlock, 0, ctx->stream>>>(         \
+            cmrs_kernel<T, H, V, UU, true, PACKED><<<ceil_div_u(n_items, kWarps), kBlock, 0, ctx->stream>>>( \
                 data, idx, strip_ptr, row_in_strip, x, y, n_items, height, n_rows, cap, items);             \
     } while (0)
 #define B200_CMRS_LAUNCH(H, V)             \
@@ -409,13 +431,41 @@ int b200_spmv_cmrs_f64(b200_ctx *ctx, const double *data, const int *indices, co
                        const int *row_in_strip, const double *vect, double *output, int n_strips,
                        int height, int n_rows, const b200_cmrs_plan *plan)
 {
-    return spmv_cmrs_impl<double>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows, plan);
+    return spmv_cmrs_impl<double, false>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows, plan);
 }
 int b200_spmv_cmrs_f32(b200_ctx *ctx, const float *data, const int *indices, const int *strip_ptr,
                        const int *row_in_strip, const float *vect, float *output, int n_strips,
                        int height, int n_rows, const b200_cmrs_plan *plan)
 {
-    return spmv_cmrs_impl<float>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows, plan);
+    return spmv_cmrs_impl<float, false>(ctx, data, indices, strip_ptr, row_in_strip, vect, output, n_strips, height, n_rows, plan);
+}
+int b200_cmrs_pack(b200_ctx *ctx, const int *indices, const int *row_in_strip, long long nnz, int n_cols,
+                   int height, int *packed)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(nnz >= 0 && (nnz == 0 || (indices && row_in_strip && packed)), "bad argument");
+    if (height < 1 || height > 32 || n_cols > (1 << kPackShift)) {
+        b200_set_error("packed CMRS needs height <= 32 and at most 2^%d columns (height %d, %d columns)",
+                       kPackShift, height, n_cols);
+        return B200_ERR_UNSUPPORTED;
+    }
+    if (nnz == 0) return B200_SUCCESS;
+    const unsigned blocks = (unsigned)min((long long)ctx->sm_count * 16, (nnz + 255) / 256);
+    cmrs_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(indices, row_in_strip, nnz, packed);
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+int b200_spmv_cmrs_packed_f64(b200_ctx *ctx, const double *data, const int *packed, const int *strip_ptr,
+                              const double *vect, double *output, int n_strips, int height, int n_rows,
+                              const b200_cmrs_plan *plan)
+{
+    return spmv_cmrs_impl<double, true>(ctx, data, packed, strip_ptr, nullptr, vect, output, n_strips, height, n_rows, plan);
+}
+int b200_spmv_cmrs_packed_f32(b200_ctx *ctx, const float *data, const int *packed, const int *strip_ptr,
+                              const float *vect, float *output, int n_strips, int height, int n_rows,
+                              const b200_cmrs_plan *plan)
+{
+    return spmv_cmrs_impl<float, true>(ctx, data, packed, strip_ptr, nullptr, vect, output, n_strips, height, n_rows, plan);
 }
 int b200_spmv_coo_f64(b200_ctx *ctx, const int *row, const int *col, const double *data,
                       const double *vect, double *output, int nnz, int n_rows)

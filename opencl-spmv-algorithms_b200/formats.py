@@ -274,6 +274,9 @@ class CmrsMatrix:
                  x.ptr, y.ptr, self.n_strips, self.height, self.n_rows,
                  self.plan() if use_plan else None), "b200_spmv_cmrs")
 
+    def packed(self) -> "CmrsPackedMatrix":
+        return CmrsPackedMatrix(self)
+
     def __del__(self):
         try:
             if getattr(self, "_plan", None):
@@ -286,6 +289,29 @@ class CmrsMatrix:
         V = np.dtype(dtype).itemsize
         return algorithmic_bytes("cmrs", V, n_rows=self.n_rows, n_cols=self.n_cols, nnz=self.nnz,
                                  n_strips=self.n_strips)
+
+
+class CmrsPackedMatrix:
+    """CMRS with row_in_strip folded into the top 5 bits of the column word (b200_cmrs_pack): a
+    derived device layout, 4 + V bytes per entry; the reference arrays stay in `cmrs`."""
+
+    def __init__(self, cmrs: CmrsMatrix):
+        self.ctx, self.cmrs = cmrs.ctx, cmrs
+        self.n_rows, self.n_cols, self.nnz = cmrs.n_rows, cmrs.n_cols, cmrs.nnz
+        self.packed = self.ctx.empty(self.nnz, np.int32)
+        check(lib().b200_cmrs_pack(self.ctx.h, cmrs.cols.ptr, cmrs.row_in_strip.ptr, self.nnz,
+                                   self.n_cols, cmrs.height, self.packed.ptr), "b200_cmrs_pack")
+
+    def spmv(self, x: DeviceArray, y: DeviceArray, use_plan: bool = True) -> None:
+        c = self.cmrs
+        v = c.csr.coo.values(x.dtype)
+        fn = getattr(lib(), "b200_spmv_cmrs_packed_" + suffix(x.dtype))
+        check(fn(self.ctx.h, v.ptr, self.packed.ptr, c.strip_ptr.ptr, x.ptr, y.ptr, c.n_strips,
+                 c.height, c.n_rows, c.plan() if use_plan else None), "b200_spmv_cmrs_packed")
+
+    def nbytes(self, dtype) -> int:
+        V = np.dtype(dtype).itemsize
+        return self.nnz * (I4 + V) + (self.cmrs.n_strips + 1) * I4 + (self.n_cols + self.n_rows) * V
 
 
 def algorithmic_bytes(fmt: str, V: int, *, n_rows: int, n_cols: int, nnz: int = 0,

@@ -32,11 +32,12 @@ HOOKS = ("B200_SELL_TMA", "B200_SELL_TMA_BLOCKS", "B200_CSR_LANES", "B200_CSR_UN
          "B200_SELL_UNROLL", "B200_COO_U", "B200_CMRS_U", "B200_CSR_STREAM")
 
 
-def variants(workload: str, args_no_tma: bool = False):
+def variants(workload: str, args_no_tma: bool = False, tma_only: bool = False):
     small = workload == "cant"
     lanes = (2, 4, 8, 16) if small else (4, 8)
     out = {"coo": [{"B200_COO_U": u} for u in (1, 2, 4)],
            "cmrs": [{"B200_CMRS_U": u} for u in (1, 2)],
+           "cmrs_packed": [{"B200_CMRS_U": u} for u in (1, 2)],
            "csr": [{"B200_CSR_LANES": l, "B200_CSR_UNROLL": u} for l, u in itertools.product(lanes, (1, 2, 4))],
            "ell": [{"B200_ELL_LANES": l, "B200_ELL_UNROLL": u} for l, u in itertools.product(lanes, (1, 2, 4))],
            "sell": [{"B200_SELL_WPC": w, "B200_SELL_UNROLL": u}
@@ -46,6 +47,8 @@ def variants(workload: str, args_no_tma: bool = False):
         out["sell"] += [{"B200_SELL_TMA": 1, "B200_SELL_TMA_BLOCKS": b} for b in (1, 2, 3)]
     if small:
         out["csr"].append({"B200_CSR_STREAM": 1})
+    if tma_only:
+        return {"sell": [{}] + [e for e in out["sell"] if "B200_SELL_TMA" in e]}
     for f in out:
         out[f].insert(0, {})  # the library's own default
     return out
@@ -67,6 +70,7 @@ def main():
     ap.add_argument("--rows", type=int, default=2097152)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-tma", action="store_true", help="skip the bulk-copy SELL variants")
+    ap.add_argument("--tma-only", action="store_true", help="only the bulk-copy SELL variants (+ the default)")
     args = ap.parse_args()
     dtype = np.dtype(np.float32 if args.dtype == "f32" else np.float64)
 
@@ -88,6 +92,7 @@ def main():
     for c in coos:
         m = pkg.build_all(c, dtype)
         m["ell_colmajor"] = m.pop("ellcm")
+        m["cmrs_packed"] = m["cmrs"].packed()
         sets.append(m)
     y = ctx.zeros(n_rows, dtype)
     ctx.set_l2_persist(x)
@@ -105,7 +110,7 @@ def main():
             m.plan()
 
     results = []
-    for fmt, envs in variants(args.workload, args.no_tma).items():
+    for fmt, envs in variants(args.workload, args.no_tma, args.tma_only).items():
         nbytes = sets[0][fmt].nbytes(dtype)
         for env in envs:
             set_env(env)
@@ -144,6 +149,9 @@ def main():
                    "gbs": round(nbytes / (ms * 1e-3) * 1e-9, 1), "frac_measured": round(nbytes / (ms * 1e-3) * 1e-9 / peak, 4),
                    "gflops": round(2.0 * nnz / (ms * 1e-3) * 1e-9, 1)}
             results.append(rec)
+            if args.out:
+                Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+                Path(args.out).write_text(json.dumps(results, indent=1))
             print(f"{args.workload:6s} {args.dtype} {fmt:12s} {json.dumps(env):48s} {ms * 1e3:9.2f} us  "
                   f"{rec['gbs']:7.1f} GB/s  {rec['frac_measured']:.3f}", file=sys.stderr, flush=True)
     set_env({})

@@ -449,3 +449,35 @@ def test_launch_graph_replays_recorded_spmvs(ctx):
     yd = ctx.zeros(n_rows, np.float64)   # and the context is usable afterwards
     m["csr"].spmv(xd, yd)
     assert yd.download().tobytes() == direct["csr"].tobytes()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("height", [8, 5, 32])
+def test_cmrs_packed_layout(ctx, dtype, height, monkeypatch):
+    """Packed CMRS: (row_in_strip << 27) | column must equal the reference arrays bit for bit when
+    unpacked, and the packed kernel must give the same bits as the two-array kernel (same order of
+    operations) -- including the long-strip plan and both load-batch depths."""
+    n_rows, n_cols = 3001, 5000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 90, 91, long_rows=((11, 4000), (12, 4900)))
+    x = np.random.default_rng(92).uniform(-1, 1, n_cols)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    cmrs = pkg.CmrsMatrix(pkg.CsrMatrix(coo), height=height)
+    packed = cmrs.packed()
+    w = packed.packed.download().view(np.uint32)
+    np.testing.assert_array_equal((w >> 27).astype(np.int32), cmrs.row_in_strip.download())
+    np.testing.assert_array_equal((w & ((1 << 27) - 1)).astype(np.int32), cols)
+    xd = ctx.array(x.astype(dtype))
+    for u in (1, 2):
+        monkeypatch.setenv("B200_CMRS_U", str(u))
+        y0, y1 = ctx.array(np.full(n_rows, np.nan, dtype)), ctx.array(np.full(n_rows, np.nan, dtype))
+        cmrs.spmv(xd, y0)
+        packed.spmv(xd, y1)
+        check_y("cmrs-packed", y1.download(), y_ref, dtype)
+        if cmrs.plan_extra_items() == 0:
+            assert y1.download().tobytes() == y0.download().tobytes()
+    assert packed.nbytes(dtype) == cmrs.nbytes(dtype) - 4 * rows.size
+    # more than 2^27 columns cannot be packed
+    with pytest.raises(pkg.B200Error):
+        pkg.check(pkg.lib().b200_cmrs_pack(ctx.h, cmrs.cols.ptr, cmrs.row_in_strip.ptr, rows.size,
+                                           (1 << 27) + 1, height, packed.packed.ptr), "b200_cmrs_pack")
