@@ -335,8 +335,10 @@ def main():
         allm["csr"].plan()
         # "ell" = the kernel on the reference's row-major arrays (fastest ELL kernel on B200); the
         # column-major thread-per-row kernel is measured next to it
+        # "cmrs_packed" = the derived 4+V bytes/entry layout (row_in_strip folded into the column word),
+        # measured next to the reference two-array layout, never in the headline
         return ({"coo": allm["coo"], "csr": allm["csr"], "ell": allm["ell"], "sell": allm["sell"],
-                 "cmrs": allm["cmrs"]}, {"ell_colmajor": allm["ellcm"]})
+                 "cmrs": allm["cmrs"]}, {"ell_colmajor": allm["ellcm"], "cmrs_packed": allm["cmrs"].packed()})
 
     # The cant-shaped formats (53-70 MB each) fit in the 126 MB L2.  "Inputs larger than L2" is
     # restored by ROTATION: n_copies independent copies of every format's arrays (own COO triples,

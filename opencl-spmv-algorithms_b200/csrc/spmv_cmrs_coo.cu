@@ -315,9 +315,10 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     const int n_items = plan ? plan->n_items : 0;
     const int cap = n_items > 0 ? plan->cap : 0;
     const int2 *items = n_items > 0 ? plan->items : nullptr;
-    // U = groups loaded per lane and round trip.  Measured on B200 (profiles/): fp32 wants 2, fp64 1
-    // (register pressure); tuning hook B200_CMRS_U=1|2
-    int u = sizeof(T) == 4 ? 2 : 1;
+    // U = groups loaded per lane and round trip.  Measured on B200 (profiles/r1e_variant_sweep.md):
+    // 1 everywhere (fp32 banded 236 vs 247 us, fp64 330 vs 431, cant 19.5 vs 21.4);
+    // tuning hook B200_CMRS_U=1|2
+    int u = 1;
     if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
 #define B200_CMRS_LAUNCH2(H, V, UU)                                                                         \
     do {                                                                                                    \
@@ -356,8 +357,9 @@ int spmv_coo_impl(b200_ctx *ctx, const int *row, const int *col, const T *data, 
     if (nnz == 0) return B200_SUCCESS;
     const bool vec = aligned16(row) && aligned16(col) && aligned16(data);
     unsigned blocks = ceil_div_u(((long long)nnz + kCooPerWarp - 1) / kCooPerWarp, kWarps);
-    // U = groups loaded per lane and round trip (tuning hook B200_COO_U=1|2|4)
-    int u = 2;
+    // U = groups loaded per lane and round trip (tuning hook B200_COO_U=1|2|4).  Measured on B200
+    // (profiles/r1e_variant_sweep.md): 2, except fp32 on launches of many waves (237 vs 246 us)
+    int u = (sizeof(T) == 4 && (long long)blocks > 8ll * ctx->sm_count) ? 4 : 2;
     if (const char *e = getenv("B200_COO_U")) u = atoi(e) == 4 ? 4 : (atoi(e) == 1 ? 1 : 2);
     if (!vec) coo_kernel<T, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
     else if (u == 4) coo_kernel<T, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);

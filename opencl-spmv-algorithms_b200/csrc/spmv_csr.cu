@@ -350,11 +350,17 @@ int pick_lanes(double mean_len, const char *override_env)
     return lanes;
 }
 
-// groups loaded per lane and round trip (row_dot_vec).  A launch of at most ~2 waves of resident
-// threads is a latency chain: batch deeper there.  Tuning hook: <env> = 1|2|4.
-int pick_unroll(const b200_ctx *ctx, long long threads, const char *override_env)
+// groups loaded per lane and round trip (row_dot_vec); tuning hook <env> = 1|2|4.
+// Measured on B200 (profiles/r1e_variant_sweep.md): deeper batching only costs registers once a
+// lane has ~4 groups in total, and fp64 groups are 48 bytes in flight already:
+//   CSR  fp32 -> 2;  fp64 -> 2 on launches of at most ~2 waves (cant), 1 on large ones
+//   ELL  fp32 -> 2 (4 on small launches);  fp64 -> 1
+int pick_unroll(const b200_ctx *ctx, long long threads, int value_bytes, bool ell, const char *override_env)
 {
-    int u = threads <= 2ll * ctx->sm_count * 2048 ? 4 : 2;
+    const bool small = threads <= 2ll * ctx->sm_count * 2048;
+    int u;
+    if (ell) u = value_bytes == 8 ? 1 : (small ? 4 : 2);
+    else u = (value_bytes == 4 || small) ? 2 : 1;
     if (const char *e = getenv(override_env)) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4) u = v;
@@ -492,7 +498,7 @@ int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data,
                    int n_rows, int long_threshold, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    const int u = pick_unroll(ctx, (long long)n_rows * LPR, "B200_CSR_UNROLL");
+    const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), false, "B200_CSR_UNROLL");
     if (!vec)
         csr_vector_kernel<T, LPR, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
     else if (u == 4)
@@ -569,7 +575,7 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
                    int row_size, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    const int u = pick_unroll(ctx, (long long)n_rows * LPR, "B200_ELL_UNROLL");
+    const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), true, "B200_ELL_UNROLL");
     if (!vec)
         ell_rowmajor_kernel<T, LPR, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
     else if (u == 4)

@@ -579,8 +579,11 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
     unsigned blocks = ceil_div_u((long long)n_slices * 32, kBlock);
     if (aligned16(data) && aligned16(idx)) {
         const int wmax = plan && plan->n_items > 0 ? plan->wmax : 0;
-        // B200_SELL_TMA=1: the bulk-copy (TMA engine) staged kernel, persistent grid
-        bool tma = false;
+        // The bulk-copy (TMA engine) staged kernel with its persistent grid is the default once every
+        // resident warp has at least ~8 chunks to walk (measured: 157 vs 162 us on the banded fp32
+        // workload, equal in fp64); smaller matrices want more, shorter-lived warps (WPC below).
+        // B200_SELL_TMA=0|1 overrides.
+        bool tma = (long long)n_slices >= 8ll * ctx->sm_count * 2 * (kBlock / 32);
         if (const char *e = getenv("B200_SELL_TMA")) tma = atoi(e) != 0;
         if (tma && wmax == 0) {
             constexpr size_t smem = (size_t)(kBlock / 32) * kStages * (kPiece * (sizeof(int) + sizeof(T)) + 8);
@@ -612,8 +615,9 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             const int v = atoi(e);
             if (wmax == 0 && (v == 1 || v == 2 || v == 4 || v == 8)) wpc = v;
         }
-        // groups per lane and round trip (tuning hook B200_SELL_UNROLL=1|2|4)
-        int u = (long long)n_slices * wpc <= 2ll * ctx->sm_count * 64 ? 4 : 2;
+        // groups per lane and round trip (tuning hook B200_SELL_UNROLL=1|2|4): 4 for whole-chunk
+        // warps, 2 once the chunk is shared by 4+ warps (cant: 11.3 us at WPC 4 / U 2 vs 18.3 at 1 / 1)
+        int u = wpc >= 4 ? 2 : 4;
         if (const char *e = getenv("B200_SELL_UNROLL")) {
             const int v = atoi(e);
             if (v == 1 || v == 2 || v == 4) u = v;
