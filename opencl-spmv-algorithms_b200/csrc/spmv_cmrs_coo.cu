@@ -315,10 +315,11 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     const int n_items = plan ? plan->n_items : 0;
     const int cap = n_items > 0 ? plan->cap : 0;
     const int2 *items = n_items > 0 ? plan->items : nullptr;
-    // U = groups loaded per lane and round trip.  Measured on B200 (profiles/r1e_variant_sweep.md):
-    // 1 everywhere (fp32 banded 236 vs 247 us, fp64 330 vs 431, cant 19.5 vs 21.4);
-    // tuning hook B200_CMRS_U=1|2
-    int u = 1;
+    // U = groups loaded per lane and round trip; tuning hook B200_CMRS_U=1|2.  Measured on B200
+    // (profiles/r1e_variant_sweep.md), sustained 200-step runs: fp32 2 (0.259 vs 0.284 ms), fp64 1
+    // (0.371 vs 0.444: 90 registers); launches of at most ~2 waves (cant): 1
+    const bool small = (long long)n_strips * 32 <= 2ll * ctx->sm_count * 2048;
+    int u = (sizeof(T) == 4 && !small) ? 2 : 1;
     if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
 #define B200_CMRS_LAUNCH2(H, V, UU)                                                                         \
     do {                                                                                                    \

@@ -165,18 +165,32 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+// suspend_ns > 0: the warp may be parked for up to that long before "not yet" is reported
+// (NANOSLEEP.SYNCS in SASS): a waiting warp should sleep, not poll
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity, unsigned suspend_ns)
 {
     unsigned done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+    if (suspend_ns > 0) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(suspend_ns)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
     return done != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
@@ -192,7 +206,7 @@ template <typename T, typename P>
 __global__ void __launch_bounds__(kBlock)
 sell32_tma_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
                   T *__restrict__ y, const P *__restrict__ slice_ptr, int n_slices, int n_out,
-                  const int *__restrict__ perm, int *__restrict__ err_flag)
+                  const int *__restrict__ perm, int *__restrict__ err_flag, unsigned suspend_ns)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kWarps = kBlock / 32;
@@ -256,9 +270,9 @@ sell32_tma_kernel(const T *__restrict__ data, const int *__restrict__ idx, const
         for (long long off = 0; off < n; off += kPiece) {
             const int stage = consumed % kStages;
             const unsigned parity = (consumed / kStages) & 1u;
-            if (!mbar_try_wait(bars + stage, parity)) {
+            if (!mbar_try_wait(bars + stage, parity, suspend_ns)) {
                 const unsigned long long t0 = global_timer_ns();
-                while (!mbar_try_wait(bars + stage, parity)) {
+                while (!mbar_try_wait(bars + stage, parity, suspend_ns)) {
                     if (global_timer_ns() - t0 > kWaitLimitNs) {
                         if (lane == 0) atomicExch(err_flag, 1);
                         return;
@@ -601,8 +615,11 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             B200_CUDA(cudaFuncSetAttribute(sell32_tma_kernel<T, P>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             const long long want = ((long long)n_slices + kBlock / 32 - 1) / (kBlock / 32);
             const unsigned grid = (unsigned)min(want, (long long)ctx->sm_count * per_sm);
+            // how long a waiting warp may sleep before it polls again (B200_SELL_TMA_SUSPEND_NS; 0 = poll)
+            unsigned suspend_ns = 1000;
+            if (const char *e = getenv("B200_SELL_TMA_SUSPEND_NS")) suspend_ns = (unsigned)atoi(e);
             sell32_tma_kernel<T, P><<<grid, kBlock, smem, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices, n_out, perm,
-                                                                        ctx->scratch + kWatchFlag);
+                                                                        ctx->scratch + kWatchFlag, suspend_ns);
             B200_LAUNCH_CHECK();
             ctx->watch_flag = true;
             return B200_SUCCESS;
