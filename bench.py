@@ -872,19 +872,32 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
     # over NVLink (CUDA IPC peer pointers); one 1-element all-reduce per step is all that is left
     fused_ms = None
     fused_norm = None
+    fused_full_ms = None
+    halo_bytes = None
     if fmt == "sell":
         bufs = pkg.PeerBuffers(pkg, ctx, blocks, rank, world)
-        pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[0].ptr, n, 11, 0.0, 1.0), "gen x0")
-        sync_all()
-        r0 = pkg.power_iteration_fused(pkg, ctx, mat, bufs, rank, blocks, args.warmup + (args.warmup % 2))
-        sync_all()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        r1 = pkg.power_iteration_fused(pkg, ctx, mat, bufs, rank, blocks, args.steps, first_step=r0.next_step, acc=r0.acc)
-        f1.record()
-        sync_all()
-        fused_ms = f0.elapsed_time(f1) / args.steps
-        fused_norm = r1.norm
+        # halo-limited exchange (default): every rank learns which of its rows the others read as
+        # columns (min/max column of each block, exchanged once) and the kernel stores only those
+        ranges = pkg.exchange_col_ranges(pkg, ctx, coo.cols, lo, world)
+        halo = pkg.halo_rows(ranges, blocks, rank)
+        halo_bytes = 8 * sum(h - l for d, (l, h) in enumerate(zip(*halo)) if d != rank)
+
+        def fused_run(h):
+            pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[0].ptr, n, 11, 0.0, 1.0), "gen x0")
+            pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[1].ptr, n, 11, 0.0, 1.0), "gen x0")
+            sync_all()
+            r0 = pkg.power_iteration_fused(pkg, ctx, mat, bufs, rank, blocks, args.warmup + (args.warmup % 2), halo=h)
+            sync_all()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            r1 = pkg.power_iteration_fused(pkg, ctx, mat, bufs, rank, blocks, args.steps, first_step=r0.next_step,
+                                           acc=r0.acc, halo=h)
+            f1.record()
+            sync_all()
+            return f0.elapsed_time(f1) / args.steps, r1.norm
+
+        fused_full_ms, _ = fused_run(None)
+        fused_ms, fused_norm = fused_run(halo)
         bufs.close()
 
     # split: SpMV alone and the all-gather alone, same buffers (explains the step time)
@@ -903,7 +916,8 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
     sync_all()
     gather_ms = a.elapsed_time(b) / 10
 
-    t = torch.tensor([step_ms, spmv_ms, gather_ms, float(nnz), fused_ms or 0.0], device="cuda", dtype=torch.float64)
+    t = torch.tensor([step_ms, spmv_ms, gather_ms, float(nnz), fused_ms or 0.0, fused_full_ms or 0.0,
+                      float(halo_bytes or 0)], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -911,6 +925,8 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         step_ms, spmv_ms, gather_ms, nnz_total = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tsum[3])
         fused_ms = float(tmax[4]) if fused_ms is not None else None
+        fused_full_ms = float(tmax[5]) if fused_full_ms is not None else None
+        halo_bytes = int(tmax[6]) if halo_bytes is not None else None
     else:
         nnz_total = float(nnz)
     nccl_ms = step_ms
@@ -930,8 +946,14 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
                                    f"{int(nnz_total)} nnz, fp64, {fmt.upper()}, {world} row block(s), NCCL all-gather of x per step",
                        "rows_per_gpu": int(n_local), "nnz_per_gpu": int(nnz),
                        "cache": "inputs larger than L2 (0.7 GB matrix + 2 x 64 MB x per GPU per world rank), no flush"},
-            "exchange": ("fused: SpMV kernel stores y into every rank's x buffer over NVLink (CUDA IPC) + 1-element "
-                         "NCCL all-reduce" if fused_ms is not None else "NCCL all_gather_into_tensor (in place)"),
+            "exchange": ("fused, halo-limited: the SpMV kernel stores each y row into the x buffers of the ranks that "
+                         "read it (its own + neighbours) over NVLink (CUDA IPC) + one 256-byte NCCL all-reduce"
+                         if fused_ms is not None else "NCCL all_gather_into_tensor (in place)"),
+            "fused_full_broadcast": (None if fused_full_ms is None else
+                                     {"ms_per_step": round(fused_full_ms, 5),
+                                      "gflops": round(2.0 * nnz_total / (fused_full_ms * 1e-3) * 1e-9, 2),
+                                      "what": "same kernel, every row to every rank (what an all-gather moves)"}),
+            "halo_bytes_sent_per_step_max_rank": halo_bytes,
             "nccl_allgather_formulation": {"ms_per_step": round(nccl_ms, 5),
                                            "gflops": round(2.0 * nnz_total / (nccl_ms * 1e-3) * 1e-9, 2),
                                            "split_ms": {"spmv": round(spmv_ms, 5), "all_gather": round(gather_ms, 5),

@@ -325,6 +325,18 @@ int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indic
                              const int *row_indices, int chunk, int n_slices, int n_rows,
                              const double *scale_sumsq, double *sumsq_out, double *const *dst,
                              int n_dst, long long dst_offset);
+/* Same kernel, halo-limited: destination d receives only rows [dst_row_lo[d], dst_row_hi[d]) of this
+ * rank's block (local row numbers; HOST arrays of n_dst ints; lo >= hi = nothing).  The caller passes,
+ * per destination, the rows that destination's matrix block actually reads as columns
+ * (b200_minmax_i32 over its column indices, exchanged once): the rank's own buffer gets the whole
+ * block, a neighbour the halo, everyone else nothing.  NULL, NULL = every row to every destination
+ * (b200_spmv_sell_bcast_f64).  SURVEY 8f.3. */
+int b200_spmv_sell_halo_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                            const int *row_indices, int chunk, int n_slices, int n_rows,
+                            const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
+                            long long dst_offset, const int *dst_row_lo, const int *dst_row_hi);
+/* min and max of a device int array (host outputs): the column range a row block reads */
+int b200_minmax_i32(b200_ctx *ctx, const int *a, long long n, int *min_out, int *max_out);
 /* CUDA IPC plumbing for the peers' buffers (allocations made with b200_malloc) */
 int b200_ipc_get_handle(b200_ctx *ctx, void *dptr, unsigned char handle[64]);
 int b200_ipc_open_handle(b200_ctx *ctx, const unsigned char handle[64], void **peer_dptr);

@@ -134,6 +134,8 @@ SIGNATURES = {
     "b200_gen_uniform_f64_host": (_i, [_vp, _ll, _u64, C.c_double, C.c_double]),
     "b200_partition_rows": (_i, [_vp, _i, _i, _i, _vp]),
     "b200_spmv_sell_bcast_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _ll]),
+    "b200_spmv_sell_halo_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
+    "b200_minmax_i32": (_i, [_vp, _vp, _ll, C.POINTER(_i), C.POINTER(_i)]),
     "b200_ipc_get_handle": (_i, [_vp, _vp, _vp]),
     "b200_ipc_open_handle": (_i, [_vp, _vp, _vpp]),
     "b200_ipc_close_handle": (_i, [_vp, _vp]),
@@ -334,5 +336,6 @@ class Event:
 
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix, CmrsPackedMatrix,  # noqa: E402,F401
                       algorithmic_bytes, build_all, partition_rows)
-from .iterate import (PeerBuffers, RowBlocks, equal_row_blocks, gpu_callables, power_iteration,  # noqa: E402,F401
+from .iterate import (PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges, gpu_callables, halo_rows,
+                      power_iteration,  # noqa: E402,F401
                       power_iteration_fused)

@@ -352,15 +352,16 @@ int pick_lanes(double mean_len, const char *override_env)
 
 // groups loaded per lane and round trip (row_dot_vec); tuning hook <env> = 1|2|4.
 // Measured on B200 (profiles/r1e_variant_sweep.md).  Large launches, sustained 200-step runs (the GPU
-// sits at its power cap there, and the deeper batch wins although a 10-launch burst shows no
-// difference): fp32 -> 4 (CSR 0.176 vs 0.179 ms, ELL 0.167 vs 0.172).  Launches of at most ~2 waves
-// (cant): CSR 2, ELL fp32 4 / fp64 1.
+// sits at its power cap there; a 10-launch burst shows no difference between the depths):
+//   fp32: 4 (CSR 0.176 vs 0.179 ms, ELL 0.167 vs 0.172);  fp64: 2 (CSR 0.261 vs 0.266 at 1 and 0.326
+//   at 4 -- 96 registers; ELL 0.252 / 0.255 / 0.289).
+// Launches of at most ~2 waves (cant): CSR 2; ELL fp32 4, fp64 1.
 int pick_unroll(const b200_ctx *ctx, long long threads, int value_bytes, bool ell, const char *override_env)
 {
     const bool small = threads <= 2ll * ctx->sm_count * 2048;
     int u;
-    if (ell) u = value_bytes == 8 ? 1 : 4;
-    else u = small ? 2 : (value_bytes == 4 ? 4 : 1);
+    if (ell) u = value_bytes == 4 ? 4 : (small ? 1 : 2);
+    else u = (value_bytes == 4 && !small) ? 4 : 2;
     if (const char *e = getenv(override_env)) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4) u = v;

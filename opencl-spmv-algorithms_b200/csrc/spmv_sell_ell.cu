@@ -355,6 +355,12 @@ constexpr int kMaxPeers = 16;
 template <typename T>
 struct PeerDst {
     T *p[kMaxPeers];
+    // rows [lo[d], hi[d]) of THIS rank's block (local numbering) that destination d reads as columns:
+    // the whole block for the rank itself, the halo for a neighbour, nothing (lo >= hi) for a rank
+    // whose rows never touch these columns.  A banded matrix then moves kilobytes per step instead of
+    // the full vector (7-point Laplacian: one 160 000-row plane per neighbour instead of 8 M rows to
+    // all 7 peers).
+    int lo[kMaxPeers], hi[kMaxPeers];
 };
 
 // ||y||^2 is accumulated by the same kernel into kSumsqSlots partial sums (one atomic per block,
@@ -382,34 +388,18 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
         const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
         const int *ip = idx + chunk_base;
         const T *dp = data + chunk_base;
-        // two groups per lane and round trip (a 7-point-stencil chunk is 56 groups: one round trip)
-        constexpr int U = 2;
-        for (long long g0 = lane; g0 < n_groups; g0 += 32 * U) {
-            IVec4 c[U];
-            Vec4<T> v[U];
-            T xv[U][4];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const long long g = g0 + 32 * u;
-                c[u].zero();
-                v[u].zero();
-                if (g < n_groups) {
-                    c[u].load(ip + (g << 2));
-                    v[u].load(dp + (g << 2));
-                }
-            }
-            const int hold = batch_hold<U, T>(c, v);  // 0; orders the gathers after ALL loads (common.cuh)
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) xv[u][k] = ld_x(x, c[u].v[k] + hold);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                acc0 += v[u].v[0] * xv[u][0];
-                acc1 += v[u].v[1] * xv[u][1];
-                acc2 += v[u].v[2] * xv[u][2];
-                acc3 += v[u].v[3] * xv[u][3];
-            }
+        // one group per lane and round trip: a 7-point-stencil chunk is only 56 groups, and the
+        // batched form (58 registers) measured slower here (0.196 vs 0.189 ms per step)
+#pragma unroll 4
+        for (long long g = lane; g < n_groups; g += 32) {
+            IVec4 c;
+            Vec4<T> v;
+            c.load(ip + (g << 2));
+            v.load(dp + (g << 2));
+            acc0 += v.v[0] * ld_x(x, c.v[0]);
+            acc1 += v.v[1] * ld_x(x, c.v[1]);
+            acc2 += v.v[2] * ld_x(x, c.v[2]);
+            acc3 += v.v[3] * ld_x(x, c.v[3]);
         }
     }
 #pragma unroll
@@ -437,10 +427,12 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
         for (int d = 0; d < kMaxPeers; ++d) {
             if (d < n_dst) {
                 T *out = dst.p[d] + dst_offset + r;
-                if (r + 1 < n_rows) {
+                const long long first = dst.lo[d], last = min((long long)dst.hi[d], (long long)n_rows);
+                if (r >= first && r + 1 < last) {
                     *reinterpret_cast<double2 *>(out) = make_double2(lo, hi);
-                } else if (r < n_rows) {
-                    out[0] = lo;
+                } else {
+                    if (r >= first && r < last) out[0] = lo;
+                    if (r + 1 >= first && r + 1 < last) out[1] = hi;
                 }
             }
         }
@@ -593,11 +585,12 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
     unsigned blocks = ceil_div_u((long long)n_slices * 32, kBlock);
     if (aligned16(data) && aligned16(idx)) {
         const int wmax = plan && plan->n_items > 0 ? plan->wmax : 0;
-        // The bulk-copy (TMA engine) staged kernel with its persistent grid is the default once every
-        // resident warp has at least ~8 chunks to walk (measured: 157 vs 162 us on the banded fp32
-        // workload, equal in fp64); smaller matrices want more, shorter-lived warps (WPC below).
-        // B200_SELL_TMA=0|1 overrides.
-        bool tma = (long long)n_slices >= 8ll * ctx->sm_count * 2 * (kBlock / 32);
+        // B200_SELL_TMA=1 selects the bulk-copy (TMA engine) staged kernel with its persistent grid.
+        // Opt-in: measured on B200 (profiles/r1e_variant_sweep.md) it is the fastest SELL kernel in
+        // isolation on wide chunks (banded fp32: 157-161 us vs 162-174, a third of the L1 traffic),
+        // equal within 1 % in sustained power-capped runs (0.1689 vs 0.1671 ms), 5 % slower in fp64,
+        // and much slower on narrow chunks (7-point stencil: 2.7 KB pieces, 0.248 vs 0.161 ms).
+        bool tma = false;
         if (const char *e = getenv("B200_SELL_TMA")) tma = atoi(e) != 0;
         if (tma && wmax == 0) {
             constexpr size_t smem = (size_t)(kBlock / 32) * kStages * (kPiece * (sizeof(int) + sizeof(T)) + 8);
@@ -767,6 +760,15 @@ int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indic
                              const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
                              long long dst_offset)
 {
+    return b200_spmv_sell_halo_f64(ctx, data, indices, vect, row_indices, chunk, n_slices, n_rows, scale_sumsq,
+                                   sumsq_out, dst, n_dst, dst_offset, nullptr, nullptr);
+}
+
+int b200_spmv_sell_halo_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                            const int *row_indices, int chunk, int n_slices, int n_rows,
+                            const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
+                            long long dst_offset, const int *dst_row_lo, const int *dst_row_hi)
+{
     B200_ENTER(ctx);
     B200_REQUIRE(vect && row_indices && dst && n_slices >= 0 && n_rows >= 0 && dst_offset >= 0, "bad argument");
     B200_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers, "n_dst must be in 1..16");
@@ -778,8 +780,14 @@ int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indic
     B200_REQUIRE(aligned16(data) && aligned16(indices), "SELL arrays must be 16-byte aligned");
     if (n_slices == 0) return B200_SUCCESS;
     PeerDst<double> d;
-    for (int i = 0; i < kMaxPeers; ++i) d.p[i] = i < n_dst ? dst[i] : nullptr;
+    B200_REQUIRE((dst_row_lo == nullptr) == (dst_row_hi == nullptr), "give both row-range arrays or neither");
+    for (int i = 0; i < kMaxPeers; ++i) {
+        d.p[i] = i < n_dst ? dst[i] : nullptr;
+        d.lo[i] = (i < n_dst && dst_row_lo) ? dst_row_lo[i] : 0;
+        d.hi[i] = i < n_dst ? (dst_row_hi ? dst_row_hi[i] : n_rows) : 0;
+    }
     for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
+    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.lo[i] >= 0, "negative row range");
     sell32_bcast_kernel<double, int><<<ceil_div_u((long long)n_slices * 32, kBlock), kBlock, 0, ctx->stream>>>(
         data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
     B200_LAUNCH_CHECK();

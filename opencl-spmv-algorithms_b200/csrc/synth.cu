@@ -165,6 +165,25 @@ __global__ void sumsq_kernel(const double *__restrict__ y, long long n, double *
     }
 }
 
+__global__ void minmax_kernel(const int *__restrict__ a, long long n, int *__restrict__ out)
+{
+    int lo = 0x7fffffff, hi = (int)0x80000000;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int v = a[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
 inline unsigned capped_grid(const b200_ctx *ctx, long long n)
 {
     long long b = (n + kBlock - 1) / kBlock;
@@ -317,6 +336,26 @@ int b200_sumsq_f64(b200_ctx *ctx, const double *y, long long n, double *acc_devi
     if (n == 0) return B200_SUCCESS;
     sumsq_kernel<<<capped_grid(ctx, n), kBlock, 0, ctx->stream>>>(y, n, acc_device);
     B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_minmax_i32(b200_ctx *ctx, const int *a, long long n, int *min_out, int *max_out)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(n >= 0 && min_out && max_out && (n == 0 || a), "bad argument");
+    *min_out = 0x7fffffff;
+    *max_out = (int)0x80000000;
+    if (n == 0) return B200_SUCCESS;
+    int *d = ctx->scratch + 256;
+    const int init[2] = {0x7fffffff, (int)0x80000000};
+    B200_CUDA(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    minmax_kernel<<<capped_grid(ctx, n), kBlock, 0, ctx->stream>>>(a, n, d);
+    B200_LAUNCH_CHECK();
+    int got[2];
+    B200_CUDA(cudaMemcpyAsync(got, d, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    *min_out = got[0];
+    *max_out = got[1];
     return B200_SUCCESS;
 }
 

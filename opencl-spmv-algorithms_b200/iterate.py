@@ -169,11 +169,55 @@ class PeerBuffers:
         self._opened = []
 
 
+def halo_rows(col_ranges, blocks: RowBlocks, rank: int):
+    """Which rows of rank `rank`'s block each rank reads as columns.
+
+    col_ranges[d] = (cmin_d, cmax_d): smallest / largest column index in rank d's matrix block
+    (b200_minmax_i32 over its column array, exchanged once with all_gather).  Returns (lo, hi): two
+    lists of LOCAL row numbers, destination d needs rows [lo[d], hi[d]) of this rank's y-block; the
+    rank itself always gets its whole block (it is the next x of its own rows AND the result).
+    Pure host function (also exercised on CPU in tests/test_distributed_cpu.py)."""
+    b0, b1 = blocks.bounds(rank)
+    lo, hi = [], []
+    for d, (cmin, cmax) in enumerate(col_ranges):
+        if d == rank:
+            lo.append(0)
+            hi.append(b1 - b0)
+            continue
+        first, last = max(int(cmin), b0), min(int(cmax) + 1, b1)
+        if last <= first:
+            lo.append(0)
+            hi.append(0)
+        else:
+            lo.append(first - b0)
+            hi.append(last - b0)
+    return lo, hi
+
+
+def exchange_col_ranges(pkg, ctx, cols, row_begin: int, world: int):
+    """(cmin, cmax) of every rank's column array `cols` (device, GLOBAL column indices): one tiny
+    reduction on the device + one all_gather of two ints."""
+    import ctypes as C
+    lo, hi = C.c_int(0), C.c_int(0)
+    pkg.check(pkg.lib().b200_minmax_i32(ctx.h, cols.ptr, cols.n, C.byref(lo), C.byref(hi)), "b200_minmax_i32")
+    mine = (lo.value, hi.value)
+    if world == 1:
+        return [mine]
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    return out
+
+
 def power_iteration_fused(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: RowBlocks, steps: int,
-                          first_step: int = 0, acc=None) -> IterationResult:
+                          first_step: int = 0, acc=None, halo=None) -> IterationResult:
     """`steps` power-iteration steps with the fused SpMV + exchange kernel.  bufs.local[first_step % 2]
     holds the current (unnormalised) vector on every rank; `acc` carries the two ||y||^2 scalars
-    between calls (pass the returned result's .acc back in to continue a run)."""
+    between calls (pass the returned result's .acc back in to continue a run).
+
+    halo = (lo, hi) from halo_rows(): every destination receives only the rows it reads (its own block
+    in full); the buffers then hold a rank's own block plus its halo, not the whole vector.
+    halo = None: every row goes to every rank (the buffers hold the whole vector, as an all-gather)."""
     import torch
     import torch.distributed as dist
     L = pkg.lib()
@@ -182,6 +226,12 @@ def power_iteration_fused(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: 
     if acc is None:
         acc = [torch.zeros(slots, dtype=torch.float64, device="cuda") for _ in range(2)]
     assert sell.perm is None and sell.row_indices is not None, "fused path: SELL-32, sigma = 1, int32 pointers"
+    row_lo = row_hi = None
+    if halo is not None:
+        import ctypes as C
+        assert len(halo[0]) == bufs.world and len(halo[1]) == bufs.world
+        row_lo = (C.c_int * bufs.world)(*halo[0])
+        row_hi = (C.c_int * bufs.world)(*halo[1])
 
     def step(k):
         """One launch + one tiny all-reduce: memset of the 32 slots, the fused kernel, NCCL."""
@@ -189,10 +239,10 @@ def power_iteration_fused(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: 
         scale = acc[(k - 1) % 2].data_ptr() if k > 0 else None
         a = acc[k % 2]
         pkg.check(L.b200_memset_async(ctx.h, a.data_ptr(), 0, 8 * slots), "b200_memset_async")
-        pkg.check(L.b200_spmv_sell_bcast_f64(ctx.h, sell.data.ptr, sell.cols.ptr, bufs.local[cur].ptr,
-                                             sell.row_indices.ptr, 32, sell.n_slices, n_local, scale,
-                                             a.data_ptr(), bufs.dst[nxt], bufs.world, rank * blocks.count),
-                  "b200_spmv_sell_bcast_f64")
+        pkg.check(L.b200_spmv_sell_halo_f64(ctx.h, sell.data.ptr, sell.cols.ptr, bufs.local[cur].ptr,
+                                            sell.row_indices.ptr, 32, sell.n_slices, n_local, scale,
+                                            a.data_ptr(), bufs.dst[nxt], bufs.world, rank * blocks.count,
+                                            row_lo, row_hi), "b200_spmv_sell_halo_f64")
         if bufs.world > 1:
             dist.all_reduce(a, op=dist.ReduceOp.SUM)  # the norm AND the barrier that orders peer writes
 

@@ -141,3 +141,28 @@ def test_equal_row_blocks():
     assert [b.bounds(r) for r in range(3)] == [(0, 352), (352, 704), (704, 1000)]
     b = pkg.equal_row_blocks(40, 4)       # more ranks than blocks of 32: trailing ranks own nothing
     assert [b.bounds(r) for r in range(4)] == [(0, 32), (32, 40), (40, 40), (40, 40)]
+
+
+def test_halo_rows_from_column_ranges():
+    """halo_rows: the rows of a rank's block that every other rank reads as columns (host logic of
+    the halo-limited fused exchange)."""
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    blocks = pkg.equal_row_blocks(1000, 4)            # 256 rows per rank, last block 232
+    ranges = [(0, 300), (200, 600), (400, 800), (700, 999)]
+    assert pkg.halo_rows(ranges, blocks, 1) == ([0, 0, 144, 0], [45, 256, 256, 0])
+    assert pkg.halo_rows(ranges, blocks, 3) == ([0, 0, 0, 0], [0, 0, 33, 232])
+    # a rank whose columns span everything gets every block in full; nobody else gets anything
+    full = [(0, 999), (300, 400), (600, 700), (800, 900)]
+    for r in range(4):
+        lo, hi = pkg.halo_rows(full, blocks, r)
+        b0, b1 = blocks.bounds(r)
+        assert (lo[0], hi[0]) == (0, b1 - b0)
+        assert all(hi[d] - lo[d] == 0 for d in range(1, 4) if d != r)
+    # 7-point Laplacian blocks: one plane to each neighbour
+    nx = ny = 10
+    blocks = pkg.equal_row_blocks(nx * ny * 40, 4, align=32)
+    ranges = [(max(blocks.bounds(r)[0] - nx * ny, 0), min(blocks.bounds(r)[1] + nx * ny, blocks.n_rows) - 1)
+              for r in range(4)]
+    lo, hi = pkg.halo_rows(ranges, blocks, 2)
+    assert [h - l for l, h in zip(lo, hi)] == [0, 100, blocks.count, 100]

@@ -216,3 +216,77 @@ def test_fused_power_iteration_one_gpu(ctx):
     assert np.max(np.abs(y_un / np.linalg.norm(y_un) - x)) <= 1e-12
     bufs.close()
     tctx.close()
+
+
+def test_halo_limited_exchange_three_emulated_ranks(ctx):
+    """b200_spmv_sell_halo_f64: three row blocks of a 7-point Laplacian run one after the other on ONE
+    GPU, each storing into the next-x buffers of all three 'ranks' but only the rows the destination
+    reads (halo_rows from the blocks' column ranges).  The all-reduce of ||y||^2 is emulated on the
+    host.  Must reproduce the CPU power iteration; rows outside a rank's block + halo must never be
+    touched."""
+    import ctypes as C
+    L = pkg.lib()
+    nx, ny, nz, steps, G = 16, 12, 30, 25, 3
+    n, rows, cols, vals = laplace7(nx, ny, nz)
+    blocks = pkg.equal_row_blocks(n, G)
+    rng = np.random.default_rng(5)
+    x0 = np.zeros(blocks.padded)
+    x0[:n] = rng.uniform(0, 1, n)
+    ptr, _ = O.build_csr(n, rows)
+    x = x0[:n].copy()
+    for _ in range(steps):
+        y = O.spmv_csr(n, ptr, cols, vals, x)
+        nrm = np.linalg.norm(y)
+        x = y / nrm
+    sells, ranges, n_local = [], [], []
+    for r in range(G):
+        b0, b1 = blocks.bounds(r)
+        sel = slice(ptr[b0], ptr[b1])
+        coo = pkg.CooMatrix.from_host(ctx, b1 - b0, n, rows[sel] - b0, cols[sel], vals[sel])
+        sells.append(pkg.SellMatrix(pkg.CsrMatrix(coo), np.float64))
+        lo, hi = C.c_int(0), C.c_int(0)
+        pkg.check(L.b200_minmax_i32(ctx.h, coo.cols.ptr, coo.nnz, C.byref(lo), C.byref(hi)), "minmax")
+        assert (lo.value, hi.value) == (int(cols[sel].min()), int(cols[sel].max()))
+        ranges.append((lo.value, hi.value))
+        n_local.append(b1 - b0)
+    halos = [pkg.halo_rows(ranges, blocks, r) for r in range(G)]
+    plane = nx * ny
+    # rank 1 reads rank 0's LAST plane, rank 2 nothing of it; rank 1 feeds its first plane to rank 0 and
+    # its last plane to rank 2
+    assert halos[0] == ([0, n_local[0] - plane, 0], [n_local[0], n_local[0], 0])
+    assert halos[1] == ([0, 0, n_local[1] - plane], [plane, n_local[1], n_local[1]])
+    SENTINEL = -7.0
+    # bufs[r][b]: buffer b of emulated rank r; untouched entries keep the sentinel
+    bufs = [[ctx.array(np.where(np.arange(blocks.padded) < n, x0, 0.0) if b == 0 else
+                       np.full(blocks.padded, SENTINEL)) for b in range(2)] for r in range(G)]
+    acc = [[ctx.zeros(32, np.float64) for _ in range(2)] for r in range(G)]
+    for k in range(steps):
+        cur, nxt = k % 2, (k + 1) % 2
+        for r in range(G):
+            dst = (C.c_void_p * G)(*[bufs[d][nxt].ptr for d in range(G)])
+            lo_a, hi_a = (C.c_int * G)(*halos[r][0]), (C.c_int * G)(*halos[r][1])
+            acc[r][k % 2].fill_bytes(0)
+            pkg.check(L.b200_spmv_sell_halo_f64(
+                ctx.h, sells[r].data.ptr, sells[r].cols.ptr, bufs[r][cur].ptr, sells[r].row_indices.ptr, 32,
+                sells[r].n_slices, n_local[r], acc[r][(k - 1) % 2].ptr if k > 0 else None, acc[r][k % 2].ptr,
+                dst, G, r * blocks.count, lo_a, hi_a), "b200_spmv_sell_halo_f64")
+        total = np.zeros(32)
+        for r in range(G):                      # the all-reduce
+            total += acc[r][k % 2].download()
+        for r in range(G):
+            acc[r][k % 2].upload(total)
+        ctx.sync()
+    assert abs(np.sqrt(total.sum()) - nrm) <= 1e-12 * nrm
+    last = steps % 2
+    for r in range(G):
+        got = bufs[r][last].download()
+        b0, b1 = blocks.bounds(r)
+        own = got[b0:b1]
+        y_own = own / np.sqrt(total.sum())       # buffers hold the unnormalised A x_{k-1}
+        assert np.max(np.abs(y_own - x[b0:b1])) <= 1e-12
+        need_lo, need_hi = max(b0 - plane, 0), min(b1 + plane, n)
+        outside = np.ones(blocks.padded, bool)
+        outside[need_lo:need_hi] = False
+        if steps % 2 == 1:                       # buffer 1 started as sentinels: nothing outside block + halo written
+            assert np.all(got[outside] == SENTINEL), r
+        assert not np.any(got[need_lo:need_hi] == SENTINEL)
