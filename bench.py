@@ -372,6 +372,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    overlap = None
     if n_copies == 1:
         for _ in range(args.warmup):
             for f in mats:
@@ -442,6 +443,32 @@ def main():
                     reps.append(a.elapsed_ms_until(b) / n_f)
                 per_ms[f] = float(np.mean(reps))
         step_ms = total_ms / args.steps
+
+        # the same graphs recorded with launch overlap on (b200_ctx_set_launch_overlap: programmatic
+        # dependent launch -- every kernel streams its matrix arrays while its predecessor drains and
+        # touches x / y only after it has finished).  Reported next to the in-order numbers.
+        ctx.set_launch_overlap(True)
+        g_steps_o = record_steps(args.steps)
+        g_fmt_o = {f: record_format(f, 0, n_f) for f in mats}
+        ctx.set_launch_overlap(False)
+        g_steps_o.launch()
+        barrier()
+        e0.record()
+        g_steps_o.launch()
+        e1.record()
+        barrier()
+        overlap = {"ms_per_step": e0.elapsed_ms_until(e1) / args.steps, "formats": {}}
+        for f in mats:
+            g_fmt_o[f].launch()
+            reps = []
+            for _ in range(5):
+                a, b = ctx.event(), ctx.event()
+                a.record()
+                g_fmt_o[f].launch()
+                b.record()
+                ctx.sync()
+                reps.append(a.elapsed_ms_until(b) / n_f)
+            overlap["formats"][f] = float(np.mean(reps))
 
     # extra (untimed for the headline): the column-major ELL kernel, same method
     for f in extra:
@@ -650,7 +677,16 @@ def main():
                                  f"arrays ({min(bytes_alg.values()) >> 20}-{max(bytes_alg.values()) >> 20} MiB each), launch i "
                                  f"reads copy i mod {n_copies}; no flush; the K steps are one CUDA-graph replay" if n_copies > 1 else
                                  "inputs larger than L2 (0.8-1.6 GB per format), no flush")},
-            "formats": fm, "formats_flush_each_launch_context_only": flushed,
+            "formats": fm,
+            "launch_overlap": (None if overlap is None else {
+                "what": "same K-step graph with b200_ctx_set_launch_overlap(1): kernels are programmatic dependents "
+                        "(matrix arrays streamed while the previous launch drains; x read / y written after it ends); "
+                        "COO unchanged (its y memset node is not a kernel)",
+                "ms_per_step": round(overlap["ms_per_step"], 5),
+                "value": round(flops_step / (overlap["ms_per_step"] * 1e-3) * 1e-9, 2),
+                "formats": {f: {"ms": round(ms, 5), "frac_measured": round(bytes_alg[f] / (ms * 1e-3) * 1e-9 / peak, 4)}
+                            for f, ms in overlap["formats"].items()}}),
+            "formats_flush_each_launch_context_only": flushed,
             "formats_warm_l2_context_only": warm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(args.steps * len(mats)), "clocks": clk.summary(),
         }

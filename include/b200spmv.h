@@ -69,6 +69,16 @@ int b200_ctx_device(const b200_ctx *ctx, int *device);
  * bytes = 0 clears the window.  New: the OpenCL reference has no equivalent. */
 int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes);
 
+/* Launch overlap (new; programmatic dependent launch).  With enable != 0 the CSR / ELL / SELL / CMRS
+ * launches on this context may START before earlier work on its queue has finished: they stream
+ * their row pointers and the first batch of indices/values at once and read `vect` / write `output`
+ * only after everything queued before them has completed.  Results are unchanged; the ~2 us of launch
+ * ramp and drain between consecutive small launches (a cant-sized SpMV lasts ~12 us) overlap.
+ * Contract: while it is enabled the caller must not enqueue work that WRITES a matrix array (uploads,
+ * builds, packs) directly before an SpMV that reads it without a b200_sync in between.  Default off:
+ * the in-order semantics of the reference's queue (csr.c:115). */
+int b200_ctx_set_launch_overlap(b200_ctx *ctx, int enable);
+
 /* ---- buffers: clCreateBuffer (csr.c:123-127), clReleaseMemObject (csr.c:260-263),
  *      clEnqueueWriteBuffer (csr.c:183-186), clEnqueueReadBuffer (csr.c:220), clFinish ---- */
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);

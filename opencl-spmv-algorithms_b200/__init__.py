@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200_event_record": (_i, [_vp, _vp]),
     "b200_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
     "b200_event_destroy": (_i, [_vp]),
+    "b200_ctx_set_launch_overlap": (_i, [_vp, _i]),
     "b200_graph_begin": (_i, [_vp]),
     "b200_graph_end": (_i, [_vp, _vpp]),
     "b200_graph_launch": (_i, [_vp, _vp]),
@@ -264,6 +265,11 @@ class Context:
     def set_l2_persist(self, arr: DeviceArray | None) -> None:
         check(lib().b200_ctx_set_l2_persist(self.h, arr.ptr if arr else None,
                                             arr.nbytes if arr else 0), "b200_ctx_set_l2_persist")
+
+    def set_launch_overlap(self, enable: bool) -> None:
+        """b200_ctx_set_launch_overlap: SpMV launches become programmatic dependents (see the header
+        for the contract: no un-synchronised writes to matrix arrays while enabled)."""
+        check(lib().b200_ctx_set_launch_overlap(self.h, 1 if enable else 0), "b200_ctx_set_launch_overlap")
 
     def event(self) -> "Event":
         return Event(self)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/b200spmv.h"
 
@@ -21,6 +22,8 @@ struct b200_ctx {
     int *scratch;          // small device scratch (flags / counters), 4 KiB
     void *host_scratch;    // pinned, 4 KiB, for small readbacks
     bool watch_flag;       // a bulk-copy kernel ran since the last sync: b200_sync reads kWatchFlag
+    bool overlap;          // b200_ctx_set_launch_overlap: SpMV kernels are launched as programmatic
+                           // dependents (they stream their matrix arrays while earlier work drains)
 };
 // scratch[kWatchFlag]: set by a kernel whose mbarrier wait ran into its spin limit (never expected;
 // reported by the next b200_sync / b200_memcpy_d2h instead of hanging the device)
@@ -71,6 +74,26 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 static inline unsigned ceil_div_u(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+// Launch on the context's stream; with ctx->overlap the kernel is a programmatic dependent of the
+// previous kernel on the stream (see pdl_wait below).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b200_launch(const b200_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                      size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------
 // Loads.  Matrix arrays (indices, values) are read exactly once per SpMV: stream them with
 // evict-first (ld.global.cs) so they do not push x out of L1/L2.  x is gathered through the
@@ -140,6 +163,29 @@ struct IVec4 {
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 };
+
+// Programmatic dependent launch (PDL), template flag OVL on the SpMV kernels.  An OVL kernel lets its
+// successor start at once (launch_dependents at the top) and reads x / writes y only after
+// pdl_wait_once(), i.e. after all earlier work on the stream has completed and is visible; what it
+// does BEFORE the wait -- row pointers and the first batch of index/value loads -- touches only the
+// matrix arrays.  x must then be gathered with COHERENT loads (ld.global.ca): ptxas treats
+// ld.global.nc data as immutable and hoists such loads above griddepcontrol.wait (seen in SASS: the
+// gathers landed before ACQBULK), which would read x while the previous launch is still writing it.
+// OVL = false (the default launch path) compiles to exactly the kernels without any of this.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+template <bool OVL>
+__device__ __forceinline__ void pdl_wait_once(bool &waited)
+{
+    if (OVL && !waited) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        waited = true;
+    }
+}
+template <bool OVL, typename T>
+__device__ __forceinline__ T ld_xo(const T *x, int c)
+{
+    return OVL ? __ldca(x + c) : __ldg(x + c);
+}
 
 // Load batching.  The kernels issue U groups of matrix loads, then the x gathers, then the FMAs.
 // ptxas, left alone, sinks the later loads of a batch below the first gathers (fewer live

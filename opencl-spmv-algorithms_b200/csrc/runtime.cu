@@ -102,6 +102,7 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool own, b200_ctx *
     c->scratch = nullptr;
     c->host_scratch = nullptr;
     c->watch_flag = false;
+    c->overlap = false;
     if (own) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -178,6 +179,13 @@ int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes)
 }
 
 static int check_watch_flag(b200_ctx *ctx);
+
+int b200_ctx_set_launch_overlap(b200_ctx *ctx, int enable)
+{
+    B200_REQUIRE(ctx, "null context");
+    ctx->overlap = enable != 0;
+    return B200_SUCCESS;
+}
 
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
 {

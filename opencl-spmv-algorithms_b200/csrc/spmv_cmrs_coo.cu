@@ -51,12 +51,14 @@ __device__ __forceinline__ void cmrs_flush(T (&acc)[HMAX], int key, T sum)
 constexpr int kPackShift = 27;  // 5 key bits (height <= 32), columns < 2^27
 constexpr int kPackMask = (1 << kPackShift) - 1;
 
-template <typename T, int HMAX, bool VEC, int U, bool EXTRA, bool PACKED = false>
+template <typename T, int HMAX, bool VEC, int U, bool EXTRA, bool PACKED = false, bool OVL = false>
 __global__ void __launch_bounds__(kBlock)
 cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *__restrict__ strip_ptr,
             const int *__restrict__ row_in_strip, const T *__restrict__ x, T *__restrict__ y,
             int n_work, int height, int n_rows, int cap, const int2 *__restrict__ items)
 {
+    pdl_launch_dependents();
+    bool waited = false;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long work = (long long)blockIdx.x * kWarps + warp;
     if (work >= n_work) return;  // whole warps leave together
@@ -104,12 +106,13 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
                     }
                 }
             }
+            pdl_wait_once<OVL>(waited);  // x may still be being written by the previous launch (common.cuh)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int j = (g0 + 4 * u) << 2;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    xv[u][k] = (g0 + 4 * u < g_end && j + k >= ss && j + k < ee) ? ld_x(x, c[u].v[k]) : T(0);
+                    xv[u][k] = (g0 + 4 * u < g_end && j + k >= ss && j + k < ee) ? ld_xo<OVL>(x, c[u].v[k]) : T(0);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -135,6 +138,7 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
             }
         }
     } else {
+        pdl_wait_once<OVL>(waited);
         for (int j = ss + (lane & 3); j < ee; j += 4) {
             int c = ld_stream(idx + j);
             const int r = PACKED ? (int)((unsigned)c >> kPackShift) : ld_stream(row_in_strip + j);
@@ -144,10 +148,11 @@ cmrs_kernel(const T *__restrict__ data, const int *__restrict__ idx, const int *
                 cur = r;
                 sum = 0;
             }
-            sum += ld_stream(data + j) * ld_x(x, c);
+            sum += ld_stream(data + j) * ld_xo<OVL>(x, c);
         }
     }
     cmrs_flush<T, HMAX>(acc, cur, sum);
+    pdl_wait_once<OVL>(waited);  // lanes without entries never waited: y must not be written early either
 
     // transposing butterfly: after the HMAX-halving steps lane L holds the partial of row
     // (L % HMAX) over the lanes of its HMAX-group; plain xor steps finish the sum.
@@ -323,8 +328,13 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
 #define B200_CMRS_LAUNCH2(H, V, UU)                                                                         \
     do {                                                                                                    \
-        cmrs_kernel<T, H, V, UU, false, PACKED><<<ceil_div_u(n_strips, kWarps), kBlock, 0, ctx->stream>>>(   \
-            data, idx, strip_ptr, row_in_strip, x, y, n_strips, height, n_rows, cap, nullptr);              \
+        B200_CUDA(ctx->overlap                                                                              \
+                      ? b200_launch(ctx, cmrs_kernel<T, H, V, UU, false, PACKED, true>,                     \
+                                    dim3(ceil_div_u(n_strips, kWarps)), dim3(kBlock), 0, data, idx, strip_ptr, \
+                                    row_in_strip, x, y, n_strips, height, n_rows, cap, nullptr)             \
+                      : b200_launch(ctx, cmrs_kernel<T, H, V, UU, false, PACKED, false>,                    \
+                                    dim3(ceil_div_u(n_strips, kWarps)), dim3(kBlock), 0, data, idx, strip_ptr, \
+                                    row_in_strip, x, y, n_strips, height, n_rows, cap, nullptr));           \
         if (n_items > 0)                                                                                    \
             cmrs_kernel<T, H, V, UU, true, PACKED><<<ceil_div_u(n_items, kWarps), kBlock, 0, ctx->stream>>>( \
                 data, idx, strip_ptr, row_in_strip, x, y, n_items, height, n_rows, cap, items);             \

@@ -27,9 +27,10 @@ constexpr int kBlock = 256;
 // load -> gather -> FMA -> load ... (cuobjdump -sass), i.e. one round trip per group: fine when
 // dozens of warps per SM hide it, a latency chain on matrices of one or two waves (cant).
 // U = 1 keeps the register count at 32 (full occupancy); U = 2 / 4 trade occupancy for loads in flight.
-template <typename T, int LPR, int U = 2>
+template <typename T, int LPR, int U, bool OVL>
 __device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *__restrict__ data,
-                                         const T *__restrict__ x, long long s, long long e, int lane)
+                                         const T *__restrict__ x, long long s, long long e, int lane,
+                                         bool &waited)
 {
     T acc0 = 0, acc1 = 0;
     const long long g_end = (e + 3) >> 2;
@@ -48,6 +49,7 @@ __device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *_
             }
         }
         const int hold = batch_hold<U, T>(c, v);  // 0; orders the gathers after ALL loads (common.cuh)
+        pdl_wait_once<OVL>(waited);  // x may still be being written by the previous launch (common.cuh)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long long j = (g0 + (long long)u * LPR) << 2;
@@ -55,7 +57,7 @@ __device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *_
             for (int k = 0; k < 4; ++k) {
                 // j + k < e implies the group was loaded; masked slots contribute exactly +0
                 const bool ok = j + k >= s && j + k < e;
-                xv[u][k] = ok ? ld_x(x, c[u].v[k] + hold) : T(0);
+                xv[u][k] = ok ? ld_xo<OVL>(x, c[u].v[k] + hold) : T(0);
                 if (!ok) v[u].v[k] = T(0);
             }
         }
@@ -71,20 +73,24 @@ __device__ __forceinline__ T row_dot_vec(const int *__restrict__ col, const T *_
 }
 
 // same, scalar loads: used only when an array is not 16-byte aligned
-template <typename T, int LPR>
+template <typename T, int LPR, bool OVL>
 __device__ __forceinline__ T row_dot_scalar(const int *__restrict__ col, const T *__restrict__ data,
-                                            const T *__restrict__ x, long long s, long long e, int lane)
+                                            const T *__restrict__ x, long long s, long long e, int lane,
+                                            bool &waited)
 {
     T acc = 0;
-    for (long long j = s + lane; j < e; j += LPR) acc += ld_stream(data + j) * ld_x(x, ld_stream(col + j));
+    pdl_wait_once<OVL>(waited);
+    for (long long j = s + lane; j < e; j += LPR) acc += ld_stream(data + j) * ld_xo<OVL>(x, ld_stream(col + j));
     return acc;
 }
 
-template <typename T, int LPR, bool VEC, int U>
+template <typename T, int LPR, bool VEC, int U, bool OVL>
 __global__ void __launch_bounds__(kBlock)
 csr_vector_kernel(const int *__restrict__ ptr, const int *__restrict__ col, const T *__restrict__ data,
                   const T *__restrict__ x, T *__restrict__ y, int n_rows, int long_threshold)
 {
+    pdl_launch_dependents();
+    bool waited = false;
     const int lane = threadIdx.x & (LPR - 1);
     const long long row = ((long long)blockIdx.x * kBlock + threadIdx.x) / LPR;
     int s = 0, e = 0;
@@ -95,8 +101,9 @@ csr_vector_kernel(const int *__restrict__ ptr, const int *__restrict__ col, cons
     const bool is_long = (e - s) > long_threshold;
     T acc = 0;
     if (!is_long)
-        acc = VEC ? row_dot_vec<T, LPR, U>(col, data, x, s, e, lane)
-                  : row_dot_scalar<T, LPR>(col, data, x, s, e, lane);
+        acc = VEC ? row_dot_vec<T, LPR, U, OVL>(col, data, x, s, e, lane, waited)
+                  : row_dot_scalar<T, LPR, OVL>(col, data, x, s, e, lane, waited);
+    pdl_wait_once<OVL>(waited);  // rows without entries never waited: y must not be written early either
     acc = subwarp_sum<LPR>(acc);
     // long rows: publish 0 here; csr_long_rows_kernel accumulates into it afterwards
     if (lane == 0 && row < n_rows) y[row] = is_long ? T(0) : acc;
@@ -277,11 +284,13 @@ __global__ void csr_stream_fixup_kernel(T *__restrict__ y, int n_tiles, const in
 }
 
 // row-major ELL (the reference's arrays): row r owns entries [r*K, (r+1)*K)
-template <typename T, int LPR, bool VEC, int U>
+template <typename T, int LPR, bool VEC, int U, bool OVL>
 __global__ void __launch_bounds__(kBlock)
 ell_rowmajor_kernel(const T *__restrict__ data, const int *__restrict__ col, const T *__restrict__ x,
                     T *__restrict__ y, int n_rows, int row_size)
 {
+    pdl_launch_dependents();
+    bool waited = false;
     const int lane = threadIdx.x & (LPR - 1);
     const long long row = ((long long)blockIdx.x * kBlock + threadIdx.x) / LPR;
     long long s = 0, e = 0;
@@ -289,8 +298,9 @@ ell_rowmajor_kernel(const T *__restrict__ data, const int *__restrict__ col, con
         s = row * row_size;
         e = s + row_size;
     }
-    T acc = VEC ? row_dot_vec<T, LPR, U>(col, data, x, s, e, lane)
-                : row_dot_scalar<T, LPR>(col, data, x, s, e, lane);
+    T acc = VEC ? row_dot_vec<T, LPR, U, OVL>(col, data, x, s, e, lane, waited)
+                : row_dot_scalar<T, LPR, OVL>(col, data, x, s, e, lane, waited);
+    pdl_wait_once<OVL>(waited);
     acc = subwarp_sum<LPR>(acc);
     if (lane == 0 && row < n_rows) y[row] = acc;
 }
@@ -501,13 +511,17 @@ int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data,
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
     const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), false, "B200_CSR_UNROLL");
     if (!vec)
-        csr_vector_kernel<T, LPR, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, csr_vector_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else if (u == 4)
-        csr_vector_kernel<T, LPR, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, csr_vector_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else if (u == 2)
-        csr_vector_kernel<T, LPR, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, csr_vector_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else
-        csr_vector_kernel<T, LPR, true, 1><<<blocks, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, n_rows, long_threshold);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, csr_vector_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -578,13 +592,17 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
     const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), true, "B200_ELL_UNROLL");
     if (!vec)
-        ell_rowmajor_kernel<T, LPR, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else if (u == 4)
-        ell_rowmajor_kernel<T, LPR, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else if (u == 2)
-        ell_rowmajor_kernel<T, LPR, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else
-        ell_rowmajor_kernel<T, LPR, true, 1><<<blocks, kBlock, 0, ctx->stream>>>(data, col, x, y, n_rows, row_size);
+        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

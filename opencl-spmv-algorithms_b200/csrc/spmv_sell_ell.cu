@@ -31,7 +31,7 @@ constexpr int kBlock = 256;
 //         one-warp-per-chunk only 13 warps per SM, each walking ~20 dependent round trips; WPC warps
 //         take the chunk's 32-group rounds in turn and their 32 row sums meet in shared memory
 //         (fixed order: deterministic, no atomics).
-template <typename T, typename P, bool EXTRA, int WPC, int U>
+template <typename T, typename P, bool EXTRA, int WPC, int U, bool OVL = false>
 __global__ void __launch_bounds__(kBlock)
 sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
               T *__restrict__ y, const P *__restrict__ slice_ptr, int n_work, int n_out,
@@ -39,6 +39,8 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
 {
     static_assert(!EXTRA || WPC == 1, "extra segments are one warp each");
     __shared__ T red[WPC > 1 ? kBlock / 32 : 1][32];
+    pdl_launch_dependents();
+    bool waited = false;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long work = ((long long)blockIdx.x * kBlock + threadIdx.x) / (32 * WPC);
@@ -78,12 +80,13 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
                 }
             }
             const int hold = batch_hold<U, T>(c, v);  // 0; orders the gathers after ALL loads (common.cuh)
+            pdl_wait_once<OVL>(waited);  // x may still be being written by the previous launch
             // a group that was not loaded reads x[0] and multiplies it by 0: every group of a chunk
             // is whole (padding slots are (col 0, value 0) in the format itself)
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xv[u][k] = ld_x(x, c[u].v[k] + hold);
+                for (int k = 0; k < 4; ++k) xv[u][k] = ld_xo<OVL>(x, c[u].v[k] + hold);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 acc0 += v[u].v[0] * xv[u][0];
@@ -93,6 +96,7 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
             }
         }
     }
+    pdl_wait_once<OVL>(waited);  // empty chunks never waited: y must not be written early either
 #pragma unroll
     for (int off = 8; off <= 16; off <<= 1) {
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
@@ -633,8 +637,13 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             if (v == 1 || v == 2 || v == 4) u = v;
         }
 #define B200_SELL_MAIN(W, UU)                                                                              \
-    sell32_kernel<T, P, false, W, UU><<<ceil_div_u((long long)n_slices * 32 * W, kBlock), kBlock, 0, ctx->stream>>>( \
-        data, idx, x, y, slice_ptr, n_slices, n_out, perm, wmax, nullptr)
+    B200_CUDA(ctx->overlap                                                                                   \
+                  ? b200_launch(ctx, sell32_kernel<T, P, false, W, UU, true>,                                \
+                                dim3(ceil_div_u((long long)n_slices * 32 * W, kBlock)), dim3(kBlock), 0, data, idx, x, \
+                                y, slice_ptr, n_slices, n_out, perm, wmax, nullptr)                          \
+                  : b200_launch(ctx, sell32_kernel<T, P, false, W, UU, false>,                               \
+                                dim3(ceil_div_u((long long)n_slices * 32 * W, kBlock)), dim3(kBlock), 0, data, idx, x, \
+                                y, slice_ptr, n_slices, n_out, perm, wmax, nullptr))
 #define B200_SELL_MAIN_U(W)                  \
     do {                                     \
         if (u == 4) B200_SELL_MAIN(W, 4);    \

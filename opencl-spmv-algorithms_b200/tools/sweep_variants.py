@@ -71,6 +71,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-tma", action="store_true", help="skip the bulk-copy SELL variants")
     ap.add_argument("--tma-only", action="store_true", help="only the bulk-copy SELL variants (+ the default)")
+    ap.add_argument("--overlap", action="store_true", help="b200_ctx_set_launch_overlap(1): PDL launches")
     args = ap.parse_args()
     dtype = np.dtype(np.float32 if args.dtype == "f32" else np.float64)
 
@@ -97,6 +98,7 @@ def main():
     y = ctx.zeros(n_rows, dtype)
     ctx.set_l2_persist(x)
     ctx.sync()
+    ctx.set_launch_overlap(args.overlap)
     nnz = coos[0].nnz
     n_launch = 4 * len(sets) if len(sets) > 1 else 10
 

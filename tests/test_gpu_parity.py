@@ -481,3 +481,46 @@ def test_cmrs_packed_layout(ctx, dtype, height, monkeypatch):
     with pytest.raises(pkg.B200Error):
         pkg.check(pkg.lib().b200_cmrs_pack(ctx.h, cmrs.cols.ptr, cmrs.row_in_strip.ptr, rows.size,
                                            (1 << 27) + 1, height, packed.packed.ptr), "b200_cmrs_pack")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_launch_overlap_chain_is_bit_identical(ctx, dtype):
+    """b200_ctx_set_launch_overlap: a chain of DEPENDENT SpMVs (x -> y -> x -> ..., each launch reads
+    what the previous one wrote, no other kernel in between) gives the same bits with the launches
+    overlapped (programmatic dependent launch: matrix streamed before the wait, x gathered after it)
+    as in order -- directly, and replayed from a launch graph.  A stale or early read of x would
+    change the result."""
+    n = 6000
+    rows, cols, vals = random_sorted_matrix(n, n, 1, 70, 95)
+    vals = vals / 40.0                                   # keep 60 chained products in range
+    x0 = np.random.default_rng(96).uniform(-1, 1, n).astype(dtype)
+    coo = pkg.CooMatrix.from_host(ctx, n, n, rows, cols, vals)
+    m = pkg.build_all(coo, dtype)
+    m["cmrs_packed"] = m["cmrs"].packed()
+    m.pop("coo")                                         # atomics: not bit-reproducible anyway
+    steps = 60
+
+    def chain(mat, a, b):
+        for k in range(steps):
+            src, dst = (a, b) if k % 2 == 0 else (b, a)
+            mat.spmv(src, dst)
+
+    for name, mat in m.items():
+        a, b = ctx.array(x0), ctx.zeros(n, dtype)
+        chain(mat, a, b)                                 # in order (also creates the plans)
+        want = a.download()
+        assert np.isfinite(want).all() and np.abs(want).max() > 0
+        ctx.set_launch_overlap(True)
+        try:
+            a2, b2 = ctx.array(x0), ctx.zeros(n, dtype)
+            chain(mat, a2, b2)
+            got = a2.download()
+            a3, b3 = ctx.array(x0), ctx.zeros(n, dtype)
+            with ctx.record_graph() as g:
+                chain(mat, a3, b3)
+            g.launch()
+            got_graph = a3.download()
+        finally:
+            ctx.set_launch_overlap(False)
+        assert got.tobytes() == want.tobytes(), name
+        assert got_graph.tobytes() == want.tobytes(), name
