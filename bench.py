@@ -680,8 +680,7 @@ def main():
             "formats": fm,
             "launch_overlap": (None if overlap is None else {
                 "what": "same K-step graph with b200_ctx_set_launch_overlap(1): kernels are programmatic dependents "
-                        "(matrix arrays streamed while the previous launch drains; x read / y written after it ends); "
-                        "COO unchanged (its y memset node is not a kernel)",
+                        "(matrix arrays streamed while the previous launch drains; x read / y written after it ends)",
                 "ms_per_step": round(overlap["ms_per_step"], 5),
                 "value": round(flops_step / (overlap["ms_per_step"] * 1e-3) * 1e-9, 2),
                 "formats": {f: {"ms": round(ms, 5), "frac_measured": round(bytes_alg[f] / (ms * 1e-3) * 1e-9 / peak, 4)}

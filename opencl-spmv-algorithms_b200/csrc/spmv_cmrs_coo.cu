@@ -199,11 +199,24 @@ __global__ void cmrs_long_items_kernel(const int *__restrict__ strip_ptr, int n_
         for (int k = 0; k < extra; ++k) items[at + k] = make_int2((int)t, k + 1);
 }
 
-template <typename T, bool VEC, int U>
+// y = 0 as a kernel instead of a memset node, so that with launch overlap on the COO kernel can be a
+// programmatic dependent of it (and it of whatever ran before): memset nodes take no part in that
+template <typename T>
+__global__ void zero_ovl_kernel(T *__restrict__ y, int n)
+{
+    pdl_launch_dependents();
+    bool waited = false;
+    pdl_wait_once<true>(waited);  // y may still be being read / written by the previous launch
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = T(0);
+}
+
+template <typename T, bool VEC, int U, bool OVL = false>
 __global__ void __launch_bounds__(kBlock)
 coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__restrict__ data,
            const T *__restrict__ x, T *__restrict__ y, int nnz)
 {
+    pdl_launch_dependents();
+    bool waited = false;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const long long ss = warp * kCooPerWarp + (lane >> 2) * (kCooPerWarp / kSubWarps);
@@ -240,10 +253,11 @@ coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__
                 for (int u = 0; u < U; ++u) hold |= hold_bits(c[u], v[u]) & r[u].v[0];
                 hold >>= 31;
             }
+            pdl_wait_once<OVL>(waited);  // y is being zeroed, x maybe still written (common.cuh)
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) xv[u][k] = (j0 + 16 * u + k < ee) ? ld_x(x, c[u].v[k] + hold) : T(0);
+                for (int k = 0; k < 4; ++k) xv[u][k] = (j0 + 16 * u + k < ee) ? ld_xo<OVL>(x, c[u].v[k] + hold) : T(0);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long j = j0 + 16 * u;
@@ -267,6 +281,7 @@ coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__
             }
         }
     } else {
+        pdl_wait_once<OVL>(waited);
         for (long long j = ss + (lane & 3); j < ee; j += 4) {
             const int r = ld_stream(row + j);
             if (r != cur) {
@@ -274,9 +289,10 @@ coo_kernel(const int *__restrict__ row, const int *__restrict__ col, const T *__
                 cur = r;
                 sum = 0;
             }
-            sum += ld_stream(data + j) * ld_x(x, ld_stream(col + j));
+            sum += ld_stream(data + j) * ld_xo<OVL>(x, ld_stream(col + j));
         }
     }
+    pdl_wait_once<OVL>(waited);
     // warp-level segmented inclusive scan over the lanes' final (cur, sum); heads delimit runs
     const int prev = __shfl_up_sync(0xffffffffu, cur, 1);
     const bool head = lane == 0 || prev != cur;
@@ -364,7 +380,12 @@ int spmv_coo_impl(b200_ctx *ctx, const int *row, const int *col, const T *data, 
     B200_ENTER(ctx);
     B200_REQUIRE(x && y && nnz >= 0 && n_rows >= 0, "bad argument");
     B200_REQUIRE(nnz == 0 || (row && col && data), "null row/col/data");
-    B200_CUDA(cudaMemsetAsync(y, 0, sizeof(T) * (size_t)n_rows, ctx->stream));
+    if (ctx->overlap && n_rows > 0) {
+        const unsigned zb = (unsigned)min((long long)ctx->sm_count * 8, ((long long)n_rows + 255) / 256);
+        B200_CUDA(b200_launch(ctx, zero_ovl_kernel<T>, dim3(zb), dim3(256), 0, y, n_rows));
+    } else {
+        B200_CUDA(cudaMemsetAsync(y, 0, sizeof(T) * (size_t)n_rows, ctx->stream));
+    }
     if (nnz == 0) return B200_SUCCESS;
     const bool vec = aligned16(row) && aligned16(col) && aligned16(data);
     unsigned blocks = ceil_div_u(((long long)nnz + kCooPerWarp - 1) / kCooPerWarp, kWarps);
@@ -372,10 +393,14 @@ int spmv_coo_impl(b200_ctx *ctx, const int *row, const int *col, const T *data, 
     // (profiles/r1e_variant_sweep.md): 2, except fp32 on launches of many waves (237 vs 246 us)
     int u = (sizeof(T) == 4 && (long long)blocks > 8ll * ctx->sm_count) ? 4 : 2;
     if (const char *e = getenv("B200_COO_U")) u = atoi(e) == 4 ? 4 : (atoi(e) == 1 ? 1 : 2);
-    if (!vec) coo_kernel<T, false, 1><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
-    else if (u == 4) coo_kernel<T, true, 4><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
-    else if (u == 2) coo_kernel<T, true, 2><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
-    else coo_kernel<T, true, 1><<<blocks, kBlock, 0, ctx->stream>>>(row, col, data, x, y, nnz);
+#define B200_COO_LAUNCH(V, UU)                                                                            \
+    B200_CUDA(ctx->overlap ? b200_launch(ctx, coo_kernel<T, V, UU, true>, dim3(blocks), dim3(kBlock), 0, row, col, data, x, y, nnz) \
+                           : b200_launch(ctx, coo_kernel<T, V, UU, false>, dim3(blocks), dim3(kBlock), 0, row, col, data, x, y, nnz))
+    if (!vec) B200_COO_LAUNCH(false, 1);
+    else if (u == 4) B200_COO_LAUNCH(true, 4);
+    else if (u == 2) B200_COO_LAUNCH(true, 2);
+    else B200_COO_LAUNCH(true, 1);
+#undef B200_COO_LAUNCH
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }

@@ -492,12 +492,18 @@ def test_launch_overlap_chain_is_bit_identical(ctx, dtype):
     change the result."""
     n = 6000
     rows, cols, vals = random_sorted_matrix(n, n, 1, 70, 95)
-    vals = vals / 40.0                                   # keep 60 chained products in range
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    v = np.ones(n)
+    for _ in range(30):                                  # scale to spectral radius ~1: 60 chained
+        v = A @ v                                        # products stay in fp32 range
+        rho = np.linalg.norm(v)
+        v /= rho
+    vals = vals / rho
     x0 = np.random.default_rng(96).uniform(-1, 1, n).astype(dtype)
     coo = pkg.CooMatrix.from_host(ctx, n, n, rows, cols, vals)
     m = pkg.build_all(coo, dtype)
     m["cmrs_packed"] = m["cmrs"].packed()
-    m.pop("coo")                                         # atomics: not bit-reproducible anyway
     steps = 60
 
     def chain(mat, a, b):
@@ -522,5 +528,10 @@ def test_launch_overlap_chain_is_bit_identical(ctx, dtype):
             got_graph = a3.download()
         finally:
             ctx.set_launch_overlap(False)
-        assert got.tobytes() == want.tobytes(), name
-        assert got_graph.tobytes() == want.tobytes(), name
+        if name == "coo":                                # atomics: same values up to summation order
+            scale = np.abs(want).max()
+            assert np.abs(got.astype(np.float64) - want).max() <= 100 * TOL[np.dtype(dtype)] * scale
+            assert np.abs(got_graph.astype(np.float64) - want).max() <= 100 * TOL[np.dtype(dtype)] * scale
+        else:
+            assert got.tobytes() == want.tobytes(), name
+            assert got_graph.tobytes() == want.tobytes(), name
