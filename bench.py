@@ -908,6 +908,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
     fused_ms = None
     fused_norm = None
     fused_full_ms = None
+    fused_halo_ms = None
     halo_bytes = None
     if fmt == "sell":
         bufs = pkg.PeerBuffers(pkg, ctx, blocks, rank, world)
@@ -932,7 +933,22 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
             return f0.elapsed_time(f1) / args.steps, r1.norm
 
         fused_full_ms, _ = fused_run(None)
-        fused_ms, fused_norm = fused_run(halo)
+        fused_halo_ms, fused_halo_norm = fused_run(halo)
+
+        # ring: no collective call in the loop; flags + partial sums travel through peer memory
+        def ring_run():
+            pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[bufs.ring_step % 2].ptr, n, 11, 0.0, 1.0), "gen x0")
+            sync_all()
+            pkg.power_iteration_ring(pkg, ctx, mat, bufs, rank, blocks, args.warmup + (args.warmup % 2), halo=halo)
+            sync_all()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            r1 = pkg.power_iteration_ring(pkg, ctx, mat, bufs, rank, blocks, args.steps, halo=halo)
+            f1.record()
+            sync_all()
+            return f0.elapsed_time(f1) / args.steps, r1.norm
+
+        fused_ms, fused_norm = ring_run()
         bufs.close()
 
     # split: SpMV alone and the all-gather alone, same buffers (explains the step time)
@@ -952,7 +968,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
     gather_ms = a.elapsed_time(b) / 10
 
     t = torch.tensor([step_ms, spmv_ms, gather_ms, float(nnz), fused_ms or 0.0, fused_full_ms or 0.0,
-                      float(halo_bytes or 0)], device="cuda", dtype=torch.float64)
+                      float(halo_bytes or 0), fused_halo_ms or 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -962,6 +978,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
         fused_ms = float(tmax[4]) if fused_ms is not None else None
         fused_full_ms = float(tmax[5]) if fused_full_ms is not None else None
         halo_bytes = int(tmax[6]) if halo_bytes is not None else None
+        fused_halo_ms = float(tmax[7]) if fused_halo_ms is not None else None
     else:
         nnz_total = float(nnz)
     nccl_ms = step_ms
@@ -981,9 +998,14 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
                                    f"{int(nnz_total)} nnz, fp64, {fmt.upper()}, {world} row block(s), NCCL all-gather of x per step",
                        "rows_per_gpu": int(n_local), "nnz_per_gpu": int(nnz),
                        "cache": "inputs larger than L2 (0.7 GB matrix + 2 x 64 MB x per GPU per world rank), no flush"},
-            "exchange": ("fused, halo-limited: the SpMV kernel stores each y row into the x buffers of the ranks that "
-                         "read it (its own + neighbours) over NVLink (CUDA IPC) + one 256-byte NCCL all-reduce"
+            "exchange": ("ring: ONE kernel per step and no collective call -- the SpMV kernel stores each y row into "
+                         "the x buffers of the ranks that read it (its own + neighbours) over NVLink (CUDA IPC), and "
+                         "the ranks hand over ||y||^2 partial sums and 'step done' flags through peer memory"
                          if fused_ms is not None else "NCCL all_gather_into_tensor (in place)"),
+            "fused_halo_allreduce": (None if fused_halo_ms is None else
+                                     {"ms_per_step": round(fused_halo_ms, 5),
+                                      "gflops": round(2.0 * nnz_total / (fused_halo_ms * 1e-3) * 1e-9, 2),
+                                      "what": "halo-limited stores + one 256-byte NCCL all-reduce per step"}),
             "fused_full_broadcast": (None if fused_full_ms is None else
                                      {"ms_per_step": round(fused_full_ms, 5),
                                       "gflops": round(2.0 * nnz_total / (fused_full_ms * 1e-3) * 1e-9, 2),
@@ -1000,7 +1022,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": fmt, "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src},
             "cpu_baseline": None, "e2e": None,
-            "gpu_launches": int(args.steps * 3), "clocks": clk.summary(),
+            "gpu_launches": int(args.steps * (1 if fused_ms is not None else 3)), "clocks": clk.summary(),
         }
         emit_json(out)
     if world > 1:

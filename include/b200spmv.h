@@ -345,6 +345,22 @@ int b200_spmv_sell_halo_f64(b200_ctx *ctx, const double *data, const int *indice
                             const int *row_indices, int chunk, int n_slices, int n_rows,
                             const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
                             long long dst_offset, const int *dst_row_lo, const int *dst_row_hi);
+/* Same kernel with NO collective call per step at all ("ring" of flags over peer memory).  Every rank
+ * allocates one zero-filled sync block of B200_SYNC_BLOCK_BYTES with b200_malloc and maps the others'
+ * (b200_ipc_*); sync_blocks[r] (HOST array, n_dst entries, indexed by RANK like dst[]) is rank r's
+ * block as seen from this process.  At `step` k the kernel first waits until every rank has finished
+ * step k-1, folds their partial sums of ||y||^2 (left in this rank's block by the peers) into the
+ * 1/||x|| scale (k = 0: no wait, no scaling), runs the SpMV + halo stores, and its last block
+ * publishes this rank's partial sums to every rank and releases "step k done" flags system-wide.
+ * The flags are the barrier that orders the peer writes of the double-buffered x.  All ranks must
+ * call it with the same consecutive step numbers.  ||y||^2 of step k = sum over ranks r and slots s of
+ * the doubles at byte offset 8*(16 + ((k&1)*16 + r)*32 + s) of any rank's block, valid once every rank
+ * has finished step k (synchronise all ranks before reading it on the host). */
+#define B200_SYNC_BLOCK_BYTES 16384
+int b200_spmv_sell_ring_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                            const int *row_indices, int chunk, int n_slices, int n_rows, double *const *dst,
+                            int n_dst, long long dst_offset, const int *dst_row_lo, const int *dst_row_hi,
+                            void *const *sync_blocks, int my_rank, unsigned long long step);
 /* min and max of a device int array (host outputs): the column range a row block reads */
 int b200_minmax_i32(b200_ctx *ctx, const int *a, long long n, int *min_out, int *max_out);
 /* CUDA IPC plumbing for the peers' buffers (allocations made with b200_malloc) */

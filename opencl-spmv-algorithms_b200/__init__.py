@@ -136,6 +136,7 @@ SIGNATURES = {
     "b200_partition_rows": (_i, [_vp, _i, _i, _i, _vp]),
     "b200_spmv_sell_bcast_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _ll]),
     "b200_spmv_sell_halo_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
+    "b200_spmv_sell_ring_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _ll, _vp, _vp, _vp, _i, _u64]),
     "b200_minmax_i32": (_i, [_vp, _vp, _ll, C.POINTER(_i), C.POINTER(_i)]),
     "b200_ipc_get_handle": (_i, [_vp, _vp, _vp]),
     "b200_ipc_open_handle": (_i, [_vp, _vp, _vpp]),
@@ -343,5 +344,5 @@ class Event:
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix, CmrsPackedMatrix,  # noqa: E402,F401
                       algorithmic_bytes, build_all, partition_rows)
 from .iterate import (PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges, gpu_callables, halo_rows,
-                      power_iteration,  # noqa: E402,F401
+                      power_iteration, power_iteration_ring,  # noqa: E402,F401
                       power_iteration_fused)

@@ -372,20 +372,87 @@ struct PeerDst {
 // step's kernel -- adds the slots up after the ranks' all-reduce.
 constexpr int kSumsqSlots = 32;
 
-template <typename T, typename P>
+// RING variant: no NCCL call in the loop at all.  Every rank owns a small "sync block" in device
+// memory that all ranks map (CUDA IPC), laid out in 8-byte words:
+//   [kSyncFlags + r]              steps completed by rank r, written by r into EVERY rank's block
+//   [kSyncSums + (p*16 + r)*32 + s]  the 32 partial sums of ||y_r||^2 at step parity p, written by r
+//   [kSyncDone]                   this rank's "blocks finished" ticket counter (local use)
+//   [kSyncAcc + s]                this rank's running partial sums of the current step (local use)
+// Step k: warp 0 of every block waits until all ranks have completed step k-1 (flags >= k), folds
+// the ranks' partial sums into 1/||x||, the block runs the SpMV and stores y to the ranks that read
+// it; the LAST block to finish (ticket) publishes this rank's 32 partial sums to every rank, fences,
+// and releases flag = k+1 everywhere.  The flag is both the norm hand-off and the barrier that orders
+// the peer writes of x (double-buffered), which is what the all-reduce did before.
+constexpr int kSyncFlags = 0;
+constexpr int kSyncSums = 16;
+constexpr int kSyncDone = kSyncSums + 2 * 16 * 32;
+constexpr int kSyncAcc = kSyncDone + 2;
+constexpr int kSyncWords = kSyncAcc + 32;
+static_assert(kSyncWords * 8 <= B200_SYNC_BLOCK_BYTES, "sync block layout exceeds B200_SYNC_BLOCK_BYTES");
+
+struct PeerSync {
+    unsigned long long *blk[kMaxPeers];  // sync block of every rank (own + IPC-mapped peers), by rank
+    unsigned long long *mine;            // == blk[my_rank]
+    int my_rank, world;
+    unsigned long long step;
+    int *err_flag;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <typename T, typename P, bool RING = false>
 __global__ void __launch_bounds__(kBlock)
 sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
                     const P *__restrict__ slice_ptr, int n_slices, int n_rows,
                     const T *__restrict__ scale2, T *__restrict__ sumsq_out, PeerDst<T> dst, int n_dst,
-                    long long dst_offset)
+                    long long dst_offset, PeerSync sync)
 {
     __shared__ T warp_sq[kBlock / 32];
+    __shared__ T s_alpha;
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const bool active = slice < n_slices;  // no early return: the block reduces ||y||^2 together
     // 1/||x||: one coalesced load of the 32 partial sums per warp, folded with shuffles
     T alpha = 1;
-    if (scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
+    if (!RING && scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
+    if (RING) {
+        if (threadIdx.x < 32) {
+            T a = 1;
+            if (sync.step > 0) {
+                // all ranks must have completed the previous step: their x rows and partial sums
+                // are then in this GPU's memory (their stores precede their release of the flag)
+                const unsigned long long t0 = global_timer_ns();
+                for (;;) {
+                    const unsigned long long f =
+                        lane < sync.world ? ld_acquire_sys(sync.mine + kSyncFlags + lane) : ~0ull;
+                    if (__all_sync(0xffffffffu, f >= sync.step)) break;
+                    __nanosleep(100);
+                    if (global_timer_ns() - t0 > kWaitLimitNs) {  // a peer died: flag it, do not hang
+                        if (lane == 0) atomicExch(sync.err_flag, 2);
+                        break;
+                    }
+                }
+                const double *sums = reinterpret_cast<const double *>(sync.mine + kSyncSums) +
+                                     ((sync.step - 1) & 1) * 16 * 32;
+                T part = 0;
+                for (int r = 0; r < sync.world; ++r) part += __ldcg(sums + r * 32 + lane);
+                a = rsqrt(subwarp_sum<32>(part));
+            }
+            if (lane == 0) s_alpha = a;
+        }
+        __syncthreads();
+        alpha = s_alpha;
+    }
     T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
     if (active) {
         const long long chunk_base = slice_ptr[slice];
@@ -420,6 +487,7 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     const T b0 = __shfl_sync(0xffffffffu, acc0, src), b1 = __shfl_sync(0xffffffffu, acc1, src);
     const T b2 = __shfl_sync(0xffffffffu, acc2, src), b3 = __shfl_sync(0xffffffffu, acc3, src);
     T sq = 0;
+    bool wrote_peer = false;
     if (active && lane < 16) {
         const T lo = ((lane & 1) ? b2 : b0) * alpha, hi = ((lane & 1) ? b3 : b1) * alpha;
         const long long r = slice * 32 + lane * 2;
@@ -438,8 +506,47 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
                     if (r >= first && r < last) out[0] = lo;
                     if (r + 1 >= first && r + 1 < last) out[1] = hi;
                 }
+                if (RING && d != sync.my_rank && r + 1 >= first && r < last) wrote_peer = true;
             }
         }
+    }
+    if (RING) {
+        // every thread makes its stores visible (system-wide if they crossed NVLink) before the block
+        // takes its ticket: the last block's release of the flag then covers all of them
+        if (wrote_peer) __threadfence_system();
+        else __threadfence();
+        sq = subwarp_sum<32>(sq);
+        if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T total = 0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) total += warp_sq[w];
+            atomicAdd(reinterpret_cast<double *>(sync.mine + kSyncAcc) + (blockIdx.x & (kSumsqSlots - 1)), total);
+            __threadfence();
+            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(sync.mine + kSyncDone), 1u);
+            s_last = ticket == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x < 32) {
+            __threadfence();
+            double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
+            const double v = atomicAdd(acc + lane, 0.0);  // read through L2, after every block's add
+            acc[lane] = 0.0;                              // ready for the next step's kernel
+            const long long at = (long long)(sync.step & 1) * 16 * 32 + (long long)sync.my_rank * 32 + lane;
+#pragma unroll
+            for (int d = 0; d < kMaxPeers; ++d)
+                if (d < sync.world) reinterpret_cast<double *>(sync.blk[d] + kSyncSums)[at] = v;
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                *reinterpret_cast<unsigned *>(sync.mine + kSyncDone) = 0u;
+#pragma unroll
+                for (int d = 0; d < kMaxPeers; ++d)
+                    if (d < sync.world) st_release_sys(sync.blk[d] + kSyncFlags + sync.my_rank, sync.step + 1);
+            }
+        }
+        return;
     }
     if (sumsq_out) {
         sq = subwarp_sum<32>(sq);
@@ -714,6 +821,57 @@ int spmv_ellcm_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T 
 
 }  // namespace
 
+static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                              const int *row_indices, int chunk, int n_slices, int n_rows,
+                              const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
+                              long long dst_offset, const int *dst_row_lo, const int *dst_row_hi,
+                              void *const *sync_blocks, int my_rank, unsigned long long step)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(vect && row_indices && dst && n_slices >= 0 && n_rows >= 0 && dst_offset >= 0, "bad argument");
+    B200_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers, "n_dst must be in 1..16");
+    B200_REQUIRE((long long)n_rows <= (long long)n_slices * 32, "n_rows exceeds n_slices*32");
+    if (chunk != 32) {
+        b200_set_error("SELL chunk must be 32 (warp-aligned), got %d", chunk);
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_REQUIRE(aligned16(data) && aligned16(indices), "SELL arrays must be 16-byte aligned");
+    B200_REQUIRE(!sync_blocks || n_slices > 0, "ring exchange needs at least one chunk per rank");
+    if (n_slices == 0) return B200_SUCCESS;
+    PeerDst<double> d;
+    B200_REQUIRE((dst_row_lo == nullptr) == (dst_row_hi == nullptr), "give both row-range arrays or neither");
+    for (int i = 0; i < kMaxPeers; ++i) {
+        d.p[i] = i < n_dst ? dst[i] : nullptr;
+        d.lo[i] = (i < n_dst && dst_row_lo) ? dst_row_lo[i] : 0;
+        d.hi[i] = i < n_dst ? (dst_row_hi ? dst_row_hi[i] : n_rows) : 0;
+    }
+    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
+    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.lo[i] >= 0, "negative row range");
+    PeerSync sync;
+    memset(&sync, 0, sizeof sync);
+    const unsigned grid = ceil_div_u((long long)n_slices * 32, kBlock);
+    if (sync_blocks) {
+        for (int i = 0; i < n_dst; ++i) {
+            B200_REQUIRE(sync_blocks[i], "null sync block");
+            sync.blk[i] = static_cast<unsigned long long *>(sync_blocks[i]);
+        }
+        sync.mine = sync.blk[my_rank];
+        sync.my_rank = my_rank;
+        sync.world = n_dst;
+        sync.step = step;
+        sync.err_flag = ctx->scratch + kWatchFlag;
+        sell32_bcast_kernel<double, int, true><<<grid, kBlock, 0, ctx->stream>>>(
+            data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
+        ctx->watch_flag = true;
+    } else {
+        sell32_bcast_kernel<double, int, false><<<grid, kBlock, 0, ctx->stream>>>(
+            data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset, sync);
+    }
+    B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+
 extern "C" {
 
 int b200_sell_plan_create(b200_ctx *ctx, const int *row_indices, int n_slices, b200_sell_plan **plan)
@@ -778,29 +936,18 @@ int b200_spmv_sell_halo_f64(b200_ctx *ctx, const double *data, const int *indice
                             const double *scale_sumsq, double *sumsq_out, double *const *dst, int n_dst,
                             long long dst_offset, const int *dst_row_lo, const int *dst_row_hi)
 {
-    B200_ENTER(ctx);
-    B200_REQUIRE(vect && row_indices && dst && n_slices >= 0 && n_rows >= 0 && dst_offset >= 0, "bad argument");
-    B200_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers, "n_dst must be in 1..16");
-    B200_REQUIRE((long long)n_rows <= (long long)n_slices * 32, "n_rows exceeds n_slices*32");
-    if (chunk != 32) {
-        b200_set_error("SELL chunk must be 32 (warp-aligned), got %d", chunk);
-        return B200_ERR_UNSUPPORTED;
-    }
-    B200_REQUIRE(aligned16(data) && aligned16(indices), "SELL arrays must be 16-byte aligned");
-    if (n_slices == 0) return B200_SUCCESS;
-    PeerDst<double> d;
-    B200_REQUIRE((dst_row_lo == nullptr) == (dst_row_hi == nullptr), "give both row-range arrays or neither");
-    for (int i = 0; i < kMaxPeers; ++i) {
-        d.p[i] = i < n_dst ? dst[i] : nullptr;
-        d.lo[i] = (i < n_dst && dst_row_lo) ? dst_row_lo[i] : 0;
-        d.hi[i] = i < n_dst ? (dst_row_hi ? dst_row_hi[i] : n_rows) : 0;
-    }
-    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
-    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.lo[i] >= 0, "negative row range");
-    sell32_bcast_kernel<double, int><<<ceil_div_u((long long)n_slices * 32, kBlock), kBlock, 0, ctx->stream>>>(
-        data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
-    B200_LAUNCH_CHECK();
-    return B200_SUCCESS;
+    return sell_exchange_impl(ctx, data, indices, vect, row_indices, chunk, n_slices, n_rows, scale_sumsq, sumsq_out,
+                              dst, n_dst, dst_offset, dst_row_lo, dst_row_hi, nullptr, 0, 0);
+}
+
+int b200_spmv_sell_ring_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
+                            const int *row_indices, int chunk, int n_slices, int n_rows, double *const *dst,
+                            int n_dst, long long dst_offset, const int *dst_row_lo, const int *dst_row_hi,
+                            void *const *sync_blocks, int my_rank, unsigned long long step)
+{
+    B200_REQUIRE(sync_blocks && my_rank >= 0 && my_rank < n_dst, "bad sync arguments");
+    return sell_exchange_impl(ctx, data, indices, vect, row_indices, chunk, n_slices, n_rows, nullptr, nullptr, dst,
+                              n_dst, dst_offset, dst_row_lo, dst_row_hi, sync_blocks, my_rank, step);
 }
 
 int b200_ipc_get_handle(b200_ctx *ctx, void *dptr, unsigned char handle[64])

@@ -123,8 +123,10 @@ def gpu_callables(pkg, ctx, matrix, n_rows_local: int):
 # NVLink (peer memory mapped with CUDA IPC) -- no all-gather, no pack, no separate scale pass.
 # ---------------------------------------------------------------------------------------------
 class PeerBuffers:
-    """Two full-length x buffers per rank, allocated through the C ABI and mapped on every rank
-    (b200_ipc_get_handle / b200_ipc_open_handle; handles travel with all_gather_object)."""
+    """Two full-length x buffers (and one small sync block) per rank, allocated through the C ABI and
+    mapped on every rank (b200_ipc_get_handle / b200_ipc_open_handle; handles travel with
+    all_gather_object)."""
+    SYNC_BLOCK_BYTES = 16384  # B200_SYNC_BLOCK_BYTES
 
     def __init__(self, pkg, ctx, blocks: RowBlocks, rank: int, world: int):
         import ctypes as C
@@ -132,9 +134,12 @@ class PeerBuffers:
         self.pkg, self.ctx, self.rank, self.world = pkg, ctx, rank, world
         L = pkg.lib()
         self.local = [ctx.zeros(blocks.padded, np.float64) for _ in range(2)]
+        # sync block of the ring exchange (b200_spmv_sell_ring_f64): flags + partial sums, zero-filled
+        self.sync_block = ctx.zeros(self.SYNC_BLOCK_BYTES // 8, np.float64)
+        self.ring_step = 0  # steps issued so far with the ring kernel (flags only ever grow)
         ctx.sync()
         handles = []
-        for buf in self.local:
+        for buf in self.local + [self.sync_block]:
             h = (C.c_ubyte * 64)()
             pkg.check(L.b200_ipc_get_handle(ctx.h, buf.ptr, h), "b200_ipc_get_handle")
             handles.append(bytes(h))
@@ -145,11 +150,11 @@ class PeerBuffers:
             dist.all_gather_object(gathered, handles)
         self._opened = []
         self.ptrs = []  # ptrs[b][r] = device pointer of buffer b of rank r, valid in THIS process
-        for b in range(2):
+        for b in range(3):
             row = []
             for r in range(world):
                 if r == rank:
-                    row.append(self.local[b].ptr)
+                    row.append((self.local + [self.sync_block])[b].ptr)
                 else:
                     p = C.c_void_p()
                     hb = (C.c_ubyte * 64).from_buffer_copy(gathered[r][b])
@@ -159,7 +164,8 @@ class PeerBuffers:
             self.ptrs.append(row)
         # (rotating the destination order by rank was tried at 8 GPUs: no gain, 1.85 vs 1.55 ms/step
         # on another box -- within box-to-box noise -- so the plain order is kept)
-        self.dst = [(C.c_void_p * world)(*row) for row in self.ptrs]
+        self.dst = [(C.c_void_p * world)(*row) for row in self.ptrs[:2]]
+        self.sync = (C.c_void_p * world)(*self.ptrs[2])  # sync block of every rank, by rank
 
     def close(self):
         L = self.pkg.lib()
@@ -207,6 +213,41 @@ def exchange_col_ranges(pkg, ctx, cols, row_begin: int, world: int):
     out = [None] * world
     dist.all_gather_object(out, mine)
     return out
+
+
+def power_iteration_ring(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: RowBlocks, steps: int,
+                         halo=None) -> IterationResult:
+    """`steps` power-iteration steps with NO collective call inside the loop: one kernel launch per
+    step (b200_spmv_sell_ring_f64).  The kernel waits on the peers' "previous step done" flags, takes
+    1/||x|| from the partial sums they left in this rank's sync block, runs the SpMV + halo stores and
+    releases its own flag.  bufs.local[bufs.ring_step % 2] holds the current vector; consecutive calls
+    continue the run (the step counter lives in `bufs`).  The result's norm is read after a barrier
+    over all ranks (the peers' last partial sums must have landed)."""
+    import numpy as np
+    L = pkg.lib()
+    n_local = blocks.bounds(rank)[1] - blocks.bounds(rank)[0]
+    assert sell.perm is None and sell.row_indices is not None, "ring path: SELL-32, sigma = 1, int32 pointers"
+    row_lo = row_hi = None
+    if halo is not None:
+        import ctypes as C
+        row_lo = (C.c_int * bufs.world)(*halo[0])
+        row_hi = (C.c_int * bufs.world)(*halo[1])
+    for _ in range(steps):
+        k = bufs.ring_step
+        pkg.check(L.b200_spmv_sell_ring_f64(ctx.h, sell.data.ptr, sell.cols.ptr, bufs.local[k % 2].ptr,
+                                            sell.row_indices.ptr, 32, sell.n_slices, n_local, bufs.dst[(k + 1) % 2],
+                                            bufs.world, rank * blocks.count, row_lo, row_hi, bufs.sync, rank, k),
+                  "b200_spmv_sell_ring_f64")
+        bufs.ring_step = k + 1
+    ctx.sync()
+    if bufs.world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    last = bufs.ring_step - 1
+    words = bufs.sync_block.download()
+    at = 16 + (last & 1) * 16 * 32
+    norm2 = float(np.sum(words[at:at + bufs.world * 32])) if last >= 0 else float("nan")
+    return IterationResult(steps, norm2 ** 0.5, bufs.local[bufs.ring_step % 2])
 
 
 def power_iteration_fused(pkg, ctx, sell, bufs: PeerBuffers, rank: int, blocks: RowBlocks, steps: int,
