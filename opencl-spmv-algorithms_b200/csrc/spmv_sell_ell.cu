@@ -396,12 +396,19 @@ struct PeerSync {
     int my_rank, world;
     unsigned long long step;
     int *err_flag;
+    int relaxed_poll;  // B200_RING_RELAXED=1: poll the flags with ld.relaxed.sys (tuning hook)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
@@ -417,7 +424,6 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
                     long long dst_offset, PeerSync sync)
 {
     __shared__ T warp_sq[kBlock / 32];
-    __shared__ T s_alpha;
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
@@ -425,52 +431,84 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     // 1/||x||: one coalesced load of the 32 partial sums per warp, folded with shuffles
     T alpha = 1;
     if (!RING && scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
-    if (RING) {
-        if (threadIdx.x < 32) {
-            T a = 1;
-            if (sync.step > 0) {
-                // all ranks must have completed the previous step: their x rows and partial sums
-                // are then in this GPU's memory (their stores precede their release of the flag)
-                const unsigned long long t0 = global_timer_ns();
-                for (;;) {
-                    const unsigned long long f =
-                        lane < sync.world ? ld_acquire_sys(sync.mine + kSyncFlags + lane) : ~0ull;
-                    if (__all_sync(0xffffffffu, f >= sync.step)) break;
-                    __nanosleep(100);
-                    if (global_timer_ns() - t0 > kWaitLimitNs) {  // a peer died: flag it, do not hang
-                        if (lane == 0) atomicExch(sync.err_flag, 2);
-                        break;
-                    }
-                }
-                const double *sums = reinterpret_cast<const double *>(sync.mine + kSyncSums) +
-                                     ((sync.step - 1) & 1) * 16 * 32;
-                T part = 0;
-                for (int r = 0; r < sync.world; ++r) part += __ldcg(sums + r * 32 + lane);
-                a = rsqrt(subwarp_sum<32>(part));
-            }
-            if (lane == 0) s_alpha = a;
-        }
-        __syncthreads();
-        alpha = s_alpha;
-    }
     T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-    if (active) {
-        const long long chunk_base = slice_ptr[slice];
-        const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
-        const int *ip = idx + chunk_base;
-        const T *dp = data + chunk_base;
-        // one group per lane and round trip: a 7-point-stencil chunk is only 56 groups, and the
-        // batched form (58 registers) measured slower here (0.196 vs 0.189 ms per step)
+    if (!RING) {
+        if (active) {
+            const long long chunk_base = slice_ptr[slice];
+            const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
+            const int *ip = idx + chunk_base;
+            const T *dp = data + chunk_base;
+            // one group per lane and round trip: a 7-point-stencil chunk is only 56 groups, and the
+            // batched form (58 registers) measured slower here (0.196 vs 0.189 ms per step)
 #pragma unroll 4
-        for (long long g = lane; g < n_groups; g += 32) {
-            IVec4 c;
-            Vec4<T> v;
+            for (long long g = lane; g < n_groups; g += 32) {
+                IVec4 c;
+                Vec4<T> v;
+                c.load(ip + (g << 2));
+                v.load(dp + (g << 2));
+                acc0 += v.v[0] * ld_x(x, c.v[0]);
+                acc1 += v.v[1] * ld_x(x, c.v[1]);
+                acc2 += v.v[2] * ld_x(x, c.v[2]);
+                acc3 += v.v[3] * ld_x(x, c.v[3]);
+            }
+        }
+    } else {
+        // 1. every warp requests its first group of matrix data (the matrix never changes);
+        // 2. meanwhile warp 0 makes sure all ranks have completed the previous step -- their x rows and
+        //    partial sums are then in this GPU's memory (their stores precede their release of the
+        //    flag) -- and the block barrier passes that on to the other warps;
+        // 3. only then is x gathered, with coherent loads (ptxas moves ld.global.nc above barriers).
+        long long n_groups = 0, g = lane;
+        const int *ip = idx;
+        const T *dp = data;
+        if (active) {
+            const long long chunk_base = slice_ptr[slice];
+            n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
+            ip += chunk_base;
+            dp += chunk_base;
+        }
+        IVec4 c;
+        Vec4<T> v;
+        bool have = g < n_groups;
+        if (have) {
             c.load(ip + (g << 2));
             v.load(dp + (g << 2));
-            acc0 += v.v[0] * ld_x(x, c.v[0]);
-            acc1 += v.v[1] * ld_x(x, c.v[1]);
-            acc2 += v.v[2] * ld_x(x, c.v[2]);
-            acc3 += v.v[3] * ld_x(x, c.v[3]);
+        }
+        if (threadIdx.x < 32 && sync.step > 0) {
+            const unsigned long long t0 = global_timer_ns();
+            for (;;) {
+                unsigned long long f = ~0ull;
+                if (lane < sync.world)
+                    f = sync.relaxed_poll ? ld_relaxed_sys(sync.mine + kSyncFlags + lane)
+                                          : ld_acquire_sys(sync.mine + kSyncFlags + lane);
+                if (__all_sync(0xffffffffu, f >= sync.step)) break;
+                __nanosleep(100);
+                if (global_timer_ns() - t0 > kWaitLimitNs) {  // a peer died: flag it, do not hang
+                    if (lane == 0) atomicExch(sync.err_flag, 2);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        while (have) {
+            acc0 += v.v[0] * ld_xo<true>(x, c.v[0]);
+            acc1 += v.v[1] * ld_xo<true>(x, c.v[1]);
+            acc2 += v.v[2] * ld_xo<true>(x, c.v[2]);
+            acc3 += v.v[3] * ld_xo<true>(x, c.v[3]);
+            g += 32;
+            have = g < n_groups;
+            if (have) {
+                c.load(ip + (g << 2));
+                v.load(dp + (g << 2));
+            }
+        }
+        // 1/||x|| from the partial sums every rank left in this rank's block (per warp, off the
+        // critical path of the loads above)
+        if (sync.step > 0) {
+            const double *sums = reinterpret_cast<const double *>(sync.mine + kSyncSums) + ((sync.step - 1) & 1) * 16 * 32;
+            T part = 0;
+            for (int r = 0; r < sync.world; ++r) part += __ldcg(sums + r * 32 + lane);
+            alpha = rsqrt(subwarp_sum<32>(part));
         }
     }
 #pragma unroll
@@ -511,19 +549,19 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
         }
     }
     if (RING) {
-        // every thread makes its stores visible (system-wide if they crossed NVLink) before the block
-        // takes its ticket: the last block's release of the flag then covers all of them
-        if (wrote_peer) __threadfence_system();
-        else __threadfence();
         sq = subwarp_sum<32>(sq);
         if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
-        __syncthreads();
+        // barrier, then ONE thread fences (system-wide if any store of the block crossed NVLink) and
+        // takes the block's ticket -- the grid-sync idiom: the barrier puts the other threads' stores
+        // before the fence in causality order, so the last block's release of the flag covers them all
+        const int crossed = __syncthreads_or(wrote_peer ? 1 : 0);
         if (threadIdx.x == 0) {
             T total = 0;
 #pragma unroll
             for (int w = 0; w < kBlock / 32; ++w) total += warp_sq[w];
             atomicAdd(reinterpret_cast<double *>(sync.mine + kSyncAcc) + (blockIdx.x & (kSumsqSlots - 1)), total);
-            __threadfence();
+            if (crossed) __threadfence_system();
+            else __threadfence();
             const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(sync.mine + kSyncDone), 1u);
             s_last = ticket == gridDim.x - 1;
         }
@@ -860,6 +898,7 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         sync.world = n_dst;
         sync.step = step;
         sync.err_flag = ctx->scratch + kWatchFlag;
+        if (const char *e = getenv("B200_RING_RELAXED")) sync.relaxed_poll = atoi(e) != 0;
         sell32_bcast_kernel<double, int, true><<<grid, kBlock, 0, ctx->stream>>>(
             data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
         ctx->watch_flag = true;
