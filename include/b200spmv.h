@@ -350,8 +350,8 @@ int b200_spmv_sell_halo_f64(b200_ctx *ctx, const double *data, const int *indice
  * (b200_ipc_*); sync_blocks[r] (HOST array, n_dst entries, indexed by RANK like dst[]) is rank r's
  * block as seen from this process.  At `step` k the kernel first waits until every rank has finished
  * step k-1, folds their partial sums of ||y||^2 (left in this rank's block by the peers) into the
- * 1/||x|| scale (k = 0: no wait, no scaling), runs the SpMV + halo stores, and its last block
- * publishes this rank's partial sums to every rank and releases "step k done" flags system-wide.
+ * 1/||x|| scale (k = 0: no wait, no scaling) and runs the SpMV + halo stores; a second, one-warp launch
+ * then publishes this rank's partial sums to every rank and releases "step k done" flags system-wide.
  * The flags are the barrier that orders the peer writes of the double-buffered x.  All ranks must
  * call it with the same consecutive step numbers.  ||y||^2 of step k = sum over ranks r and slots s of
  * the doubles at byte offset 8*(16 + ((k&1)*16 + r)*32 + s) of any rank's block, valid once every rank

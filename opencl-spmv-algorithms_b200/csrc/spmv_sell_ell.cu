@@ -378,11 +378,12 @@ constexpr int kSumsqSlots = 32;
 //   [kSyncSums + (p*16 + r)*32 + s]  the 32 partial sums of ||y_r||^2 at step parity p, written by r
 //   [kSyncDone]                   this rank's "blocks finished" ticket counter (local use)
 //   [kSyncAcc + s]                this rank's running partial sums of the current step (local use)
-// Step k: warp 0 of every block waits until all ranks have completed step k-1 (flags >= k), folds
-// the ranks' partial sums into 1/||x||, the block runs the SpMV and stores y to the ranks that read
-// it; the LAST block to finish (ticket) publishes this rank's 32 partial sums to every rank, fences,
-// and releases flag = k+1 everywhere.  The flag is both the norm hand-off and the barrier that orders
-// the peer writes of x (double-buffered), which is what the all-reduce did before.
+// Step k = two launches.  SpMV kernel: every warp requests its first matrix group, warp 0 of the block
+// waits until all ranks have completed step k-1 (flags >= k), the block gathers x, scales by 1/||x||
+// folded from the ranks' partial sums, stores y to the ranks that read it and adds its ||y||^2 share
+// to [kSyncAcc].  ring_publish_kernel (one warp): hands the 32 partial sums to every rank, fences
+// system-wide and releases flag = k+1 everywhere.  The flag is both the norm hand-off and the barrier
+// that orders the peer writes of x (double-buffered), which is what the all-reduce did before.
 constexpr int kSyncFlags = 0;
 constexpr int kSyncSums = 16;
 constexpr int kSyncDone = kSyncSums + 2 * 16 * 32;
@@ -416,7 +417,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename T, typename P, bool RING = false>
+template <typename T, typename P, bool RING = false, bool XNC = false>
 __global__ void __launch_bounds__(kBlock)
 sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
                     const P *__restrict__ slice_ptr, int n_slices, int n_rows,
@@ -424,7 +425,6 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
                     long long dst_offset, PeerSync sync)
 {
     __shared__ T warp_sq[kBlock / 32];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const bool active = slice < n_slices;  // no early return: the block reduces ||y||^2 together
@@ -491,10 +491,10 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
         }
         __syncthreads();
         while (have) {
-            acc0 += v.v[0] * ld_xo<true>(x, c.v[0]);
-            acc1 += v.v[1] * ld_xo<true>(x, c.v[1]);
-            acc2 += v.v[2] * ld_xo<true>(x, c.v[2]);
-            acc3 += v.v[3] * ld_xo<true>(x, c.v[3]);
+            acc0 += v.v[0] * ld_xo<!XNC>(x, c.v[0]);
+            acc1 += v.v[1] * ld_xo<!XNC>(x, c.v[1]);
+            acc2 += v.v[2] * ld_xo<!XNC>(x, c.v[2]);
+            acc3 += v.v[3] * ld_xo<!XNC>(x, c.v[3]);
             g += 32;
             have = g < n_groups;
             if (have) {
@@ -525,7 +525,6 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     const T b0 = __shfl_sync(0xffffffffu, acc0, src), b1 = __shfl_sync(0xffffffffu, acc1, src);
     const T b2 = __shfl_sync(0xffffffffu, acc2, src), b3 = __shfl_sync(0xffffffffu, acc3, src);
     T sq = 0;
-    bool wrote_peer = false;
     if (active && lane < 16) {
         const T lo = ((lane & 1) ? b2 : b0) * alpha, hi = ((lane & 1) ? b3 : b1) * alpha;
         const long long r = slice * 32 + lane * 2;
@@ -544,48 +543,11 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
                     if (r >= first && r < last) out[0] = lo;
                     if (r + 1 >= first && r + 1 < last) out[1] = hi;
                 }
-                if (RING && d != sync.my_rank && r + 1 >= first && r < last) wrote_peer = true;
             }
         }
     }
-    if (RING) {
-        sq = subwarp_sum<32>(sq);
-        if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
-        // barrier, then ONE thread fences (system-wide if any store of the block crossed NVLink) and
-        // takes the block's ticket -- the grid-sync idiom: the barrier puts the other threads' stores
-        // before the fence in causality order, so the last block's release of the flag covers them all
-        const int crossed = __syncthreads_or(wrote_peer ? 1 : 0);
-        if (threadIdx.x == 0) {
-            T total = 0;
-#pragma unroll
-            for (int w = 0; w < kBlock / 32; ++w) total += warp_sq[w];
-            atomicAdd(reinterpret_cast<double *>(sync.mine + kSyncAcc) + (blockIdx.x & (kSumsqSlots - 1)), total);
-            if (crossed) __threadfence_system();
-            else __threadfence();
-            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(sync.mine + kSyncDone), 1u);
-            s_last = ticket == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (s_last && threadIdx.x < 32) {
-            __threadfence();
-            double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
-            const double v = atomicAdd(acc + lane, 0.0);  // read through L2, after every block's add
-            acc[lane] = 0.0;                              // ready for the next step's kernel
-            const long long at = (long long)(sync.step & 1) * 16 * 32 + (long long)sync.my_rank * 32 + lane;
-#pragma unroll
-            for (int d = 0; d < kMaxPeers; ++d)
-                if (d < sync.world) reinterpret_cast<double *>(sync.blk[d] + kSyncSums)[at] = v;
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) {
-                *reinterpret_cast<unsigned *>(sync.mine + kSyncDone) = 0u;
-#pragma unroll
-                for (int d = 0; d < kMaxPeers; ++d)
-                    if (d < sync.world) st_release_sys(sync.blk[d] + kSyncFlags + sync.my_rank, sync.step + 1);
-            }
-        }
-        return;
-    }
+    // RING: the partial sums go to this rank's sync block; ring_publish_kernel hands them to the peers
+    if (RING) sumsq_out = reinterpret_cast<T *>(sync.mine + kSyncAcc);
     if (sumsq_out) {
         sq = subwarp_sum<32>(sq);
         if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
@@ -596,6 +558,30 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
             for (int w = 0; w < kBlock / 32; ++w) total += warp_sq[w];
             atomicAdd(sumsq_out + (blockIdx.x & (kSumsqSlots - 1)), total);
         }
+    }
+}
+
+// Second (tiny) launch of a ring step: one warp hands this rank's 32 partial sums of ||y||^2 to every
+// rank, fences system-wide and releases the "step done" flags.  It runs after the SpMV kernel on the
+// same stream, i.e. after ALL of that kernel's stores -- own and peer -- have been performed, so the
+// SpMV kernel itself needs no per-block fence, ticket or "last block" logic (a first version had them:
+// every block then lingered ~2 us on the ticket's round trip, +0.06 ms per step).
+__global__ void ring_publish_kernel(PeerSync sync)
+{
+    const int lane = threadIdx.x;
+    double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
+    const double v = acc[lane];
+    acc[lane] = 0.0;  // ready for the next step's kernel
+    const long long at = (long long)(sync.step & 1) * 16 * 32 + (long long)sync.my_rank * 32 + lane;
+#pragma unroll
+    for (int d = 0; d < kMaxPeers; ++d)
+        if (d < sync.world) reinterpret_cast<double *>(sync.blk[d] + kSyncSums)[at] = v;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < kMaxPeers; ++d)
+            if (d < sync.world) st_release_sys(sync.blk[d] + kSyncFlags + sync.my_rank, sync.step + 1);
     }
 }
 
@@ -899,8 +885,16 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         sync.step = step;
         sync.err_flag = ctx->scratch + kWatchFlag;
         if (const char *e = getenv("B200_RING_RELAXED")) sync.relaxed_poll = atoi(e) != 0;
-        sell32_bcast_kernel<double, int, true><<<grid, kBlock, 0, ctx->stream>>>(
-            data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
+        bool xnc = false;  // B200_RING_NC=1: gather x with ld.global.nc (diagnosis only: ptxas may move
+                           // such loads above the barrier that follows the flag wait)
+        if (const char *e = getenv("B200_RING_NC")) xnc = atoi(e) != 0;
+        if (xnc)
+            sell32_bcast_kernel<double, int, true, true><<<grid, kBlock, 0, ctx->stream>>>(
+                data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
+        else
+            sell32_bcast_kernel<double, int, true, false><<<grid, kBlock, 0, ctx->stream>>>(
+                data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
+        ring_publish_kernel<<<1, 32, 0, ctx->stream>>>(sync);
         ctx->watch_flag = true;
     } else {
         sell32_bcast_kernel<double, int, false><<<grid, kBlock, 0, ctx->stream>>>(
