@@ -348,14 +348,15 @@ int b200_spmv_sell_halo_f64(b200_ctx *ctx, const double *data, const int *indice
 /* Same kernel with NO collective call per step at all ("ring" of flags over peer memory).  Every rank
  * allocates one zero-filled sync block of B200_SYNC_BLOCK_BYTES with b200_malloc and maps the others'
  * (b200_ipc_*); sync_blocks[r] (HOST array, n_dst entries, indexed by RANK like dst[]) is rank r's
- * block as seen from this process.  At `step` k the kernel first waits until every rank has finished
- * step k-1, folds their partial sums of ||y||^2 (left in this rank's block by the peers) into the
- * 1/||x|| scale (k = 0: no wait, no scaling) and runs the SpMV + halo stores; a second, one-warp launch
- * then publishes this rank's partial sums to every rank and releases "step k done" flags system-wide.
- * The flags are the barrier that orders the peer writes of the double-buffered x.  All ranks must
- * call it with the same consecutive step numbers.  ||y||^2 of step k = sum over ranks r and slots s of
- * the doubles at byte offset 8*(16 + ((k&1)*16 + r)*32 + s) of any rank's block, valid once every rank
- * has finished step k (synchronise all ranks before reading it on the host). */
+ * block as seen from this process.  Step k is two launches on the context's queue: the fused SpMV +
+ * halo-store kernel (1/||x|| from the sums folded at the end of step k-1; k = 0: no scaling), and a
+ * one-warp kernel that publishes this rank's partial sums of ||y||^2 to every rank, fences system-wide,
+ * releases "step k done" flags in every rank's block, waits until every rank's flag has arrived here
+ * and folds the ranks' sums for step k+1.  The flags are the barrier that orders the peer writes of the
+ * double-buffered x: work queued after this call sees every rank's step-k rows.  All ranks must call
+ * it with the same consecutive step numbers, concurrently (a rank that never arrives is reported as
+ * B200_ERR_CUDA by the next b200_sync after a 2 s wait, not a hang).  ||y||^2 of step k = sum over
+ * ranks r and slots s of the doubles at byte offset 8*(16 + ((k&1)*16 + r)*32 + s) of any rank's block. */
 #define B200_SYNC_BLOCK_BYTES 16384
 int b200_spmv_sell_ring_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                             const int *row_indices, int chunk, int n_slices, int n_rows, double *const *dst,

@@ -378,17 +378,15 @@ constexpr int kSumsqSlots = 32;
 //   [kSyncSums + (p*16 + r)*32 + s]  the 32 partial sums of ||y_r||^2 at step parity p, written by r
 //   [kSyncDone]                   this rank's "blocks finished" ticket counter (local use)
 //   [kSyncAcc + s]                this rank's running partial sums of the current step (local use)
-// Step k = two launches.  SpMV kernel: every warp requests its first matrix group, warp 0 of the block
-// waits until all ranks have completed step k-1 (flags >= k), the block gathers x, scales by 1/||x||
-// folded from the ranks' partial sums, stores y to the ranks that read it and adds its ||y||^2 share
-// to [kSyncAcc].  ring_publish_kernel (one warp): hands the 32 partial sums to every rank, fences
-// system-wide and releases flag = k+1 everywhere.  The flag is both the norm hand-off and the barrier
-// that orders the peer writes of x (double-buffered), which is what the all-reduce did before.
+//   [kSyncScale + s]              sum over ranks of the previous step's partial sums (local use)
+// Step k = two launches: the plain fused SpMV + halo-store kernel (scale from [kSyncScale], ||y||^2
+// share added to [kSyncAcc]) and ring_sync_kernel below.
 constexpr int kSyncFlags = 0;
 constexpr int kSyncSums = 16;
 constexpr int kSyncDone = kSyncSums + 2 * 16 * 32;
 constexpr int kSyncAcc = kSyncDone + 2;
-constexpr int kSyncWords = kSyncAcc + 32;
+constexpr int kSyncScale = kSyncAcc + 32;
+constexpr int kSyncWords = kSyncScale + 32;
 static_assert(kSyncWords * 8 <= B200_SYNC_BLOCK_BYTES, "sync block layout exceeds B200_SYNC_BLOCK_BYTES");
 
 struct PeerSync {
@@ -397,7 +395,6 @@ struct PeerSync {
     int my_rank, world;
     unsigned long long step;
     int *err_flag;
-    int relaxed_poll;  // B200_RING_RELAXED=1: poll the flags with ld.relaxed.sys (tuning hook)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -417,12 +414,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename T, typename P, bool RING = false, bool XNC = false>
+template <typename T, typename P>
 __global__ void __launch_bounds__(kBlock)
 sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
                     const P *__restrict__ slice_ptr, int n_slices, int n_rows,
                     const T *__restrict__ scale2, T *__restrict__ sumsq_out, PeerDst<T> dst, int n_dst,
-                    long long dst_offset, PeerSync sync)
+                    long long dst_offset)
 {
     __shared__ T warp_sq[kBlock / 32];
     const int lane = threadIdx.x & 31;
@@ -430,85 +427,25 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     const bool active = slice < n_slices;  // no early return: the block reduces ||y||^2 together
     // 1/||x||: one coalesced load of the 32 partial sums per warp, folded with shuffles
     T alpha = 1;
-    if (!RING && scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
+    if (scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
     T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-    if (!RING) {
-        if (active) {
-            const long long chunk_base = slice_ptr[slice];
-            const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
-            const int *ip = idx + chunk_base;
-            const T *dp = data + chunk_base;
-            // one group per lane and round trip: a 7-point-stencil chunk is only 56 groups, and the
-            // batched form (58 registers) measured slower here (0.196 vs 0.189 ms per step)
+    if (active) {
+        const long long chunk_base = slice_ptr[slice];
+        const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
+        const int *ip = idx + chunk_base;
+        const T *dp = data + chunk_base;
+        // one group per lane and round trip: a 7-point-stencil chunk is only 56 groups, and the
+        // batched form (58 registers) measured slower here (0.196 vs 0.189 ms per step)
 #pragma unroll 4
-            for (long long g = lane; g < n_groups; g += 32) {
-                IVec4 c;
-                Vec4<T> v;
-                c.load(ip + (g << 2));
-                v.load(dp + (g << 2));
-                acc0 += v.v[0] * ld_x(x, c.v[0]);
-                acc1 += v.v[1] * ld_x(x, c.v[1]);
-                acc2 += v.v[2] * ld_x(x, c.v[2]);
-                acc3 += v.v[3] * ld_x(x, c.v[3]);
-            }
-        }
-    } else {
-        // 1. every warp requests its first group of matrix data (the matrix never changes);
-        // 2. meanwhile warp 0 makes sure all ranks have completed the previous step -- their x rows and
-        //    partial sums are then in this GPU's memory (their stores precede their release of the
-        //    flag) -- and the block barrier passes that on to the other warps;
-        // 3. only then is x gathered, with coherent loads (ptxas moves ld.global.nc above barriers).
-        long long n_groups = 0, g = lane;
-        const int *ip = idx;
-        const T *dp = data;
-        if (active) {
-            const long long chunk_base = slice_ptr[slice];
-            n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
-            ip += chunk_base;
-            dp += chunk_base;
-        }
-        IVec4 c;
-        Vec4<T> v;
-        bool have = g < n_groups;
-        if (have) {
+        for (long long g = lane; g < n_groups; g += 32) {
+            IVec4 c;
+            Vec4<T> v;
             c.load(ip + (g << 2));
             v.load(dp + (g << 2));
-        }
-        if (threadIdx.x < 32 && sync.step > 0) {
-            const unsigned long long t0 = global_timer_ns();
-            for (;;) {
-                unsigned long long f = ~0ull;
-                if (lane < sync.world)
-                    f = sync.relaxed_poll ? ld_relaxed_sys(sync.mine + kSyncFlags + lane)
-                                          : ld_acquire_sys(sync.mine + kSyncFlags + lane);
-                if (__all_sync(0xffffffffu, f >= sync.step)) break;
-                __nanosleep(100);
-                if (global_timer_ns() - t0 > kWaitLimitNs) {  // a peer died: flag it, do not hang
-                    if (lane == 0) atomicExch(sync.err_flag, 2);
-                    break;
-                }
-            }
-        }
-        __syncthreads();
-        while (have) {
-            acc0 += v.v[0] * ld_xo<!XNC>(x, c.v[0]);
-            acc1 += v.v[1] * ld_xo<!XNC>(x, c.v[1]);
-            acc2 += v.v[2] * ld_xo<!XNC>(x, c.v[2]);
-            acc3 += v.v[3] * ld_xo<!XNC>(x, c.v[3]);
-            g += 32;
-            have = g < n_groups;
-            if (have) {
-                c.load(ip + (g << 2));
-                v.load(dp + (g << 2));
-            }
-        }
-        // 1/||x|| from the partial sums every rank left in this rank's block (per warp, off the
-        // critical path of the loads above)
-        if (sync.step > 0) {
-            const double *sums = reinterpret_cast<const double *>(sync.mine + kSyncSums) + ((sync.step - 1) & 1) * 16 * 32;
-            T part = 0;
-            for (int r = 0; r < sync.world; ++r) part += __ldcg(sums + r * 32 + lane);
-            alpha = rsqrt(subwarp_sum<32>(part));
+            acc0 += v.v[0] * ld_x(x, c.v[0]);
+            acc1 += v.v[1] * ld_x(x, c.v[1]);
+            acc2 += v.v[2] * ld_x(x, c.v[2]);
+            acc3 += v.v[3] * ld_x(x, c.v[3]);
         }
     }
 #pragma unroll
@@ -546,8 +483,6 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
             }
         }
     }
-    // RING: the partial sums go to this rank's sync block; ring_publish_kernel hands them to the peers
-    if (RING) sumsq_out = reinterpret_cast<T *>(sync.mine + kSyncAcc);
     if (sumsq_out) {
         sq = subwarp_sum<32>(sq);
         if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
@@ -561,21 +496,27 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     }
 }
 
-// Second (tiny) launch of a ring step: one warp hands this rank's 32 partial sums of ||y||^2 to every
-// rank, fences system-wide and releases the "step done" flags.  It runs after the SpMV kernel on the
-// same stream, i.e. after ALL of that kernel's stores -- own and peer -- have been performed, so the
-// SpMV kernel itself needs no per-block fence, ticket or "last block" logic (a first version had them:
-// every block then lingered ~2 us on the ticket's round trip, +0.06 ms per step).
-__global__ void ring_publish_kernel(PeerSync sync)
+// Second (one-warp) launch of a ring step -- the whole "all-reduce + barrier" of the step:
+//   publish  this rank's 32 partial sums of ||y||^2 go to every rank's sync block, a system-wide fence,
+//            then flag[my_rank] = k+1 is released in every rank's block.  The kernel runs after the SpMV
+//            kernel on the same stream, i.e. after ALL of its stores -- own and peer -- have been
+//            performed, so the release covers this rank's halo stores too;
+//   wait     until every rank's flag in THIS rank's block is k+1 (acquire): their x rows and sums are
+//            then in this GPU's memory, and they are done reading the buffers step k+1 will overwrite;
+//   fold     the ranks' sums into the 32 local slots the next SpMV kernel takes 1/||x|| from.
+// (A first version did all this inside the SpMV kernel -- flag wait in every block, "last block"
+// ticket -- and cost +0.03 ms per step on ONE GPU: every block sat out an acquire and a ticket round
+// trip.  Two plain launches are cheaper.)
+__global__ void ring_sync_kernel(PeerSync sync)
 {
     const int lane = threadIdx.x;
     double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
     const double v = acc[lane];
-    acc[lane] = 0.0;  // ready for the next step's kernel
-    const long long at = (long long)(sync.step & 1) * 16 * 32 + (long long)sync.my_rank * 32 + lane;
+    acc[lane] = 0.0;  // ready for the next step's SpMV kernel
+    const long long base = (long long)(sync.step & 1) * 16 * 32;
 #pragma unroll
     for (int d = 0; d < kMaxPeers; ++d)
-        if (d < sync.world) reinterpret_cast<double *>(sync.blk[d] + kSyncSums)[at] = v;
+        if (d < sync.world) reinterpret_cast<double *>(sync.blk[d] + kSyncSums)[base + (long long)sync.my_rank * 32 + lane] = v;
     __threadfence_system();
     __syncwarp();
     if (lane == 0) {
@@ -583,6 +524,20 @@ __global__ void ring_publish_kernel(PeerSync sync)
         for (int d = 0; d < kMaxPeers; ++d)
             if (d < sync.world) st_release_sys(sync.blk[d] + kSyncFlags + sync.my_rank, sync.step + 1);
     }
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        const unsigned long long f = lane < sync.world ? ld_acquire_sys(sync.mine + kSyncFlags + lane) : ~0ull;
+        if (__all_sync(0xffffffffu, f >= sync.step + 1)) break;
+        __nanosleep(100);
+        if (global_timer_ns() - t0 > kWaitLimitNs) {  // a peer died: flag it, do not hang
+            if (lane == 0) atomicExch(sync.err_flag, 2);
+            break;
+        }
+    }
+    const double *sums = reinterpret_cast<const double *>(sync.mine + kSyncSums) + base;
+    double total = 0;
+    for (int r = 0; r < sync.world; ++r) total += __ldcg(sums + r * 32 + lane);
+    reinterpret_cast<double *>(sync.mine + kSyncScale)[lane] = total;
 }
 
 // scalar-load variant for unaligned arrays: lane = row (the reference's mapping)
@@ -884,21 +839,15 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         sync.world = n_dst;
         sync.step = step;
         sync.err_flag = ctx->scratch + kWatchFlag;
-        if (const char *e = getenv("B200_RING_RELAXED")) sync.relaxed_poll = atoi(e) != 0;
-        bool xnc = false;  // B200_RING_NC=1: gather x with ld.global.nc (diagnosis only: ptxas may move
-                           // such loads above the barrier that follows the flag wait)
-        if (const char *e = getenv("B200_RING_NC")) xnc = atoi(e) != 0;
-        if (xnc)
-            sell32_bcast_kernel<double, int, true, true><<<grid, kBlock, 0, ctx->stream>>>(
-                data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
-        else
-            sell32_bcast_kernel<double, int, true, false><<<grid, kBlock, 0, ctx->stream>>>(
-                data, indices, vect, row_indices, n_slices, n_rows, nullptr, nullptr, d, n_dst, dst_offset, sync);
-        ring_publish_kernel<<<1, 32, 0, ctx->stream>>>(sync);
+        double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
+        const double *scale = step > 0 ? reinterpret_cast<const double *>(sync.mine + kSyncScale) : nullptr;
+        sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
+            data, indices, vect, row_indices, n_slices, n_rows, scale, acc, d, n_dst, dst_offset);
+        ring_sync_kernel<<<1, 32, 0, ctx->stream>>>(sync);
         ctx->watch_flag = true;
     } else {
-        sell32_bcast_kernel<double, int, false><<<grid, kBlock, 0, ctx->stream>>>(
-            data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset, sync);
+        sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
+            data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
     }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;

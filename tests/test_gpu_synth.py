@@ -294,9 +294,10 @@ def test_halo_limited_exchange_three_emulated_ranks(ctx):
 
 def test_ring_exchange_three_emulated_ranks(ctx):
     """b200_spmv_sell_ring_f64: the same three emulated ranks, but no host-side all-reduce at all --
-    the kernels hand over partial sums of ||y||^2 and 'step done' flags through the sync blocks.  On one
-    stream the ranks' kernels of a step simply run one after the other, so every wait is already
-    satisfied; the data flow (flags, partial sums, halo stores, double buffering) is the real one."""
+    the ranks hand over partial sums of ||y||^2 and 'step done' flags through their sync blocks.  Each
+    emulated rank has its own context (stream) on the one GPU, so a rank's sync kernel can wait for the
+    others' flags while their kernels run: the data flow (flags, partial sums, halo stores, double
+    buffering) is the real one."""
     import ctypes as C
     L = pkg.lib()
     nx, ny, nz, steps, G = 16, 12, 30, 24, 3
@@ -310,28 +311,32 @@ def test_ring_exchange_three_emulated_ranks(ctx):
         y = O.spmv_csr(n, ptr, cols, vals, x)
         nrm = np.linalg.norm(y)
         x = y / nrm
+    ctxs = [pkg.Context(0) for _ in range(G)]
     sells, ranges, n_local = [], [], []
     for r in range(G):
         b0, b1 = blocks.bounds(r)
         sel = slice(ptr[b0], ptr[b1])
-        coo = pkg.CooMatrix.from_host(ctx, b1 - b0, n, rows[sel] - b0, cols[sel], vals[sel])
+        coo = pkg.CooMatrix.from_host(ctxs[r], b1 - b0, n, rows[sel] - b0, cols[sel], vals[sel])
         sells.append(pkg.SellMatrix(pkg.CsrMatrix(coo), np.float64))
         ranges.append((int(cols[sel].min()), int(cols[sel].max())))
         n_local.append(b1 - b0)
     halos = [pkg.halo_rows(ranges, blocks, r) for r in range(G)]
-    bufs = [[ctx.array(x0 if b == 0 else np.zeros(blocks.padded)) for b in range(2)] for r in range(G)]
-    sync = [ctx.zeros(16384 // 8, np.float64) for r in range(G)]
+    bufs = [[ctxs[r].array(x0 if b == 0 else np.zeros(blocks.padded)) for b in range(2)] for r in range(G)]
+    sync = [ctxs[r].zeros(16384 // 8, np.float64) for r in range(G)]
     sync_ptrs = (C.c_void_p * G)(*[s.ptr for s in sync])
+    for c in ctxs:
+        c.sync()
     for k in range(steps):
         cur, nxt = k % 2, (k + 1) % 2
         for r in range(G):
             dst = (C.c_void_p * G)(*[bufs[d][nxt].ptr for d in range(G)])
             lo_a, hi_a = (C.c_int * G)(*halos[r][0]), (C.c_int * G)(*halos[r][1])
             pkg.check(L.b200_spmv_sell_ring_f64(
-                ctx.h, sells[r].data.ptr, sells[r].cols.ptr, bufs[r][cur].ptr, sells[r].row_indices.ptr, 32,
+                ctxs[r].h, sells[r].data.ptr, sells[r].cols.ptr, bufs[r][cur].ptr, sells[r].row_indices.ptr, 32,
                 sells[r].n_slices, n_local[r], dst, G, r * blocks.count, lo_a, hi_a, sync_ptrs, r, k),
                 "b200_spmv_sell_ring_f64")
-    ctx.sync()                                            # also reports a timed-out flag wait
+    for c in ctxs:
+        c.sync()                                          # also reports a timed-out flag wait
     last = steps - 1
     at = 16 + (last & 1) * 16 * 32
     for r in range(G):
@@ -339,7 +344,9 @@ def test_ring_exchange_three_emulated_ranks(ctx):
         assert np.array_equal(words[:G].view(np.uint64), np.full(G, steps, np.uint64))     # flags
         norm = np.sqrt(words[at:at + G * 32].sum())
         assert abs(norm - nrm) <= 1e-12 * nrm
-        assert words[16 + 2 * 16 * 32] == 0.0                                              # ticket counter reset
         b0, b1 = blocks.bounds(r)
         own = bufs[r][steps % 2].download()[b0:b1]
         assert np.max(np.abs(own / norm - x[b0:b1])) <= 1e-12
+    del sells, bufs, sync
+    for c in ctxs:
+        c.close()
