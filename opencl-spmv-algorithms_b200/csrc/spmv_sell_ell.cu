@@ -395,6 +395,9 @@ struct PeerSync {
     int my_rank, world;
     unsigned long long step;
     int *err_flag;
+    int flush_after_flag;  // B200_RING_FLUSH (default 1): system fence AFTER the flag stores as well
+    int poll_mode;         // B200_RING_POLL: 0 acquire loads (default), 1 relaxed loads + one fence at the end
+    int sleep_ns;          // B200_RING_SLEEP_NS between polls (default 100; 0 = none)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -524,16 +527,22 @@ __global__ void ring_sync_kernel(PeerSync sync)
         for (int d = 0; d < kMaxPeers; ++d)
             if (d < sync.world) st_release_sys(sync.blk[d] + kSyncFlags + sync.my_rank, sync.step + 1);
     }
+    // push the flag stores out now: without a fence behind them they may sit in the write path until
+    // the kernel ends -- and this kernel only ends when the PEERS' flags have arrived
+    if (sync.flush_after_flag) __threadfence_system();
     const unsigned long long t0 = global_timer_ns();
     for (;;) {
-        const unsigned long long f = lane < sync.world ? ld_acquire_sys(sync.mine + kSyncFlags + lane) : ~0ull;
+        unsigned long long f = ~0ull;
+        if (lane < sync.world)
+            f = sync.poll_mode ? ld_relaxed_sys(sync.mine + kSyncFlags + lane) : ld_acquire_sys(sync.mine + kSyncFlags + lane);
         if (__all_sync(0xffffffffu, f >= sync.step + 1)) break;
-        __nanosleep(100);
+        if (sync.sleep_ns > 0) __nanosleep(sync.sleep_ns);
         if (global_timer_ns() - t0 > kWaitLimitNs) {  // a peer died: flag it, do not hang
             if (lane == 0) atomicExch(sync.err_flag, 2);
             break;
         }
     }
+    if (sync.poll_mode) __threadfence_system();
     const double *sums = reinterpret_cast<const double *>(sync.mine + kSyncSums) + base;
     double total = 0;
     for (int r = 0; r < sync.world; ++r) total += __ldcg(sums + r * 32 + lane);
@@ -839,6 +848,12 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         sync.world = n_dst;
         sync.step = step;
         sync.err_flag = ctx->scratch + kWatchFlag;
+        sync.flush_after_flag = 1;
+        sync.poll_mode = 0;
+        sync.sleep_ns = 100;
+        if (const char *e = getenv("B200_RING_FLUSH")) sync.flush_after_flag = atoi(e) != 0;
+        if (const char *e = getenv("B200_RING_POLL")) sync.poll_mode = atoi(e) != 0;
+        if (const char *e = getenv("B200_RING_SLEEP_NS")) sync.sleep_ns = atoi(e);
         double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
         const double *scale = step > 0 ? reinterpret_cast<const double *>(sync.mine + kSyncScale) : nullptr;
         sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
