@@ -909,6 +909,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
     fused_norm = None
     fused_full_ms = None
     fused_halo_ms = None
+    ring_ms = None
     halo_bytes = None
     if fmt == "sell":
         bufs = pkg.PeerBuffers(pkg, ctx, blocks, rank, world)
@@ -948,7 +949,8 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
             sync_all()
             return f0.elapsed_time(f1) / args.steps, r1.norm
 
-        fused_ms, fused_norm = ring_run()
+        ring_ms, ring_norm = ring_run()
+        fused_ms, fused_norm = fused_halo_ms, fused_halo_norm   # the product path
         bufs.close()
 
     # split: SpMV alone and the all-gather alone, same buffers (explains the step time)
@@ -968,7 +970,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
     gather_ms = a.elapsed_time(b) / 10
 
     t = torch.tensor([step_ms, spmv_ms, gather_ms, float(nnz), fused_ms or 0.0, fused_full_ms or 0.0,
-                      float(halo_bytes or 0), fused_halo_ms or 0.0], device="cuda", dtype=torch.float64)
+                      float(halo_bytes or 0), ring_ms or 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -978,7 +980,7 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
         fused_ms = float(tmax[4]) if fused_ms is not None else None
         fused_full_ms = float(tmax[5]) if fused_full_ms is not None else None
         halo_bytes = int(tmax[6]) if halo_bytes is not None else None
-        fused_halo_ms = float(tmax[7]) if fused_halo_ms is not None else None
+        ring_ms = float(tmax[7]) if ring_ms is not None else None
     else:
         nnz_total = float(nnz)
     nccl_ms = step_ms
@@ -998,14 +1000,16 @@ def laplace_iter_arm(pkg, args, rank, world, local_rank):
                                    f"{int(nnz_total)} nnz, fp64, {fmt.upper()}, {world} row block(s), NCCL all-gather of x per step",
                        "rows_per_gpu": int(n_local), "nnz_per_gpu": int(nnz),
                        "cache": "inputs larger than L2 (0.7 GB matrix + 2 x 64 MB x per GPU per world rank), no flush"},
-            "exchange": ("ring: ONE kernel per step and no collective call -- the SpMV kernel stores each y row into "
-                         "the x buffers of the ranks that read it (its own + neighbours) over NVLink (CUDA IPC), and "
-                         "the ranks hand over ||y||^2 partial sums and 'step done' flags through peer memory"
+            "exchange": ("fused, halo-limited: the SpMV kernel stores each y row into the x buffers of the ranks that "
+                         "read it (its own + neighbours) over NVLink (CUDA IPC) + one 256-byte NCCL all-reduce"
                          if fused_ms is not None else "NCCL all_gather_into_tensor (in place)"),
-            "fused_halo_allreduce": (None if fused_halo_ms is None else
-                                     {"ms_per_step": round(fused_halo_ms, 5),
-                                      "gflops": round(2.0 * nnz_total / (fused_halo_ms * 1e-3) * 1e-9, 2),
-                                      "what": "halo-limited stores + one 256-byte NCCL all-reduce per step"}),
+            "ring_no_collective": (None if ring_ms is None else
+                                   {"ms_per_step": round(ring_ms, 5),
+                                    "gflops": round(2.0 * nnz_total / (ring_ms * 1e-3) * 1e-9, 2),
+                                    "what": "same halo-limited kernel + a one-warp kernel that hands over ||y||^2 partial "
+                                            "sums and 'step done' flags through peer memory instead of the all-reduce "
+                                            "(b200_spmv_sell_ring_f64); opt-in: measured slower than the all-reduce at "
+                                            "2 GPUs"}),
             "fused_full_broadcast": (None if fused_full_ms is None else
                                      {"ms_per_step": round(fused_full_ms, 5),
                                       "gflops": round(2.0 * nnz_total / (fused_full_ms * 1e-3) * 1e-9, 2),
