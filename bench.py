@@ -2,10 +2,12 @@
 """bench.py -- the measurement contract.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload banded|cant] [--dtype f32|f64] [--rows-per-gpu R]
+                    [--workload banded|cant|rmat|laplace-iter] [--dtype f32|f64] [--rows-per-gpu R]
 
 One "step" = one pass of the hot path over the workload = one SpMV in each of the reference's five
-formats (COO, CSR, ELL, SELL-32, CMRS) on the same matrix.  Default workload: BASELINE.json
+formats (COO, CSR, ELL, SELL-32, CMRS) on the same matrix.  (--workload cant: the cant-shaped matrix
+fits in L2, so 7 independent copies are used in rotation and the K steps are one CUDA-graph replay;
+--workload rmat / laplace-iter: BASELINE configs[3] / configs[4])  Default workload: BASELINE.json
 configs[2], the synthetic banded FEM-like matrix, 2 097 152 rows x 64 nnz/row per GPU, fp32,
 generated on the device (weak scaling: rank r owns rows [r*R, (r+1)*R) of the (N*R)-row global
 matrix, x replicated, no collective in the data path).  Every format's arrays (0.8-1.6 GB) are far
