@@ -34,6 +34,8 @@ typedef struct {
     int device;         /* --device D */
     int no_cpu;         /* --no-cpu        skip the "CPU calculations" block */
     int rowmajor;       /* --rowmajor (default) | --colmajor   (ell only) which ELL kernel/layout runs */
+    int expand_symmetric; /* --expand-symmetric  mirror the off-diagonal entries of a symmetric file (default:
+                             ignore the banner's symmetry, as the reference does) */
 } driver_options;
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt);
@@ -42,6 +44,16 @@ bool read_size_of_matrices_from_file(FILE *file, int *number_of_rows, int *numbe
                                      int *number_of_nonzeroes);
 /* the per-driver "%d %d %lg\n" loop (csr.c:77-83), 1-based -> 0-based; false on a short file */
 bool read_entries(FILE *file, int number_of_nonzeroes, int *rows, int *cols, double *data);
+
+/* New, optional: with set_expand_symmetric(1), driver_load_matrix and check_result mirror the
+ * off-diagonal entries of files whose banner says symmetric / hermitian (skew-symmetric: negated)
+ * and sort the result by (row, column).  expand_symmetric_entries does the work on malloc'ed arrays
+ * (replaced on success); symmetry: 0 general (no-op), 1 symmetric, -1 skew.  last_banner_symmetry()
+ * = that code for the header read last by read_size_of_matrices_from_file. */
+void set_expand_symmetric(int enable);
+int last_banner_symmetry(void);
+bool expand_symmetric_entries(int number_of_rows, int number_of_columns, int symmetry, int *number_of_nonzeroes,
+                              int **rows, int **cols, double **data);
 
 void calculate_and_print_performance(double ms, int number_of_nonzeroes);
 void calculate_and_print_speed(double ms, int number_of_nonzeroes);

@@ -13,6 +13,8 @@
 
 static int g_value_bytes = 8;
 static double g_rel_tolerance = 1e-12;
+static int g_expand_symmetric = 0;   /* --expand-symmetric */
+static int g_banner_symmetry = 0;    /* of the last header read: 0 general, 1 symmetric/hermitian, -1 skew */
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt)
 {
@@ -23,6 +25,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     opt->device = 0;
     opt->no_cpu = 0;
     opt->rowmajor = 1;
+    opt->expand_symmetric = 0;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
         const char *v = i + 1 < argc ? argv[i + 1] : NULL;
@@ -38,15 +41,17 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
         else if (!strcmp(a, "--no-cpu")) opt->no_cpu = 1;
         else if (!strcmp(a, "--rowmajor")) opt->rowmajor = 1;
         else if (!strcmp(a, "--colmajor")) opt->rowmajor = 0;
+        else if (!strcmp(a, "--expand-symmetric")) opt->expand_symmetric = 1;
         else goto bad;
     }
     if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0) goto bad;
     set_value_bytes(opt->use_f32 ? 4 : 8);
     set_check_tolerance(opt->use_f32 ? 1e-5 : 1e-12);
+    set_expand_symmetric(opt->expand_symmetric);
     return 0;
 bad:
     fprintf(stderr, "usage: %s [--matrix FILE.mtx] [--dtype f32|f64] [--sigma N] [--reps N] "
-                    "[--device D] [--no-cpu] [--rowmajor|--colmajor]\n", argv[0]);
+                    "[--device D] [--no-cpu] [--rowmajor|--colmajor] [--expand-symmetric]\n", argv[0]);
     return 1;
 }
 
@@ -68,6 +73,7 @@ bool read_size_of_matrices_from_file(FILE *file, int *number_of_rows, int *numbe
         free(name);
         return false;
     }
+    g_banner_symmetry = mm_is_skew(matcode) ? -1 : (mm_is_symmetric(matcode) || mm_is_hermitian(matcode)) ? 1 : 0;
     return mm_read_mtx_crd_size(file, number_of_rows, number_of_columns, number_of_nonzeroes) == 0;
 }
 
@@ -189,6 +195,89 @@ bool read_entries(FILE *file, int number_of_nonzeroes, int *rows, int *cols, dou
     return ok;
 }
 
+/* ---- optional symmetric expansion (new) ---------------------------------------------------
+ * The reference reads the banner's symmetry and ignores it (inc/helper_functions.h:143-156), so on
+ * the shipped cant.mtx -- stored `symmetric`, lower triangle only -- it multiplies by the lower
+ * triangle.  That stays the default.  With --expand-symmetric every off-diagonal entry (r, c, v) of
+ * a symmetric / hermitian / skew-symmetric file also yields (c, r, +-v), and the result is sorted
+ * by (row, column) with two stable counting sorts, which is the order the CSR / ELL / SELL / CMRS
+ * builders need.  A `general` file is left untouched. */
+void set_expand_symmetric(int enable) { g_expand_symmetric = enable; }
+int last_banner_symmetry(void) { return g_banner_symmetry; }
+
+static bool counting_sort_by(const int *key, int n_keys, int n, const int *in_perm, int *out_perm)
+{
+    size_t *start = (size_t *)calloc((size_t)n_keys + 1, sizeof(size_t));
+    if (!start) return false;
+    for (int i = 0; i < n; ++i) start[key[in_perm[i]] + 1]++;
+    for (int k = 0; k < n_keys; ++k) start[k + 1] += start[k];
+    for (int i = 0; i < n; ++i) out_perm[start[key[in_perm[i]]]++] = in_perm[i];
+    free(start);
+    return true;
+}
+
+bool expand_symmetric_entries(int number_of_rows, int number_of_columns, int symmetry, int *number_of_nonzeroes,
+                              int **rows, int **cols, double **data)
+{
+    if (symmetry == 0) return true;
+    const int nnz = *number_of_nonzeroes;
+    long long extra = 0;
+    for (int i = 0; i < nnz; ++i) extra += (*rows)[i] != (*cols)[i];
+    const long long total = (long long)nnz + extra;
+    if (total > 0x7fffffffll || number_of_rows != number_of_columns) return false;
+    const int n = (int)total;
+    int *r = (int *)malloc(sizeof(int) * (size_t)n + 16), *c = (int *)malloc(sizeof(int) * (size_t)n + 16);
+    double *v = (double *)malloc(sizeof(double) * (size_t)n + 16);
+    int *p0 = (int *)malloc(sizeof(int) * (size_t)n + 16), *p1 = (int *)malloc(sizeof(int) * (size_t)n + 16);
+    bool ok = r && c && v && p0 && p1;
+    if (ok) {
+        int at = nnz;
+        for (int i = 0; i < nnz; ++i) {
+            r[i] = (*rows)[i];
+            c[i] = (*cols)[i];
+            v[i] = (*data)[i];
+            if (r[i] != c[i]) {
+                r[at] = c[i];
+                c[at] = r[i];
+                v[at] = symmetry < 0 ? -v[i] : v[i];
+                ++at;
+            }
+        }
+        for (int i = 0; i < n; ++i) p0[i] = i;
+        /* LSD: stable by column, then stable by row -> sorted by (row, column) */
+        ok = counting_sort_by(c, number_of_columns, n, p0, p1) && counting_sort_by(r, number_of_rows, n, p1, p0);
+    }
+    if (ok) {
+        int *r2 = (int *)malloc(sizeof(int) * (size_t)n + 16), *c2 = (int *)malloc(sizeof(int) * (size_t)n + 16);
+        double *v2 = (double *)malloc(sizeof(double) * (size_t)n + 16);
+        ok = r2 && c2 && v2;
+        if (ok) {
+            for (int i = 0; i < n; ++i) {
+                r2[i] = r[p0[i]];
+                c2[i] = c[p0[i]];
+                v2[i] = v[p0[i]];
+            }
+            free(*rows);
+            free(*cols);
+            free(*data);
+            *rows = r2;
+            *cols = c2;
+            *data = v2;
+            *number_of_nonzeroes = n;
+        } else {
+            free(r2);
+            free(c2);
+            free(v2);
+        }
+    }
+    free(r);
+    free(c);
+    free(v);
+    free(p0);
+    free(p1);
+    return ok;
+}
+
 void set_value_bytes(int bytes) { g_value_bytes = bytes; }
 void set_check_tolerance(double relative_max_norm) { g_rel_tolerance = relative_max_norm; }
 
@@ -225,6 +314,9 @@ bool check_result(const char *filename, double *vect, double *result)
     double *expect = (double *)calloc((size_t)number_of_rows, sizeof(double));
     bool ok = rows && cols && vals && expect && read_entries(file, number_of_nonzeroes, rows, cols, vals);
     fclose(file);
+    if (ok && g_expand_symmetric)
+        ok = expand_symmetric_entries(number_of_rows, number_of_columns, g_banner_symmetry, &number_of_nonzeroes,
+                                      &rows, &cols, &vals);
     if (ok) {
         for (int i = 0; i < number_of_nonzeroes; ++i) expect[rows[i]] += vals[i] * vect[cols[i]];
         double worst = 0.0, scale = 0.0;
@@ -295,6 +387,11 @@ int driver_load_matrix(const driver_options *opt, host_matrix *m)
         return FileError;
     }
     fclose(file);
+    if (g_expand_symmetric &&
+        !expand_symmetric_entries(m->n_rows, m->n_cols, g_banner_symmetry, &m->nnz, &m->rows, &m->cols, &m->data)) {
+        printf("Could not expand the symmetric matrix.\n");
+        return FileError;
+    }
     for (int i = 0; i < m->n_cols; ++i) m->vect[i] = i; /* x = ramp, csr.c:95-99 */
     return Success;
 }

@@ -1,16 +1,17 @@
 /* mtx_parse -- loads a MatrixMarket file with the drivers' own reader (read_size_of_matrices_from_file
  * + read_entries) and dumps the triples as raw binary (int32 rows, int32 cols, float64 values) so
  * that tests can compare the fast parallel parse with the reference-style fscanf parse bit for bit.
- *   mtx_parse FILE.mtx OUT.bin   -> prints "rows cols nnz milliseconds" */
+ *   mtx_parse FILE.mtx OUT.bin [--expand-symmetric]   -> prints "rows cols nnz milliseconds" */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "helper_functions.h"
 
 int main(int argc, char **argv)
 {
-    if (argc != 3) {
-        fprintf(stderr, "usage: %s FILE.mtx OUT.bin\n", argv[0]);
+    if (argc != 3 && !(argc == 4 && !strcmp(argv[3], "--expand-symmetric"))) {
+        fprintf(stderr, "usage: %s FILE.mtx OUT.bin [--expand-symmetric]\n", argv[0]);
         return OtherError;
     }
     int n_rows, n_cols, nnz;
@@ -25,6 +26,8 @@ int main(int argc, char **argv)
     double *data = (double *)malloc(sizeof(double) * (size_t)nnz + 16);
     double t0 = now_ms();
     if (!read_entries(file, nnz, rows, cols, data)) return FileError;
+    if (argc == 4 && !expand_symmetric_entries(n_rows, n_cols, last_banner_symmetry(), &nnz, &rows, &cols, &data))
+        return FileError;
     double ms = now_ms() - t0;
     fclose(file);
     FILE *out = fopen(argv[2], "wb");

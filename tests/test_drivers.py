@@ -88,6 +88,55 @@ def test_fast_parallel_parse_equals_fscanf_parse(cant_dir, tmp_path):
         assert a.tobytes() == b.tobytes()
 
 
+def test_expand_symmetric_equals_the_full_matrix(tmp_path):
+    """--expand-symmetric (new, optional): the lower triangle of a file whose banner says `symmetric`,
+    mirrored and sorted by (row, column), must equal the row-sorted FULL matrix bit for bit (the
+    generator's values are symmetric by construction); skew-symmetric negates the mirrored entries;
+    a `general` banner is left untouched (the reference's reading, and the default without the flag)."""
+    import numpy as np
+    from conftest import gen_mtx_tool, write_mtx
+    bins = build_drivers()
+    g = ["--grid", "6", "5", "9", "--dof", "3", "--order", "row"]
+    lower, full = tmp_path / "lower.mtx", tmp_path / "full.mtx"
+    subprocess.run([str(gen_mtx_tool()), *g, "--tri", "lower", "--banner", "symmetric", "--out", str(lower)], check=True)
+    subprocess.run([str(gen_mtx_tool()), *g, "--tri", "full", "--out", str(full)], check=True)
+
+    def parse(path, *flags):
+        out = tmp_path / "p.bin"
+        p = subprocess.run([str(bins / "mtx_parse"), str(path), str(out), *flags], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        n_rows, n_cols, nnz = (int(t) for t in p.stdout.split()[:3])
+        raw = out.read_bytes()
+        return (n_rows, n_cols, np.frombuffer(raw, np.int32, nnz, 0), np.frombuffer(raw, np.int32, nnz, 4 * nnz),
+                np.frombuffer(raw, np.float64, nnz, 8 * nnz))
+
+    want = O.read_mtx(full)
+    got = parse(lower, "--expand-symmetric")
+    assert got[:2] == want[:2] and got[2].size == want[2].size > O.read_mtx(lower)[2].size
+    for a, b in zip(got[2:], want[2:]):
+        assert a.tobytes() == b.tobytes()
+    # without the flag: the lower triangle as stored (what the reference multiplies by)
+    asis = parse(lower)
+    for a, b in zip(asis[2:], O.read_mtx(lower)[2:]):
+        assert a.tobytes() == b.tobytes()
+    # general banner: the flag changes nothing
+    same = parse(full, "--expand-symmetric")
+    for a, b in zip(same[2:], want[2:]):
+        assert a.tobytes() == b.tobytes()
+    # skew-symmetric: mirrored entries negated, result sorted by (row, col)
+    rows = np.array([1, 2, 2, 3, 3], np.int32)
+    cols = np.array([0, 0, 1, 1, 2], np.int32)
+    vals = np.array([1.5, -2.0, 3.25, 4.0, -5.5])
+    skew = tmp_path / "skew.mtx"
+    write_mtx(skew, 4, 4, rows, cols, vals, banner="skew-symmetric")
+    _, _, r, c, v = parse(skew, "--expand-symmetric")
+    dense = np.zeros((4, 4))
+    dense[rows, cols] = vals
+    dense[cols, rows] = -vals
+    rr, cc = np.nonzero(dense)
+    assert np.array_equal(r, rr) and np.array_equal(c, cc) and np.array_equal(v, dense[rr, cc])
+
+
 TIMING = re.compile(r"^(Your calculations took|Number of operations \d+, PERFORMANCE|GBytes transferred)")
 
 
