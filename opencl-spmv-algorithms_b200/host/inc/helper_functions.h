@@ -36,6 +36,7 @@ typedef struct {
     int rowmajor;       /* --rowmajor (default) | --colmajor   (ell only) which ELL kernel/layout runs */
     int expand_symmetric; /* --expand-symmetric  mirror the off-diagonal entries of a symmetric file (default:
                              ignore the banner's symmetry, as the reference does) */
+    int cache;          /* --cache  keep "<matrix>.b200cache" (binary triples) next to the matrix */
 } driver_options;
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt);
@@ -54,6 +55,12 @@ void set_expand_symmetric(int enable);
 int last_banner_symmetry(void);
 bool expand_symmetric_entries(int number_of_rows, int number_of_columns, int symmetry, int *number_of_nonzeroes,
                               int **rows, int **cols, double **data);
+
+/* New, optional: binary cache of the parsed triples ("<file>.b200cache", validated against the source's
+ * size and mtime).  load_triples = header + entries of a file (malloc'ed arrays), through the cache
+ * when set_use_cache(1). */
+void set_use_cache(int enable);
+bool load_triples(const char *filename, int *n_rows, int *n_cols, int *nnz, int **rows, int **cols, double **data);
 
 void calculate_and_print_performance(double ms, int number_of_nonzeroes);
 void calculate_and_print_speed(double ms, int number_of_nonzeroes);

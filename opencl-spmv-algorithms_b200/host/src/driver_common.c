@@ -4,9 +4,12 @@
 
 #include <errno.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -14,6 +17,7 @@
 static int g_value_bytes = 8;
 static double g_rel_tolerance = 1e-12;
 static int g_expand_symmetric = 0;   /* --expand-symmetric */
+static int g_use_cache = 0;          /* --cache */
 static int g_banner_symmetry = 0;    /* of the last header read: 0 general, 1 symmetric/hermitian, -1 skew */
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt)
@@ -26,6 +30,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     opt->no_cpu = 0;
     opt->rowmajor = 1;
     opt->expand_symmetric = 0;
+    opt->cache = 0;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
         const char *v = i + 1 < argc ? argv[i + 1] : NULL;
@@ -42,16 +47,18 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
         else if (!strcmp(a, "--rowmajor")) opt->rowmajor = 1;
         else if (!strcmp(a, "--colmajor")) opt->rowmajor = 0;
         else if (!strcmp(a, "--expand-symmetric")) opt->expand_symmetric = 1;
+        else if (!strcmp(a, "--cache")) opt->cache = 1;
         else goto bad;
     }
     if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0) goto bad;
     set_value_bytes(opt->use_f32 ? 4 : 8);
     set_check_tolerance(opt->use_f32 ? 1e-5 : 1e-12);
     set_expand_symmetric(opt->expand_symmetric);
+    set_use_cache(opt->cache);
     return 0;
 bad:
     fprintf(stderr, "usage: %s [--matrix FILE.mtx] [--dtype f32|f64] [--sigma N] [--reps N] "
-                    "[--device D] [--no-cpu] [--rowmajor|--colmajor] [--expand-symmetric]\n", argv[0]);
+                    "[--device D] [--no-cpu] [--rowmajor|--colmajor] [--expand-symmetric] [--cache]\n", argv[0]);
     return 1;
 }
 
@@ -278,6 +285,148 @@ bool expand_symmetric_entries(int number_of_rows, int number_of_columns, int sym
     return ok;
 }
 
+/* ---- optional binary cache of the parsed triples (new) ---------------------------------------
+ * The reference parses its 60-90 MB text file three to four times per run (the builder's one or two
+ * passes plus one per check_result, inc/helper_functions.h:209-219).  With --cache the first load
+ * writes "<file>.b200cache" next to the matrix -- a 64-byte header (magic, version, source size and
+ * mtime, dimensions, banner symmetry) followed by the raw rows / cols / data arrays as parsed, i.e.
+ * BEFORE any symmetric expansion -- and every later load of an unchanged file is one fread.  A cache
+ * that does not match the source (size, mtime, version) is ignored and rewritten. */
+void set_use_cache(int enable) { g_use_cache = enable; }
+
+typedef struct {
+    char magic[8]; /* "B200MTX\0" */
+    uint32_t version, symmetry_plus_one;
+    int64_t source_size, source_mtime_ns;
+    int32_t n_rows, n_cols, nnz, pad;
+    char reserved[16];
+} cache_header;
+
+static bool cache_identity(const char *filename, int64_t *size, int64_t *mtime_ns)
+{
+    struct stat st;
+    if (stat(filename, &st) != 0) return false;
+    *size = (int64_t)st.st_size;
+    *mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + (int64_t)st.st_mtim.tv_nsec;
+    return true;
+}
+
+static char *cache_path(const char *filename)
+{
+    const size_t n = strlen(filename);
+    char *p = (char *)malloc(n + 16);
+    if (p) snprintf(p, n + 16, "%s.b200cache", filename);
+    return p;
+}
+
+/* true = arrays (malloc'ed here) and sizes come from a valid cache */
+static bool cache_load(const char *filename, int *n_rows, int *n_cols, int *nnz, int **rows, int **cols, double **data)
+{
+    int64_t size, mtime;
+    char *path = cache_path(filename);
+    if (!path || !cache_identity(filename, &size, &mtime)) {
+        free(path);
+        return false;
+    }
+    FILE *f = fopen(path, "rb");
+    free(path);
+    if (!f) return false;
+    cache_header h;
+    bool ok = fread(&h, sizeof h, 1, f) == 1 && !memcmp(h.magic, "B200MTX", 8) && h.version == 1 &&
+              h.source_size == size && h.source_mtime_ns == mtime && h.nnz >= 0 && h.n_rows >= 0 && h.n_cols >= 0;
+    int *r = NULL, *c = NULL;
+    double *v = NULL;
+    if (ok) {
+        const size_t n = (size_t)h.nnz;
+        r = (int *)malloc(sizeof(int) * n + 16);
+        c = (int *)malloc(sizeof(int) * n + 16);
+        v = (double *)malloc(sizeof(double) * n + 16);
+        ok = r && c && v && fread(r, sizeof(int), n, f) == n && fread(c, sizeof(int), n, f) == n &&
+             fread(v, sizeof(double), n, f) == n;
+    }
+    fclose(f);
+    if (!ok) {
+        free(r);
+        free(c);
+        free(v);
+        return false;
+    }
+    *n_rows = h.n_rows;
+    *n_cols = h.n_cols;
+    *nnz = h.nnz;
+    *rows = r;
+    *cols = c;
+    *data = v;
+    g_banner_symmetry = (int)h.symmetry_plus_one - 1;
+    return true;
+}
+
+static void cache_store(const char *filename, int n_rows, int n_cols, int nnz, const int *rows, const int *cols,
+                        const double *data)
+{
+    int64_t size, mtime;
+    char *path = cache_path(filename);
+    if (!path || !cache_identity(filename, &size, &mtime)) {
+        free(path);
+        return;
+    }
+    const size_t len = strlen(path);
+    char *tmp = (char *)malloc(len + 32);
+    if (tmp) {
+        snprintf(tmp, len + 32, "%s.tmp%ld", path, (long)getpid());
+        FILE *f = fopen(tmp, "wb");
+        if (f) {
+            cache_header h;
+            memset(&h, 0, sizeof h);
+            memcpy(h.magic, "B200MTX", 8);
+            h.version = 1;
+            h.symmetry_plus_one = (uint32_t)(g_banner_symmetry + 1);
+            h.source_size = size;
+            h.source_mtime_ns = mtime;
+            h.n_rows = n_rows;
+            h.n_cols = n_cols;
+            h.nnz = nnz;
+            const size_t n = (size_t)nnz;
+            const bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(rows, sizeof(int), n, f) == n &&
+                            fwrite(cols, sizeof(int), n, f) == n && fwrite(data, sizeof(double), n, f) == n;
+            if (fclose(f) != 0 || !ok || rename(tmp, path) != 0) remove(tmp); /* best effort */
+        }
+        free(tmp);
+    }
+    free(path);
+}
+
+/* header + entries of `filename` as the drivers parse them (1-based -> 0-based, file order), through
+ * the cache when enabled; arrays are malloc'ed here (+16 spare bytes) */
+bool load_triples(const char *filename, int *n_rows, int *n_cols, int *nnz, int **rows, int **cols, double **data)
+{
+    if (g_use_cache && cache_load(filename, n_rows, n_cols, nnz, rows, cols, data)) return true;
+    FILE *file = fopen(filename, "r");
+    if (file == NULL) {
+        perror(filename);
+        return false;
+    }
+    if (!read_size_of_matrices_from_file(file, n_rows, n_cols, nnz)) {
+        fclose(file);
+        return false;
+    }
+    *rows = (int *)malloc(sizeof(int) * (size_t)*nnz + 16);
+    *cols = (int *)malloc(sizeof(int) * (size_t)*nnz + 16);
+    *data = (double *)malloc(sizeof(double) * (size_t)*nnz + 16);
+    const bool ok = *rows && *cols && *data && read_entries(file, *nnz, *rows, *cols, *data);
+    fclose(file);
+    if (!ok) {
+        free(*rows);
+        free(*cols);
+        free(*data);
+        *rows = *cols = NULL;
+        *data = NULL;
+        return false;
+    }
+    if (g_use_cache) cache_store(filename, *n_rows, *n_cols, *nnz, *rows, *cols, *data);
+    return true;
+}
+
 void set_value_bytes(int bytes) { g_value_bytes = bytes; }
 void set_check_tolerance(double relative_max_norm) { g_rel_tolerance = relative_max_norm; }
 
@@ -299,21 +448,31 @@ void calculate_and_print_speed(double ms, int number_of_nonzeroes)
 bool check_result(const char *filename, double *vect, double *result)
 {
     int number_of_rows, number_of_columns, number_of_nonzeroes;
-    FILE *file = fopen(filename, "r");
-    if (file == NULL) {
-        perror(filename);
-        return false;
-    }
-    if (!read_size_of_matrices_from_file(file, &number_of_rows, &number_of_columns, &number_of_nonzeroes)) {
+    int *rows = NULL, *cols = NULL;
+    double *vals = NULL, *expect = NULL;
+    bool ok;
+    if (g_use_cache) { /* --cache: the triples come from the binary cache written by the first load */
+        ok = load_triples(filename, &number_of_rows, &number_of_columns, &number_of_nonzeroes, &rows, &cols, &vals);
+        if (!ok) return false;
+        expect = (double *)calloc((size_t)number_of_rows, sizeof(double));
+        ok = expect != NULL;
+    } else {
+        FILE *file = fopen(filename, "r");
+        if (file == NULL) {
+            perror(filename);
+            return false;
+        }
+        if (!read_size_of_matrices_from_file(file, &number_of_rows, &number_of_columns, &number_of_nonzeroes)) {
+            fclose(file);
+            return false;
+        }
+        rows = (int *)malloc(sizeof(int) * (size_t)number_of_nonzeroes);
+        cols = (int *)malloc(sizeof(int) * (size_t)number_of_nonzeroes);
+        vals = (double *)malloc(sizeof(double) * (size_t)number_of_nonzeroes);
+        expect = (double *)calloc((size_t)number_of_rows, sizeof(double));
+        ok = rows && cols && vals && expect && read_entries(file, number_of_nonzeroes, rows, cols, vals);
         fclose(file);
-        return false;
     }
-    int *rows = (int *)malloc(sizeof(int) * (size_t)number_of_nonzeroes);
-    int *cols = (int *)malloc(sizeof(int) * (size_t)number_of_nonzeroes);
-    double *vals = (double *)malloc(sizeof(double) * (size_t)number_of_nonzeroes);
-    double *expect = (double *)calloc((size_t)number_of_rows, sizeof(double));
-    bool ok = rows && cols && vals && expect && read_entries(file, number_of_nonzeroes, rows, cols, vals);
-    fclose(file);
     if (ok && g_expand_symmetric)
         ok = expand_symmetric_entries(number_of_rows, number_of_columns, g_banner_symmetry, &number_of_nonzeroes,
                                       &rows, &cols, &vals);
@@ -368,25 +527,31 @@ int driver_load_matrix(const driver_options *opt, host_matrix *m)
     if (number_of_devices > DEVICES_DEFAULT_SIZE) number_of_devices = DEVICES_DEFAULT_SIZE;
     if (opt->device >= number_of_devices) return OpenCLDeviceError;
 
-    FILE *file = fopen(opt->matrix, "r");
-    if (file == NULL) {
-        perror(opt->matrix);
-        return FileError;
-    }
-    if (read_size_of_matrices_from_file(file, &m->n_rows, &m->n_cols, &m->nnz) == false) {
+    if (g_use_cache) { /* --cache */
+        if (!load_triples(opt->matrix, &m->n_rows, &m->n_cols, &m->nnz, &m->rows, &m->cols, &m->data)) return FileError;
+        m->vect = (double *)malloc((size_t)m->n_cols * sizeof(double) + 16);
+        if (!m->vect) return FileError;
+    } else {
+        FILE *file = fopen(opt->matrix, "r");
+        if (file == NULL) {
+            perror(opt->matrix);
+            return FileError;
+        }
+        if (read_size_of_matrices_from_file(file, &m->n_rows, &m->n_cols, &m->nnz) == false) {
+            fclose(file);
+            return FileError;
+        }
+        m->rows = (int *)malloc((size_t)m->nnz * sizeof(int) + 16);
+        m->cols = (int *)malloc((size_t)m->nnz * sizeof(int) + 16);
+        m->data = (double *)malloc((size_t)m->nnz * sizeof(double) + 16);
+        m->vect = (double *)malloc((size_t)m->n_cols * sizeof(double) + 16);
+        if (!m->rows || !m->cols || !m->data || !m->vect ||
+            !read_entries(file, m->nnz, m->rows, m->cols, m->data)) {
+            fclose(file);
+            return FileError;
+        }
         fclose(file);
-        return FileError;
     }
-    m->rows = (int *)malloc((size_t)m->nnz * sizeof(int) + 16);
-    m->cols = (int *)malloc((size_t)m->nnz * sizeof(int) + 16);
-    m->data = (double *)malloc((size_t)m->nnz * sizeof(double) + 16);
-    m->vect = (double *)malloc((size_t)m->n_cols * sizeof(double) + 16);
-    if (!m->rows || !m->cols || !m->data || !m->vect ||
-        !read_entries(file, m->nnz, m->rows, m->cols, m->data)) {
-        fclose(file);
-        return FileError;
-    }
-    fclose(file);
     if (g_expand_symmetric &&
         !expand_symmetric_entries(m->n_rows, m->n_cols, g_banner_symmetry, &m->nnz, &m->rows, &m->cols, &m->data)) {
         printf("Could not expand the symmetric matrix.\n");

@@ -137,6 +137,47 @@ def test_expand_symmetric_equals_the_full_matrix(tmp_path):
     assert np.array_equal(r, rr) and np.array_equal(c, cc) and np.array_equal(v, dense[rr, cc])
 
 
+def test_binary_cache_of_parsed_triples(tmp_path):
+    """--cache (new, optional): the first load writes <file>.b200cache, later loads of an unchanged file
+    read it and give the same bytes; a changed source (size or mtime) invalidates it; the cached
+    triples are the ones BEFORE symmetric expansion, so both options compose."""
+    import numpy as np
+    from conftest import gen_mtx_tool
+    bins = build_drivers()
+    src = tmp_path / "m.mtx"
+    g = ["--grid", "6", "5", "9", "--dof", "3", "--order", "row", "--tri", "lower", "--banner", "symmetric"]
+    subprocess.run([str(gen_mtx_tool()), *g, "--out", str(src)], check=True)
+
+    def parse(*flags):
+        out = tmp_path / "p.bin"
+        p = subprocess.run([str(bins / "mtx_parse"), str(src), str(out), *flags], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        return p.stdout.split()[:3], out.read_bytes()
+
+    plain = parse()
+    cache = tmp_path / "m.mtx.b200cache"
+    assert not cache.exists()                                  # nothing is written without the flag
+    first = parse("--cache")
+    assert cache.exists() and first == plain
+    stamp = cache.stat().st_mtime_ns
+    again = parse("--cache")
+    assert again == plain and cache.stat().st_mtime_ns == stamp   # served from the cache, not rewritten
+    assert parse("--cache", "--expand-symmetric") == parse("--expand-symmetric")
+    # a corrupted cache body with a valid header would go unnoticed -- the header is the contract -- but a
+    # changed SOURCE must invalidate: append a comment-free duplicate entry and fix the size line
+    lines = src.read_text().splitlines()
+    n_rows, n_cols, nnz = (int(t) for t in lines[2].split())
+    lines[2] = f"{n_rows} {n_cols} {nnz + 1}"
+    lines.append(lines[-1])
+    src.write_text("\n".join(lines) + "\n")
+    changed = parse("--cache")
+    assert int(changed[0][2]) == nnz + 1 and changed == parse()
+    assert parse("--cache") == changed
+    # garbage in place of the cache is ignored and replaced
+    cache.write_bytes(b"not a cache")
+    assert parse("--cache") == changed and cache.stat().st_size > 64
+
+
 TIMING = re.compile(r"^(Your calculations took|Number of operations \d+, PERFORMANCE|GBytes transferred)")
 
 
