@@ -3,13 +3,16 @@
 // Replaces kernels/Csr.cl:1-17 (scalar thread-per-row, 32 work-groups) and kernels/Ell.cl:1-39
 // (16-lane work-group per row with a local-memory tree).  B200 design:
 //   * LPR (2..32) lanes cooperate on one row; LPR is picked from the row-length statistics so
-//     that a row is covered by about one 128-bit load per lane (vector / warp-per-row family);
+//     that a lane walks ~4 groups of four entries (measured: the x gather's L1 wavefronts, not the
+//     matrix stream, are the limit, so a warp should cover ADJACENT rows);
 //   * indices and values are fetched as 128-bit loads on 16-byte ADDRESS-aligned groups of four
 //     entries; the ragged first/last group of a row is masked, never re-read;
-//   * matrix data streams with evict-first, x goes through the read-only path;
+//   * U groups per lane are loaded before any x is gathered (explicit batches, batch_hold());
+//   * matrix data streams with evict-first, x goes through the read-only path (coherent loads in
+//     the launch-overlap variants, OVL = true);
 //   * rows far longer than the mean (power-law inputs) are skipped by the vector kernel and
 //     handled by a block-per-row kernel that splits very long rows across blocks (one atomic
-//     per block);
+//     per block); short-row matrices take the nnz-split stream kernel instead;
 //   * reduction is __shfl_xor_sync only -- no shared memory, no barriers.
 // HBM-bound: algorithmic bytes = nnz*(4+V) + (R+1)*4 + Cn*V + R*V.
 #include <stdlib.h>

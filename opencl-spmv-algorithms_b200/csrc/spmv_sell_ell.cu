@@ -8,6 +8,11 @@
 // quarter of the columns; two __shfl_xor_sync steps (8, 16) fold the quarters and lanes 0-7
 // store the 32 results as 128-bit writes (or scatter through the sigma permutation).
 //
+// Variants in this file: 1-8 warps per chunk for matrices with few chunks (WPC), an opt-in kernel
+// that stages the chunks through shared memory with the TMA engine (sell32_tma_kernel), and the
+// fused SpMV + exchange kernel of the multi-GPU power iteration (sell32_bcast_kernel: halo-limited
+// peer stores; ring_sync_kernel: collective-free hand-over of the norm).
+//
 // Column-major ELL is the same idea with one "chunk" spanning the whole matrix: thread t owns rows
 // 4t..4t+3 and walks the K columns (optionally split over KS thread-slices when the matrix has
 // too few rows to fill 148 SMs).  Bytes: P*(4+V) + (S+1)*P_bytes [+R*4 perm] + Cn*V + R*V for
