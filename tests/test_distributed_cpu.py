@@ -131,6 +131,100 @@ def test_power_iteration_world2_matches_single_process(tmp_path):
     assert float(np.load(tmp_path / "shard_err.npy")[0]) <= 1e-12
 
 
+def _halo_worker(rank, world, port, case, steps, out_dir):
+    """Power iteration where every rank only ever RECEIVES the rows halo_rows says it reads: the rest
+    of its x buffer stays NaN.  If halo_rows under-estimated a halo, a NaN would enter the SpMV."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from __graft_entry__ import load_package
+        from oracle import binding as O
+        pkg = load_package()
+        O.lib().orc_set_threads(1)
+        n, rows, cols, vals, x0 = halo_case(case)
+        blocks = pkg.equal_row_blocks(n, world, align=32)
+        lo, hi = blocks.bounds(rank)
+        sel = (rows >= lo) & (rows < hi)
+        ptr, _ = O.build_csr(hi - lo, rows[sel] - lo)
+        mine = (int(cols[sel].min()), int(cols[sel].max()))         # what b200_minmax_i32 returns on the GPU
+        ranges = [None] * world
+        dist.all_gather_object(ranges, mine)
+        send_lo, send_hi = pkg.halo_rows(ranges, blocks, rank)
+        recv = [pkg.halo_rows(ranges, blocks, d) for d in range(world)]   # what the others send to me
+        x = np.full(blocks.padded, np.nan)
+        need_lo, need_hi = min(mine[0], lo), max(mine[1] + 1, hi)
+        x[need_lo:need_hi] = x0[need_lo:need_hi]                    # own block + halo only
+        norm = None
+        for _ in range(steps):
+            y = O.spmv_csr(hi - lo, ptr, cols[sel], vals[sel], np.where(np.isnan(x), np.nan, x))
+            assert not np.isnan(y).any(), "the SpMV read a row nobody sent: halo too small"
+            acc = torch.tensor([float((y ** 2).sum())], dtype=torch.float64)
+            dist.all_reduce(acc)
+            norm = float(acc[0]) ** 0.5
+            y = y / norm
+            nxt = np.full(blocks.padded, np.nan)
+            nxt[lo:hi] = y
+            reqs = []
+            for d in range(world):                                   # the kernel's peer stores
+                if d != rank and send_hi[d] > send_lo[d]:
+                    reqs.append(dist.isend(torch.from_numpy(y[send_lo[d]:send_hi[d]].copy()), d))
+            for d in range(world):
+                r_lo, r_hi = recv[d][0][rank], recv[d][1][rank]
+                if d != rank and r_hi > r_lo:
+                    buf = torch.empty(r_hi - r_lo, dtype=torch.float64)
+                    dist.recv(buf, d)
+                    d_lo = blocks.bounds(d)[0]
+                    nxt[d_lo + r_lo:d_lo + r_hi] = buf.numpy()
+            for q in reqs:
+                q.wait()
+            x = nxt
+        np.save(Path(out_dir) / f"halo_{case}_{rank}.npy", np.concatenate([[norm, lo, hi], x[lo:hi]]))
+    finally:
+        dist.destroy_process_group()
+
+
+def halo_case(case):
+    if case == "laplace":
+        n, rows, cols, vals = laplace7(10, 8, 16)
+    else:   # irregular band: every row reaches a different distance to the left and to the right
+        rng = np.random.default_rng(33)
+        n = 1500
+        left, right = rng.integers(0, 140, n), rng.integers(0, 90, n)
+        rr, cc = [], []
+        for i in range(n):
+            c = np.unique(np.clip(np.concatenate([[i], i - rng.integers(0, left[i] + 1, 4),
+                                                  i + rng.integers(0, right[i] + 1, 4)]), 0, n - 1))
+            rr.append(np.full(c.size, i))
+            cc.append(c)
+        rows, cols = np.concatenate(rr).astype(np.int32), np.concatenate(cc).astype(np.int32)
+        vals = rng.uniform(0.1, 1.0, rows.size)
+    x0 = np.random.default_rng(2).uniform(0.0, 1.0, n)
+    return n, rows, cols, vals, x0
+
+
+@pytest.mark.parametrize("case", ["laplace", "irregular"])
+def test_halo_limited_exchange_world2(tmp_path, case):
+    """World size 2 over gloo: the halo-limited exchange (each rank receives only the rows halo_rows
+    assigns to it, everything else in its x buffer is NaN) reproduces the single-process power
+    iteration on a stencil and on an irregular band."""
+    from oracle import binding as O
+    steps, world = 12, 2
+    n, rows, cols, vals, x0 = halo_case(case)
+    ptr, _ = O.build_csr(n, rows)
+    x = x0.copy()
+    for _ in range(steps):
+        y = O.spmv_csr(n, ptr, cols, vals, x)
+        nrm = np.linalg.norm(y)
+        x = y / nrm
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_halo_worker, args=(world, port, case, steps, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"halo_{case}_{r}.npy")
+        norm, lo, hi = got[0], int(got[1]), int(got[2])
+        assert abs(norm - nrm) <= 1e-12 * nrm
+        assert np.max(np.abs(got[3:] - x[lo:hi])) <= 1e-12
+
+
 def test_equal_row_blocks():
     from __graft_entry__ import load_package
     pkg = load_package()
