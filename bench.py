@@ -206,6 +206,16 @@ class quiet_stdout:
         os.close(self.saved)
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_arm(n_rows, n_cols, rows, cols, vals, x, dtype, kind, reps, warm):
     """Time one SpMV per format on the host cores; returns (seconds per five-format pass, details).
     kind='port': oracle/liboracle.so (-O3, OpenMP) in `dtype`.
@@ -690,7 +700,8 @@ def main():
             sample = "the whole cant-shaped matrix, five formats, best of 5"
         sec, detail, threads, kind, cdt = cpu_arm(sr, n_cols, rows_h, cols_h, vals_h, x_h, dtype, "port", 5, 2)
         cpu = {"value": round(2.0 * len(rows_h) * len(FORMATS) / sec * 1e-9, 3), "unit": "GFLOP/s",
-               "cores": threads, "kind": kind, "dtype": cdt, "sample": sample, "per_format_gflops": detail}
+               "cores": threads, "cpu_model": cpu_model(), "omp_wait_policy": os.environ.get("OMP_WAIT_POLICY"),
+               "kind": kind, "dtype": cdt, "sample": sample, "per_format_gflops": detail}
 
     if rank == 0:
         out = {
@@ -1092,7 +1103,8 @@ def reference_arm(pkg, args, dtype):
         "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": cdt, "data": "synthetic",
         "config": {"workload": workload, "formats": list(FORMATS)},
-        "cpu_baseline": {"value": round(value, 3), "unit": "GFLOP/s", "cores": threads, "kind": kind,
+        "cpu_baseline": {"value": round(value, 3), "unit": "GFLOP/s", "cores": threads, "cpu_model": cpu_model(),
+                         "omp_wait_policy": os.environ.get("OMP_WAIT_POLICY"), "kind": kind,
                          "sample": sample, "per_format_gflops": detail,
                          "as_shipped_no_O_flag": getattr(cpu_arm, "as_shipped", None),
                          "wall_s": round(time.perf_counter() - t0, 2)},
