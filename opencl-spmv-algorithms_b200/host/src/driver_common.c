@@ -229,7 +229,11 @@ bool expand_symmetric_entries(int number_of_rows, int number_of_columns, int sym
     if (symmetry == 0) return true;
     const int nnz = *number_of_nonzeroes;
     long long extra = 0;
-    for (int i = 0; i < nnz; ++i) extra += (*rows)[i] != (*cols)[i];
+    for (int i = 0; i < nnz; ++i) {
+        const int r = (*rows)[i], c = (*cols)[i];
+        if (r < 0 || r >= number_of_rows || c < 0 || c >= number_of_columns) return false; /* not a valid entry */
+        extra += r != c;
+    }
     const long long total = (long long)nnz + extra;
     if (total > 0x7fffffffll || number_of_rows != number_of_columns) return false;
     const int n = (int)total;
