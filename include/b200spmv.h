@@ -79,8 +79,21 @@ int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes);
  * the in-order semantics of the reference's queue (csr.c:115). */
 int b200_ctx_set_launch_overlap(b200_ctx *ctx, int enable);
 
+/* Tuning hooks (new).  Every kernel-selection heuristic can be overridden per context: `name` is one
+ * of the B200_* hooks listed in DESIGN.md section 4 ("B200_CSR_LANES", "B200_SELL_WPC", ...), `value`
+ * its decimal value, NULL or "" = back to automatic.  The environment variables of the same names are
+ * read exactly once, by b200_ctx_create; launches never call getenv.  Unknown name ->
+ * B200_ERR_INVALID_VALUE. */
+int b200_ctx_set_option(b200_ctx *ctx, const char *name, const char *value);
+
 /* ---- buffers: clCreateBuffer (csr.c:123-127), clReleaseMemObject (csr.c:260-263),
  *      clEnqueueWriteBuffer (csr.c:183-186), clEnqueueReadBuffer (csr.c:220), clFinish ---- */
+/* b200_malloc over-allocates by B200_MALLOC_PAD bytes: the kernels fetch indices and values as
+ * 16-byte-ALIGNED groups of four entries, so the last group of an array can reach up to 24 bytes
+ * past its end (fp64 values, nnz % 4 == 1).  Matrix arrays that do not come from b200_malloc (a torch
+ * tensor, a cudaMalloc of the exact size) must carry B200_MALLOC_PAD readable bytes after their last
+ * entry as well; vectors (vect / output) need none. */
+#define B200_MALLOC_PAD 32
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);
 int b200_free(b200_ctx *ctx, void *dptr);
 int b200_memcpy_h2d_async(b200_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
@@ -329,7 +342,9 @@ int b200_partition_rows(const int *ptr_host, int n_rows, int n_parts, int align,
  * The same kernel accumulates ||y||^2 of its rows into the B200_SUMSQ_SLOTS partial sums of
  * sumsq_out (device, zeroed by the caller; NULL = skip), one atomic per block.  SELL-32, reference
  * chunk pointers, no permutation.  The caller orders steps with one small all-reduce of those
- * slots (which it needs anyway for the norm): no other launch is needed per step. */
+ * slots (which it needs anyway for the norm): no other launch is needed per step.
+ * Alignment: every dst[i] must be 16-byte aligned and dst_offset even (row pairs travel as one
+ * 16-byte store); anything else is rejected with B200_ERR_INVALID_VALUE. */
 #define B200_SUMSQ_SLOTS 32
 int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                              const int *row_indices, int chunk, int n_slices, int n_rows,

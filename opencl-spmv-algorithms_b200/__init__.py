@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200_ctx_destroy": (_i, [_vp]),
     "b200_ctx_device": (_i, [_vp, C.POINTER(_i)]),
     "b200_ctx_set_l2_persist": (_i, [_vp, _vp, _sz]),
+    "b200_ctx_set_option": (_i, [_vp, C.c_char_p, C.c_char_p]),
     "b200_malloc": (_i, [_vp, _sz, _vpp]),
     "b200_free": (_i, [_vp, _vp]),
     "b200_memcpy_h2d_async": (_i, [_vp, _vp, _vp, _sz]),
@@ -249,6 +250,19 @@ class Context:
                   "b200_ctx_create_on_stream")
         self.h = h
         self.device = device
+        self._options = set()
+
+    def set_option(self, name: str, value) -> None:
+        """b200_ctx_set_option: override a tuning hook ("B200_CSR_LANES", ...) on this context;
+        value None = back to automatic.  (The environment variables of the same names are read once,
+        when the context is created.)"""
+        check(lib().b200_ctx_set_option(self.h, name.encode(), None if value is None else str(value).encode()),
+              "b200_ctx_set_option")
+        (self._options.discard if value is None else self._options.add)(name)
+
+    def clear_options(self) -> None:
+        for name in list(self._options):
+            self.set_option(name, None)
 
     def empty(self, n, dtype) -> DeviceArray:
         return DeviceArray(self, n, dtype)

@@ -4,8 +4,8 @@
 // csr.c:72-91, ell.c:68-164, sigma_c.c:71-202, cmrs.c:72-117 (COO is the triples themselves,
 // coo.c:75-84).  Here the drivers parse the file once, upload the row-sorted triples and build on
 // the device.  Integer arrays are identical to the reference's on its well-defined domain (rows
-// sorted, none empty, first row 0); tests/test_gpu_builders.py checks that bit for bit against the
-// oracle and against the recorded reference uploads.  The sigma-window sort + permutation of
+// sorted, none empty, first row 0); tests/test_gpu_parity.py (against the oracle) and
+// tests/test_golden.py (against the recorded reference uploads) check that bit for bit.  The sigma-window sort + permutation of
 // SELL-C-sigma is new (the reference has none).
 #include "common.cuh"
 

@@ -2,9 +2,12 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/b200spmv.h"
 
@@ -12,8 +15,21 @@
 #error "libb200spmv is written for sm_100a (B200) only"
 #endif
 
+// Tuning hooks.  Every hook has an environment variable of the same name; the environment is read
+// ONCE, in b200_ctx_create, into ctx->opt[] (no getenv in front of a 10 us launch), and
+// b200_ctx_set_option changes a hook on a live context.  kOptUnset = the library decides.
+enum b200_opt {
+    OPT_CSR_LANES, OPT_ELL_LANES, OPT_CSR_UNROLL, OPT_ELL_UNROLL, OPT_CSR_STREAM, OPT_SELL_WPC,
+    OPT_SELL_UNROLL, OPT_SELL_TMA, OPT_SELL_TMA_BLOCKS, OPT_SELL_TMA_SUSPEND_NS, OPT_COO_U, OPT_CMRS_U,
+    OPT_CMRS_WPS, OPT_CMRS_STREAM, OPT_ELLCM_Q, OPT_RING_FLUSH, OPT_RING_POLL, OPT_RING_SLEEP_NS,
+    OPT_BCAST_U, OPT_CSR_STREAM_G, OPT_COUNT
+};
+constexpr int kOptUnset = INT_MIN;
+extern const char *const b200_opt_names[OPT_COUNT];
+
 struct b200_ctx {
     int device;
+    int opt[OPT_COUNT];    // tuning hooks (kOptUnset = automatic)
     cudaStream_t stream;
     bool owns_stream;
     int sm_count;
@@ -22,6 +38,7 @@ struct b200_ctx {
     int *scratch;          // small device scratch (flags / counters), 4 KiB
     void *host_scratch;    // pinned, 4 KiB, for small readbacks
     bool watch_flag;       // a bulk-copy kernel ran since the last sync: b200_sync reads kWatchFlag
+    bool watch_saved;      // watch_flag as it was when b200_graph_begin started recording
     bool overlap;          // b200_ctx_set_launch_overlap: SpMV kernels are launched as programmatic
                            // dependents (they stream their matrix arrays while earlier work drains)
 };
@@ -68,6 +85,21 @@ static inline int b200_ctx_enter(const b200_ctx *ctx)
         int rc__ = b200_ctx_enter(ctx);          \
         if (rc__) return rc__;                   \
     } while (0)
+
+// value of a tuning hook, or `dflt` when it is unset
+static inline int opt_or(const b200_ctx *ctx, b200_opt o, int dflt)
+{
+    return ctx->opt[o] == kOptUnset ? dflt : ctx->opt[o];
+}
+static inline bool opt_set(const b200_ctx *ctx, b200_opt o) { return ctx->opt[o] != kOptUnset; }
+
+// NVTX range around a C-ABI call (build / H2D / spmv / exchange show up as named
+// ranges in Nsight Systems; without a tool attached a push/pop is one predicted branch each)
+struct b200_nvtx_scope {
+    explicit b200_nvtx_scope(const char *name) { nvtxRangePushA(name); }
+    ~b200_nvtx_scope() { nvtxRangePop(); }
+};
+#define B200_TRACE(name) b200_nvtx_scope nvtx_scope__(name)
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

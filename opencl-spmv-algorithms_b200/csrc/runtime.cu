@@ -1,9 +1,19 @@
 // runtime.cu -- contexts, buffers, events, errors: the C-ABI replacement of the OpenCL runtime
 // calls the reference drivers make (include/b200spmv.h cites each one).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
+
+// one name per b200_opt, in enum order: the environment variable read at b200_ctx_create and the
+// name b200_ctx_set_option takes
+const char *const b200_opt_names[OPT_COUNT] = {
+    "B200_CSR_LANES", "B200_ELL_LANES", "B200_CSR_UNROLL", "B200_ELL_UNROLL", "B200_CSR_STREAM", "B200_SELL_WPC",
+    "B200_SELL_UNROLL", "B200_SELL_TMA", "B200_SELL_TMA_BLOCKS", "B200_SELL_TMA_SUSPEND_NS", "B200_COO_U", "B200_CMRS_U",
+    "B200_CMRS_WPS", "B200_CMRS_STREAM", "B200_ELLCM_Q", "B200_RING_FLUSH", "B200_RING_POLL", "B200_RING_SLEEP_NS",
+    "B200_BCAST_U", "B200_CSR_STREAM_G",
+};
 
 static thread_local char g_last_error[512] = "";
 
@@ -102,7 +112,12 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool own, b200_ctx *
     c->scratch = nullptr;
     c->host_scratch = nullptr;
     c->watch_flag = false;
+    c->watch_saved = false;
     c->overlap = false;
+    for (int o = 0; o < OPT_COUNT; ++o) {  // the only getenv calls of the library
+        const char *e = getenv(b200_opt_names[o]);
+        c->opt[o] = (e && *e) ? atoi(e) : kOptUnset;
+    }
     if (own) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -178,6 +193,19 @@ int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes)
     return B200_SUCCESS;
 }
 
+int b200_ctx_set_option(b200_ctx *ctx, const char *name, const char *value)
+{
+    B200_REQUIRE(ctx && name, "null argument");
+    for (int o = 0; o < OPT_COUNT; ++o) {
+        if (strcmp(name, b200_opt_names[o]) == 0) {
+            ctx->opt[o] = (value && *value) ? atoi(value) : kOptUnset;
+            return B200_SUCCESS;
+        }
+    }
+    b200_set_error("b200_ctx_set_option: unknown tuning hook '%s'", name);
+    return B200_ERR_INVALID_VALUE;
+}
+
 static int check_watch_flag(b200_ctx *ctx);
 
 int b200_ctx_set_launch_overlap(b200_ctx *ctx, int enable)
@@ -192,8 +220,9 @@ int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
     B200_ENTER(ctx);
     B200_REQUIRE(dptr, "null dptr");
     *dptr = nullptr;
-    // 16 spare bytes: the vector kernels read whole aligned 16-byte groups
-    B200_CUDA(cudaMalloc(dptr, (bytes ? bytes : 1) + 16));
+    // B200_MALLOC_PAD spare bytes: the vector kernels read whole 16-byte-aligned groups of four entries
+    // (32 bytes for fp64 values), so the last group of an array may reach up to 24 bytes past its end
+    B200_CUDA(cudaMalloc(dptr, (bytes ? bytes : 1) + B200_MALLOC_PAD));
     return B200_SUCCESS;
 }
 
@@ -206,6 +235,7 @@ int b200_free(b200_ctx *ctx, void *dptr)
 
 int b200_memcpy_h2d_async(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
+    B200_TRACE("b200 H2D");
     B200_ENTER(ctx);
     if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return B200_SUCCESS;
@@ -213,6 +243,7 @@ int b200_memcpy_h2d_async(b200_ctx *ctx, void *dst, const void *src, size_t byte
 
 int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
+    B200_TRACE("b200 D2H");
     B200_ENTER(ctx);
     if (bytes) B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -317,12 +348,16 @@ struct b200_graph {
     int device;
     cudaGraph_t graph;
     cudaGraphExec_t exec;
+    bool watched;  // a kernel that can raise kWatchFlag (TMA wait, ring flag wait) was recorded
 };
 
 int b200_graph_begin(b200_ctx *ctx)
 {
     B200_ENTER(ctx);
     B200_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    // launches recorded from here on set watch_flag without having run: keep the live state aside
+    ctx->watch_saved = ctx->watch_flag;
+    ctx->watch_flag = false;
     return B200_SUCCESS;
 }
 
@@ -332,6 +367,8 @@ int b200_graph_end(b200_ctx *ctx, b200_graph **graph)
     B200_REQUIRE(graph, "null graph out");
     *graph = nullptr;
     cudaGraph_t g = nullptr;
+    const bool watched = ctx->watch_flag;
+    ctx->watch_flag = ctx->watch_saved;
     B200_CUDA(cudaStreamEndCapture(ctx->stream, &g));
     cudaGraphExec_t exec = nullptr;
     cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
@@ -343,6 +380,7 @@ int b200_graph_end(b200_ctx *ctx, b200_graph **graph)
     out->device = ctx->device;
     out->graph = g;
     out->exec = exec;
+    out->watched = watched;
     *graph = out;
     return B200_SUCCESS;
 }
@@ -352,6 +390,7 @@ int b200_graph_launch(b200_ctx *ctx, b200_graph *graph)
     B200_ENTER(ctx);
     B200_REQUIRE(graph && graph->device == ctx->device, "graph was recorded on another device");
     B200_CUDA(cudaGraphLaunch(graph->exec, ctx->stream));
+    if (graph->watched) ctx->watch_flag = true;  // every replay can time out, not only the recording
     return B200_SUCCESS;
 }
 

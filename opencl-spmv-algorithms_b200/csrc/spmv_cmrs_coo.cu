@@ -341,7 +341,7 @@ int spmv_cmrs_impl(b200_ctx *ctx, const T *data, const int *idx, const int *stri
     // (0.371 vs 0.444: 90 registers); launches of at most ~2 waves (cant): 1
     const bool small = (long long)n_strips * 32 <= 2ll * ctx->sm_count * 2048;
     int u = (sizeof(T) == 4 && !small) ? 2 : 1;
-    if (const char *e = getenv("B200_CMRS_U")) u = atoi(e) == 2 ? 2 : 1;
+    if (opt_set(ctx, OPT_CMRS_U)) u = ctx->opt[OPT_CMRS_U] == 2 ? 2 : 1;
 #define B200_CMRS_LAUNCH2(H, V, UU)                                                                         \
     do {                                                                                                    \
         B200_CUDA(ctx->overlap                                                                              \
@@ -392,7 +392,7 @@ int spmv_coo_impl(b200_ctx *ctx, const int *row, const int *col, const T *data, 
     // U = groups loaded per lane and round trip (tuning hook B200_COO_U=1|2|4).  Measured on B200
     // (profiles/r1e_variant_sweep.md): 2, except fp32 on launches of many waves (237 vs 246 us)
     int u = (sizeof(T) == 4 && (long long)blocks > 8ll * ctx->sm_count) ? 4 : 2;
-    if (const char *e = getenv("B200_COO_U")) u = atoi(e) == 4 ? 4 : (atoi(e) == 1 ? 1 : 2);
+    if (opt_set(ctx, OPT_COO_U)) u = ctx->opt[OPT_COO_U] == 4 ? 4 : (ctx->opt[OPT_COO_U] == 1 ? 1 : 2);
 #define B200_COO_LAUNCH(V, UU)                                                                            \
     B200_CUDA(ctx->overlap ? b200_launch(ctx, coo_kernel<T, V, UU, true>, dim3(blocks), dim3(kBlock), 0, row, col, data, x, y, nnz) \
                            : b200_launch(ctx, coo_kernel<T, V, UU, false>, dim3(blocks), dim3(kBlock), 0, row, col, data, x, y, nnz))

@@ -345,7 +345,7 @@ __global__ void csr_collect_long_kernel(const int *__restrict__ ptr, int n_rows,
     }
 }
 
-int pick_lanes(double mean_len, const char *override_env)
+int pick_lanes(const b200_ctx *ctx, double mean_len, b200_opt hook)
 {
     // Measured on B200 (profiles/r1_lanes_sweep.md): the kernel is bound by L1 wavefronts of the x
     // gather, not by the matrix loads.  Fewer lanes per row put more ADJACENT rows in one warp, and
@@ -356,10 +356,8 @@ int pick_lanes(double mean_len, const char *override_env)
     while (lanes < 32 && lanes * 16 < mean_len) lanes <<= 1;
     if (lanes == 2 && mean_len > 8.0) lanes = 4;
     // tuning hook: B200_CSR_LANES / B200_ELL_LANES = 2,4,8,16,32 overrides the heuristic
-    if (const char *e = getenv(override_env)) {
-        const int v = atoi(e);
-        if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
-    }
+    const int v = opt_or(ctx, hook, 0);
+    if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
     return lanes;
 }
 
@@ -369,16 +367,14 @@ int pick_lanes(double mean_len, const char *override_env)
 //   fp32: 4 (CSR 0.176 vs 0.179 ms, ELL 0.167 vs 0.172);  fp64: 2 (CSR 0.261 vs 0.266 at 1 and 0.326
 //   at 4 -- 96 registers; ELL 0.252 / 0.255 / 0.289).
 // Launches of at most ~2 waves (cant): CSR 2; ELL fp32 4, fp64 1.
-int pick_unroll(const b200_ctx *ctx, long long threads, int value_bytes, bool ell, const char *override_env)
+int pick_unroll(const b200_ctx *ctx, long long threads, int value_bytes, bool ell, b200_opt hook)
 {
     const bool small = threads <= 2ll * ctx->sm_count * 2048;
     int u;
     if (ell) u = value_bytes == 4 ? 4 : (small ? 1 : 2);
     else u = (value_bytes == 4 && !small) ? 4 : 2;
-    if (const char *e = getenv(override_env)) {
-        const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4) u = v;
-    }
+    const int v = opt_or(ctx, hook, 0);
+    if (v == 1 || v == 2 || v == 4) u = v;
     return u;
 }
 
@@ -393,21 +389,83 @@ struct b200_csr_plan {
     int *tile_lo;     // stream_tiles + 1 entries
     int *carry_row;   // stream_tiles entries
     void *carry_val;  // stream_tiles x 8 bytes (T = float or double)
+    cudaStream_t owner;  // a stream plan's carry buffers serve ONE queue: the one it was created on
 };
 
 extern "C" {
 
-int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_plan **plan)
+// fills *p; on any failure the caller destroys p (nothing leaks on the early returns)
+static int csr_plan_fill(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_plan *p)
 {
-    B200_ENTER(ctx);
-    B200_REQUIRE(ptr && plan && n_rows >= 0, "bad argument");
-    *plan = nullptr;
     int first_last[2] = {0, 0};
     if (n_rows > 0) {
         B200_CUDA(cudaMemcpyAsync(&first_last[0], ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         B200_CUDA(cudaMemcpyAsync(&first_last[1], ptr + n_rows, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    b200_csr_plan_info &in = p->info;
+    in.stream_tiles = 0;
+    in.n_rows = n_rows;
+    in.nnz = (long long)first_last[1] - first_last[0];
+    in.mean_len = n_rows > 0 ? (double)in.nnz / n_rows : 0.0;
+    in.lanes_per_row = pick_lanes(ctx, in.mean_len, OPT_CSR_LANES);
+    // a row is "long" when it would keep its lanes busy for more than 64 vector iterations
+    // (and is worth a whole block): it goes to the block-per-row kernel instead
+    in.long_threshold = in.lanes_per_row * 4 * 64 > 1024 ? in.lanes_per_row * 4 * 64 : 1024;
+    in.min_len = in.max_len = 0;
+    in.n_long_rows = 0;
+    if (n_rows == 0) return B200_SUCCESS;
+    PlanStats init = {0x7fffffff, 0, 0, 0};
+    PlanStats *d = reinterpret_cast<PlanStats *>(ctx->scratch);
+    B200_CUDA(cudaMemcpyAsync(d, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    int blocks = (int)min((long long)ctx->sm_count * 8, ((long long)n_rows + 255) / 256);
+    csr_stats_kernel<<<blocks, 256, 0, ctx->stream>>>(ptr, n_rows, in.long_threshold, d);
+    B200_LAUNCH_CHECK();
+    PlanStats got;
+    B200_CUDA(cudaMemcpyAsync(&got, d, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    in.min_len = got.min_len;
+    in.max_len = got.max_len;
+    in.n_long_rows = got.n_long;
+    if (got.n_long > 0) {
+        B200_CUDA(cudaMalloc(&p->long_rows, sizeof(int) * (size_t)got.n_long));
+        int *counter = ctx->scratch + 16;
+        B200_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+        csr_collect_long_kernel<<<blocks, 256, 0, ctx->stream>>>(ptr, n_rows, in.long_threshold, counter, p->long_rows);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        // one block streams ~64 Ki entries; longer rows are split (capped)
+        long long split = ((long long)in.max_len + 65535) / 65536;
+        p->n_split = (int)(split < 1 ? 1 : (split > 128 ? 128 : split));
+    }
+    // short rows everywhere: the nnz-split stream kernel (B200_CSR_STREAM=0|1 overrides)
+    // (any maximum row length: rows longer than 32 entries inside a tile get a whole warp, rows
+    // longer than a tile are stitched by the carries -- the split is by entries, so skewed
+    // power-law inputs stay balanced)
+    const bool possible = first_last[0] == 0 && in.nnz > 0 && in.nnz < 0x7fffffffll - kTile;
+    const bool short_rows = in.mean_len <= 16.0;
+    const bool skewed = in.mean_len <= 32.0 && (double)in.max_len > 16.0 * in.mean_len;
+    bool stream = (short_rows || skewed) && possible;
+    if (opt_set(ctx, OPT_CSR_STREAM)) stream = ctx->opt[OPT_CSR_STREAM] != 0 && possible;
+    if (stream) {
+        const int n_tiles = (int)((in.nnz + kTile - 1) / kTile);
+        B200_CUDA(cudaMalloc(&p->tile_lo, sizeof(int) * ((size_t)n_tiles + 1)));
+        B200_CUDA(cudaMalloc(&p->carry_row, sizeof(int) * (size_t)n_tiles));
+        B200_CUDA(cudaMalloc(&p->carry_val, sizeof(double) * (size_t)n_tiles));
+        csr_tile_rows_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, ctx->stream>>>(ptr, n_rows, n_tiles, p->tile_lo);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        in.stream_tiles = n_tiles;
+    }
+    return B200_SUCCESS;
+}
+
+int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_plan **plan)
+{
+    B200_TRACE("b200 csr plan");
+    B200_ENTER(ctx);
+    B200_REQUIRE(ptr && plan && n_rows >= 0, "bad argument");
+    *plan = nullptr;
     b200_csr_plan *p = new b200_csr_plan();
     p->device = ctx->device;
     p->long_rows = nullptr;
@@ -415,70 +473,11 @@ int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
     p->carry_row = nullptr;
     p->carry_val = nullptr;
     p->n_split = 1;
-    b200_csr_plan_info &in = p->info;
-    in.stream_tiles = 0;
-    in.n_rows = n_rows;
-    in.nnz = (long long)first_last[1] - first_last[0];
-    in.mean_len = n_rows > 0 ? (double)in.nnz / n_rows : 0.0;
-    in.lanes_per_row = pick_lanes(in.mean_len, "B200_CSR_LANES");
-    // a row is "long" when it would keep its lanes busy for more than 64 vector iterations
-    // (and is worth a whole block): it goes to the block-per-row kernel instead
-    in.long_threshold = in.lanes_per_row * 4 * 64 > 1024 ? in.lanes_per_row * 4 * 64 : 1024;
-    in.min_len = in.max_len = 0;
-    in.n_long_rows = 0;
-    if (n_rows > 0) {
-        PlanStats init = {0x7fffffff, 0, 0, 0};
-        PlanStats *d = reinterpret_cast<PlanStats *>(ctx->scratch);
-        B200_CUDA(cudaMemcpyAsync(d, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-        int blocks = (int)min((long long)ctx->sm_count * 8, ((long long)n_rows + 255) / 256);
-        csr_stats_kernel<<<blocks, 256, 0, ctx->stream>>>(ptr, n_rows, in.long_threshold, d);
-        B200_LAUNCH_CHECK();
-        PlanStats got;
-        B200_CUDA(cudaMemcpyAsync(&got, d, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
-        B200_CUDA(cudaStreamSynchronize(ctx->stream));
-        in.min_len = got.min_len;
-        in.max_len = got.max_len;
-        in.n_long_rows = got.n_long;
-        if (got.n_long > 0) {
-            cudaError_t e = cudaMalloc(&p->long_rows, sizeof(int) * (size_t)got.n_long);
-            if (e != cudaSuccess) {
-                delete p;
-                return b200_cuda_fail(e, "cudaMalloc(long_rows)", __FILE__, __LINE__);
-            }
-            int *counter = ctx->scratch + 16;
-            B200_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-            csr_collect_long_kernel<<<blocks, 256, 0, ctx->stream>>>(ptr, n_rows, in.long_threshold,
-                                                                    counter, p->long_rows);
-            B200_LAUNCH_CHECK();
-            B200_CUDA(cudaStreamSynchronize(ctx->stream));
-            // one block streams ~64 Ki entries; longer rows are split (capped)
-            long long split = ((long long)in.max_len + 65535) / 65536;
-            p->n_split = (int)(split < 1 ? 1 : (split > 128 ? 128 : split));
-        }
-        // short rows everywhere: the nnz-split stream kernel (B200_CSR_STREAM=0|1 overrides)
-        // (any maximum row length: rows longer than 32 entries inside a tile get a whole warp, rows
-        // longer than a tile are stitched by the carries -- the split is by entries, so skewed
-        // power-law inputs stay balanced)
-        const bool short_rows = in.mean_len <= 16.0;
-        const bool skewed = in.mean_len <= 32.0 && (double)in.max_len > 16.0 * in.mean_len;
-        bool stream = (short_rows || skewed) && first_last[0] == 0 && in.nnz > 0 &&
-                      in.nnz < 0x7fffffffll - kTile;
-        if (const char *e = getenv("B200_CSR_STREAM"))
-            stream = atoi(e) != 0 && first_last[0] == 0 && in.nnz > 0 && in.nnz < 0x7fffffffll - kTile;
-        if (stream) {
-            const int n_tiles = (int)((in.nnz + kTile - 1) / kTile);
-            cudaError_t e = cudaMalloc(&p->tile_lo, sizeof(int) * ((size_t)n_tiles + 1));
-            if (e == cudaSuccess) e = cudaMalloc(&p->carry_row, sizeof(int) * (size_t)n_tiles);
-            if (e == cudaSuccess) e = cudaMalloc(&p->carry_val, sizeof(double) * (size_t)n_tiles);
-            if (e != cudaSuccess) {
-                b200_csr_plan_destroy(p);
-                return b200_cuda_fail(e, "cudaMalloc(stream plan)", __FILE__, __LINE__);
-            }
-            csr_tile_rows_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, ctx->stream>>>(ptr, n_rows, n_tiles, p->tile_lo);
-            B200_LAUNCH_CHECK();
-            B200_CUDA(cudaStreamSynchronize(ctx->stream));
-            in.stream_tiles = n_tiles;
-        }
+    p->owner = ctx->stream;
+    const int rc = csr_plan_fill(ctx, ptr, n_rows, p);
+    if (rc != B200_SUCCESS) {
+        b200_csr_plan_destroy(p);
+        return rc;
     }
     *plan = p;
     return B200_SUCCESS;
@@ -512,7 +511,7 @@ int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data,
                    int n_rows, int long_threshold, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), false, "B200_CSR_UNROLL");
+    const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), false, OPT_CSR_UNROLL);
     if (!vec)
         B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
                                : b200_launch(ctx, csr_vector_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
@@ -533,6 +532,7 @@ template <typename T>
 int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, const T *x, T *y,
                   int n_rows, const b200_csr_plan *plan)
 {
+    B200_TRACE("b200 spmv csr");
     B200_ENTER(ctx);
     B200_REQUIRE(ptr && x && y && n_rows >= 0, "bad argument");
     if (n_rows == 0) return B200_SUCCESS;
@@ -548,6 +548,12 @@ int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, 
     const int thr = plan->info.long_threshold;
     int rc;
     if (plan->info.stream_tiles > 0) {
+        if (plan->owner != ctx->stream) {
+            if (tmp) b200_csr_plan_destroy(tmp);
+            b200_set_error("this CSR plan owns the carry buffers of the nnz-split kernel: use it on the "
+                           "context it was created on (make one plan per queue)");
+            return B200_ERR_INVALID_VALUE;
+        }
         const int n_tiles = plan->info.stream_tiles;
         T *carry_val = static_cast<T *>(plan->carry_val);
         if (vec)
@@ -593,7 +599,7 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
                    int row_size, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), true, "B200_ELL_UNROLL");
+    const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), true, OPT_ELL_UNROLL);
     if (!vec)
         B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
                                : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
@@ -614,12 +620,13 @@ template <typename T>
 int spmv_ell_impl(b200_ctx *ctx, const T *data, const int *col, const T *x, T *y, int n_rows,
                   int row_size)
 {
+    B200_TRACE("b200 spmv ell");
     B200_ENTER(ctx);
     B200_REQUIRE(x && y && n_rows >= 0 && row_size >= 0, "bad argument");
     if (n_rows == 0) return B200_SUCCESS;
     B200_REQUIRE(row_size == 0 || (data && col), "null data/indices");
     const bool vec = aligned16(col) && aligned16(data);
-    switch (pick_lanes((double)row_size, "B200_ELL_LANES")) {
+    switch (pick_lanes(ctx, (double)row_size, OPT_ELL_LANES)) {
     case 2: return launch_ell_lpr<T, 2>(ctx, data, col, x, y, n_rows, row_size, vec);
     case 4: return launch_ell_lpr<T, 4>(ctx, data, col, x, y, n_rows, row_size, vec);
     case 8: return launch_ell_lpr<T, 8>(ctx, data, col, x, y, n_rows, row_size, vec);

@@ -694,8 +694,7 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
         // isolation on wide chunks (banded fp32: 157-161 us vs 162-174, a third of the L1 traffic),
         // equal within 1 % in sustained power-capped runs (0.1689 vs 0.1671 ms), 5 % slower in fp64,
         // and much slower on narrow chunks (7-point stencil: 2.7 KB pieces, 0.248 vs 0.161 ms).
-        bool tma = false;
-        if (const char *e = getenv("B200_SELL_TMA")) tma = atoi(e) != 0;
+        const bool tma = opt_or(ctx, OPT_SELL_TMA, 0) != 0;
         if (tma && wmax == 0) {
             constexpr size_t smem = (size_t)(kBlock / 32) * kStages * (kPiece * (sizeof(int) + sizeof(T)) + 8);
             B200_CUDA(cudaFuncSetAttribute(sell32_tma_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -704,8 +703,8 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             // for the x gather
             const long long fit = (227 * 1024) / (long long)(smem + 1024);
             long long per_sm = fit < 2 ? fit : 2;
-            if (const char *e = getenv("B200_SELL_TMA_BLOCKS")) {
-                const int v = atoi(e);
+            {
+                const int v = opt_or(ctx, OPT_SELL_TMA_BLOCKS, 0);
                 if (v >= 1 && v <= fit) per_sm = v;
             }
             const int carve = (int)min(100ll, (per_sm * (long long)(smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
@@ -713,8 +712,7 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             const long long want = ((long long)n_slices + kBlock / 32 - 1) / (kBlock / 32);
             const unsigned grid = (unsigned)min(want, (long long)ctx->sm_count * per_sm);
             // how long a waiting warp may sleep before it polls again (B200_SELL_TMA_SUSPEND_NS; 0 = poll)
-            unsigned suspend_ns = 1000;
-            if (const char *e = getenv("B200_SELL_TMA_SUSPEND_NS")) suspend_ns = (unsigned)atoi(e);
+            const unsigned suspend_ns = (unsigned)opt_or(ctx, OPT_SELL_TMA_SUSPEND_NS, 1000);
             sell32_tma_kernel<T, P><<<grid, kBlock, smem, ctx->stream>>>(data, idx, x, y, slice_ptr, n_slices, n_out, perm,
                                                                         ctx->scratch + kWatchFlag, suspend_ns);
             B200_LAUNCH_CHECK();
@@ -725,15 +723,15 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
         // that the plan splits by columns anyway stay one warp each
         int wpc = 1;
         while (wmax == 0 && wpc < 8 && (long long)n_slices * wpc < (long long)ctx->sm_count * 32) wpc <<= 1;
-        if (const char *e = getenv("B200_SELL_WPC")) {
-            const int v = atoi(e);
+        {
+            const int v = opt_or(ctx, OPT_SELL_WPC, 0);
             if (wmax == 0 && (v == 1 || v == 2 || v == 4 || v == 8)) wpc = v;
         }
         // groups per lane and round trip (tuning hook B200_SELL_UNROLL=1|2|4): 4 for whole-chunk
         // warps, 2 once the chunk is shared by 4+ warps (cant: 11.3 us at WPC 4 / U 2 vs 18.3 at 1 / 1)
         int u = wpc >= 4 ? 2 : 4;
-        if (const char *e = getenv("B200_SELL_UNROLL")) {
-            const int v = atoi(e);
+        {
+            const int v = opt_or(ctx, OPT_SELL_UNROLL, 0);
             if (v == 1 || v == 2 || v == 4) u = v;
         }
 #define B200_SELL_MAIN(W, UU)                                                                              \
@@ -778,7 +776,7 @@ int launch_ellcm(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *y,
     constexpr int BX = KS == 1 ? 256 : 64;
     dim3 block(BX, KS);
     int q = 1;
-    if (const char *e = getenv("B200_ELLCM_Q")) q = (KS == 1 && atoi(e) == 2) ? 2 : 1;
+    if (KS == 1 && opt_or(ctx, OPT_ELLCM_Q, 1) == 2) q = 2;
     unsigned blocks = ceil_div_u(pitch / 4, BX * q);
     if (q == 2)
         ellcm_kernel<T, KS, BX, (KS == 1 ? 2 : 1)><<<blocks, block, 0, ctx->stream>>>(data, idx, x, y, n_rows, row_size, pitch);
@@ -839,6 +837,10 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         d.hi[i] = i < n_dst ? (dst_row_hi ? dst_row_hi[i] : n_rows) : 0;
     }
     for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
+    // the kernel writes row pairs as one 16-byte store: a misaligned destination would raise a
+    // sticky misaligned-address fault on every rank instead of an error here
+    B200_REQUIRE((dst_offset & 1) == 0, "dst_offset must be even (row pairs are stored as 16-byte words)");
+    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(aligned16(d.p[i]), "destination buffers must be 16-byte aligned");
     for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.lo[i] >= 0, "negative row range");
     PeerSync sync;
     memset(&sync, 0, sizeof sync);
@@ -853,12 +855,9 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         sync.world = n_dst;
         sync.step = step;
         sync.err_flag = ctx->scratch + kWatchFlag;
-        sync.flush_after_flag = 1;
-        sync.poll_mode = 0;
-        sync.sleep_ns = 100;
-        if (const char *e = getenv("B200_RING_FLUSH")) sync.flush_after_flag = atoi(e) != 0;
-        if (const char *e = getenv("B200_RING_POLL")) sync.poll_mode = atoi(e) != 0;
-        if (const char *e = getenv("B200_RING_SLEEP_NS")) sync.sleep_ns = atoi(e);
+        sync.flush_after_flag = opt_or(ctx, OPT_RING_FLUSH, 1) != 0;
+        sync.poll_mode = opt_or(ctx, OPT_RING_POLL, 0) != 0;
+        sync.sleep_ns = opt_or(ctx, OPT_RING_SLEEP_NS, 100);
         double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
         const double *scale = step > 0 ? reinterpret_cast<const double *>(sync.mine + kSyncScale) : nullptr;
         sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(

@@ -23,6 +23,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(autouse=True)
+def _reset_tuning_hooks(request):
+    """Tuning hooks set with ctx.set_option (b200_ctx_set_option) never leak into the next test."""
+    yield
+    if "ctx" in request.fixturenames:
+        request.getfixturevalue("ctx").clear_options()
+
+
 def check_y(name, y, y_ref, dtype):
     err = O.rel_maxnorm(y, y_ref)
     assert err <= TOL[np.dtype(dtype)], f"{name} {np.dtype(dtype).name}: rel max-norm {err:g}"
@@ -212,7 +220,7 @@ def test_unaligned_arrays_take_the_scalar_kernels(ctx, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_csr_stream_kernel(ctx, dtype, monkeypatch):
+def test_csr_stream_kernel(ctx, dtype):
     """The nnz-split CSR kernel (short rows): chosen automatically for mean <= 16 / max <= 256, and
     forced here on rows that span several 1024-entry tiles, with empty rows sitting exactly on tile
     boundaries and at the end of the matrix."""
@@ -234,14 +242,14 @@ def test_csr_stream_kernel(ctx, dtype, monkeypatch):
     rows = np.repeat(np.arange(n_rows, dtype=np.int32), lens)
     cols = np.concatenate([np.sort(rng.choice(n_cols, int(k), replace=False)) for k in lens]).astype(np.int32)
     vals = rng.uniform(-1, 1, rows.size)
-    monkeypatch.setenv("B200_CSR_STREAM", "1")
+    ctx.set_option("B200_CSR_STREAM", "1")
     coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
     csr = pkg.CsrMatrix(coo)
     assert csr.plan_info().stream_tiles == -(-rows.size // 1024)
     yd = ctx.array(np.full(n_rows, np.nan, dtype))
     csr.spmv(ctx.array(x.astype(dtype)), yd)
     check_y("csr-stream-forced", yd.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
-    monkeypatch.setenv("B200_CSR_STREAM", "0")
+    ctx.set_option("B200_CSR_STREAM", "0")
     csr2 = pkg.CsrMatrix(coo)
     assert csr2.plan_info().stream_tiles == 0
     y2 = ctx.array(np.full(n_rows, np.nan, dtype))
@@ -388,7 +396,7 @@ VARIANT_HOOKS = {
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_every_tuning_variant_matches_the_oracle(ctx, dtype, monkeypatch):
+def test_every_tuning_variant_matches_the_oracle(ctx, dtype):
     """Every kernel variant the tuning hooks can select (lanes per row, load-batch depth U, SELL
     warps per chunk) computes the same y: ragged rows (1..150 entries), a row count that is not a
     multiple of 32 or 8, and a last SELL chunk / CMRS strip that is partly empty."""
@@ -402,7 +410,7 @@ def test_every_tuning_variant_matches_the_oracle(ctx, dtype, monkeypatch):
     for fmt, envs in VARIANT_HOOKS.items():
         for env in envs:
             for k, v in env.items():
-                monkeypatch.setenv(k, str(v))
+                ctx.set_option(k, str(v))
             mat = pkg.CsrMatrix(coo) if fmt == "csr" else m[fmt]   # the CSR plan caches its lanes
             if fmt == "csr":
                 assert mat.plan_info().lanes_per_row == env["B200_CSR_LANES"]
@@ -410,7 +418,7 @@ def test_every_tuning_variant_matches_the_oracle(ctx, dtype, monkeypatch):
             mat.spmv(xd, yd)
             check_y(f"{fmt} {env}", yd.download(), y_ref, dtype)
             for k in env:
-                monkeypatch.delenv(k)
+                ctx.set_option(k, None)
 
 
 def test_launch_graph_replays_recorded_spmvs(ctx):
@@ -453,7 +461,7 @@ def test_launch_graph_replays_recorded_spmvs(ctx):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("height", [8, 5, 32])
-def test_cmrs_packed_layout(ctx, dtype, height, monkeypatch):
+def test_cmrs_packed_layout(ctx, dtype, height):
     """Packed CMRS: (row_in_strip << 27) | column must equal the reference arrays bit for bit when
     unpacked, and the packed kernel must give the same bits as the two-array kernel (same order of
     operations) -- including the long-strip plan and both load-batch depths."""
@@ -469,7 +477,7 @@ def test_cmrs_packed_layout(ctx, dtype, height, monkeypatch):
     np.testing.assert_array_equal((w & ((1 << 27) - 1)).astype(np.int32), cols)
     xd = ctx.array(x.astype(dtype))
     for u in (1, 2):
-        monkeypatch.setenv("B200_CMRS_U", str(u))
+        ctx.set_option("B200_CMRS_U", str(u))
         y0, y1 = ctx.array(np.full(n_rows, np.nan, dtype)), ctx.array(np.full(n_rows, np.nan, dtype))
         cmrs.spmv(xd, y0)
         packed.spmv(xd, y1)

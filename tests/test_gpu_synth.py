@@ -19,6 +19,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(autouse=True)
+def _reset_tuning_hooks(request):
+    """Tuning hooks set with ctx.set_option (b200_ctx_set_option) never leak into the next test."""
+    yield
+    if "ctx" in request.fixturenames:
+        request.getfixturevalue("ctx").clear_options()
+
+
 def test_banded_generator_device_equals_host(ctx):
     L = pkg.lib()
     n, npr, hb, seed = 50000, 64, 2000, 42
