@@ -43,7 +43,8 @@ enum {
     B200_ERR_INVALID_VALUE = 3,
     B200_ERR_OUT_OF_MEMORY = 4,
     B200_ERR_UNSUPPORTED = 5,
-    B200_ERR_DOMAIN = 6 /* input outside the builder's domain (e.g. rows not sorted) */
+    B200_ERR_DOMAIN = 6, /* input outside the builder's domain (e.g. rows not sorted) */
+    B200_ERR_COMM = 7    /* NCCL reported an error (synchronously, or asynchronously: b200_comm_check) */
 };
 
 typedef struct b200_ctx b200_ctx;     /* cl_context + cl_command_queue */
@@ -386,6 +387,84 @@ int b200_ipc_close_handle(b200_ctx *ctx, void *peer_dptr);
 /* power-iteration helpers for the iterated mode: y *= scale; sum of squares into *acc (device) */
 int b200_scale_f64(b200_ctx *ctx, double *y, long long n, const double *scale_device, int invert_sqrt);
 int b200_sumsq_f64(b200_ctx *ctx, const double *y, long long n, double *acc_device);
+
+
+/* =====================================================================================
+ * Iterated (power-iteration) mode behind the C ABI (new; SURVEY 8b viii, 8e).  The reference's
+ * device loop enumerates up to 8 GPUs and breaks after the first (csr.c:12,22-30,279); here one
+ * rank = one context = one GPU, ranks being processes (peers mapped with b200_ipc_*) or threads of
+ * one process (peers enabled with b200_ctx_enable_peer_access).
+ * ===================================================================================== */
+
+/* ---- communicator: NCCL over NVLink, opened at run time (dlopen of libnccl.so.2; a process that
+ *      already carries NCCL, e.g. through torch, shares that copy).  Without the library every call
+ *      fails with B200_ERR_UNSUPPORTED -- the single-GPU entry points never need it.  Rank 0 makes an
+ *      id, hands it to the other ranks by any means, and all ranks create their communicator
+ *      concurrently (collective call).  All collectives run on the context's stream. ---- */
+typedef struct b200_comm b200_comm;
+#define B200_COMM_ID_BYTES 128
+int b200_comm_get_unique_id(unsigned char id[B200_COMM_ID_BYTES]);
+int b200_comm_create(b200_ctx *ctx, const unsigned char id[B200_COMM_ID_BYTES], int rank, int world,
+                     b200_comm **comm);
+int b200_comm_destroy(b200_comm *comm);
+int b200_comm_info(const b200_comm *comm, int *rank, int *world, int *nccl_version); /* any out may be NULL */
+/* asynchronous-error poll (ncclCommGetAsyncError): B200_ERR_COMM once a peer died or a link failed;
+ * b200_iterator_run / b200_iterator_norm call it too */
+int b200_comm_check(b200_comm *comm);
+int b200_comm_allreduce_sum_f64(b200_comm *comm, double *buf_device, long long count); /* in place */
+/* in place: rank r's segment is full[r*count_per_rank .. (r+1)*count_per_rank) */
+int b200_comm_allgather_f64(b200_comm *comm, double *full_device, long long count_per_rank);
+/* threads-of-one-process ranks: let this context's device store into `peer_device`'s allocations */
+int b200_ctx_enable_peer_access(b200_ctx *ctx, int peer_device);
+
+/* which rows of rank `rank`'s block every rank reads as columns (host function).  col_min[d] /
+ * col_max[d] = smallest / largest global column index in rank d's matrix block (b200_minmax_i32 over
+ * its column array, exchanged once).  Blocks are equal: rank r owns rows [r*rows_per_rank,
+ * min((r+1)*rows_per_rank, n_rows_total)).  lo[d], hi[d] (world entries each) = LOCAL row range of this
+ * rank's block that destination d needs; the rank itself always gets its whole block. */
+int b200_halo_rows(const int *col_min, const int *col_max, int world, int rank, long long rows_per_rank,
+                   long long n_rows_total, int *lo, int *hi);
+
+/* ---- iterator: `steps` steps of  y = A_r x / ||x||_2 ;  x <- y  on row-partitioned A ---- */
+enum { B200_FORMAT_COO = 0, B200_FORMAT_CSR = 1, B200_FORMAT_ELL = 2, B200_FORMAT_SELL = 3, B200_FORMAT_CMRS = 4 };
+typedef struct {            /* this rank's row block, fp64, GLOBAL column indices, device arrays */
+    int format;             /* B200_FORMAT_CSR or B200_FORMAT_SELL (chunk 32, no permutation) */
+    int n_rows;             /* rows of the block */
+    int n_slices;           /* SELL: chunks of the block (ceil(n_rows / 32)) */
+    const int *ptr;         /* CSR: ptr[n_rows + 1];  SELL: row_indices[n_slices + 1] */
+    const int *indices;
+    const double *data;
+    const b200_csr_plan *csr_plan; /* CSR: optional plan (NULL = analyse on the fly, not recordable) */
+} b200_block_f64;
+enum {
+    B200_ITER_FUSED = 0,    /* SELL kernel stores y straight into the x buffers of the ranks that read
+                             * it (b200_spmv_sell_halo_f64) + one 256-byte all-reduce per step */
+    B200_ITER_ALLGATHER = 1 /* SpMV -> sum of squares -> all-reduce -> scale -> in-place ncclAllGather */
+};
+typedef struct {
+    int mode;               /* B200_ITER_* */
+    int world, rank;
+    long long rows_per_rank; /* multiple of 32, >= n_rows: rank r's block sits at r*rows_per_rank of x */
+    double *const *x[2];    /* x[b][r]: x buffer b (two alternate) of rank r as THIS process sees it, each
+                             * world*rows_per_rank doubles, 16-byte aligned; x[0][rank] holds the start
+                             * vector.  B200_ITER_ALLGATHER reads only x[b][rank] */
+    const int *halo_lo, *halo_hi; /* FUSED: b200_halo_rows output (world entries); NULL, NULL = every row
+                             * to every rank */
+    int graph_steps;        /* 0: every step is issued as separate launches; G (even): steps are recorded
+                             * once into a launch graph of G steps and replayed (first step always direct) */
+} b200_iter_desc;
+typedef struct b200_iterator b200_iterator;
+int b200_iterator_create(b200_ctx *ctx, b200_comm *comm /* NULL iff world == 1 */, const b200_block_f64 *block,
+                         const b200_iter_desc *desc, b200_iterator **iterator);
+/* enqueue `steps` more steps (asynchronous; all ranks must call it with the same counts) */
+int b200_iterator_run(b200_iterator *iterator, int steps);
+/* waits; *norm = ||A x_{k-1} / ||x_{k-1}|| ||_2 of the last step issued: the eigenvalue estimate */
+int b200_iterator_norm(b200_iterator *iterator, double *norm);
+/* steps issued so far, the buffer holding the current vector (own block + received rows; FUSED: not
+ * yet divided by the norm), kernels + collectives issued so far; any out may be NULL */
+int b200_iterator_state(const b200_iterator *iterator, unsigned long long *steps_done, double **x_current,
+                        unsigned long long *launches);
+int b200_iterator_destroy(b200_iterator *iterator);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,23 @@ class RowStats(C.Structure):
                 ("sum_len_excl_last", C.c_longlong), ("last_len", C.c_int)]
 
 
+class BlockF64(C.Structure):
+    """b200_block_f64: one rank's row block for the iterated mode."""
+    _fields_ = [("format", C.c_int), ("n_rows", C.c_int), ("n_slices", C.c_int), ("ptr", C.c_void_p),
+                ("indices", C.c_void_p), ("data", C.c_void_p), ("csr_plan", C.c_void_p)]
+
+
+class IterDesc(C.Structure):
+    """b200_iter_desc."""
+    _fields_ = [("mode", C.c_int), ("world", C.c_int), ("rank", C.c_int), ("rows_per_rank", C.c_longlong),
+                ("x", C.POINTER(C.c_void_p) * 2), ("halo_lo", C.POINTER(C.c_int)), ("halo_hi", C.POINTER(C.c_int)),
+                ("graph_steps", C.c_int)]
+
+
+FORMAT_COO, FORMAT_CSR, FORMAT_ELL, FORMAT_SELL, FORMAT_CMRS = range(5)
+ITER_FUSED, ITER_ALLGATHER = 0, 1
+COMM_ID_BYTES = 128
+
 _vp, _i, _ll, _u64, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_uint64, C.c_size_t
 _vpp = C.POINTER(C.c_void_p)
 
@@ -142,6 +159,20 @@ SIGNATURES = {
     "b200_ipc_get_handle": (_i, [_vp, _vp, _vp]),
     "b200_ipc_open_handle": (_i, [_vp, _vp, _vpp]),
     "b200_ipc_close_handle": (_i, [_vp, _vp]),
+    "b200_comm_get_unique_id": (_i, [_vp]),
+    "b200_comm_create": (_i, [_vp, _vp, _i, _i, _vpp]),
+    "b200_comm_destroy": (_i, [_vp]),
+    "b200_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "b200_comm_check": (_i, [_vp]),
+    "b200_comm_allreduce_sum_f64": (_i, [_vp, _vp, _ll]),
+    "b200_comm_allgather_f64": (_i, [_vp, _vp, _ll]),
+    "b200_ctx_enable_peer_access": (_i, [_vp, _i]),
+    "b200_halo_rows": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _vp]),
+    "b200_iterator_create": (_i, [_vp, _vp, C.POINTER(BlockF64), C.POINTER(IterDesc), _vpp]),
+    "b200_iterator_run": (_i, [_vp, _i]),
+    "b200_iterator_norm": (_i, [_vp, C.POINTER(C.c_double)]),
+    "b200_iterator_state": (_i, [_vp, C.POINTER(C.c_ulonglong), _vpp, C.POINTER(C.c_ulonglong)]),
+    "b200_iterator_destroy": (_i, [_vp]),
     "b200_scale_f64": (_i, [_vp, _vp, _ll, _vp, _i]),
     "b200_sumsq_f64": (_i, [_vp, _vp, _ll, _vp]),
 }
@@ -357,6 +388,5 @@ class Event:
 
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix, CmrsPackedMatrix,  # noqa: E402,F401
                       algorithmic_bytes, build_all, partition_rows)
-from .iterate import (PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges, gpu_callables, halo_rows,
-                      power_iteration, power_iteration_ring,  # noqa: E402,F401
-                      power_iteration_fused)
+from .iterate import (Comm, Iterator, PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges,  # noqa: E402,F401
+                      gpu_callables, halo_rows, power_iteration, power_iteration_ring, power_iteration_fused)

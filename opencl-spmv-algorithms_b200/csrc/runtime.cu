@@ -48,6 +48,7 @@ const char *b200_status_string(int status)
     case B200_ERR_OUT_OF_MEMORY: return "out of device memory";
     case B200_ERR_UNSUPPORTED: return "unsupported";
     case B200_ERR_DOMAIN: return "input outside the builder's domain";
+    case B200_ERR_COMM: return "communicator (NCCL) error";
     default: return "unknown status";
     }
 }

@@ -119,6 +119,114 @@ def gpu_callables(pkg, ctx, matrix, n_rows_local: int):
 
 
 # ---------------------------------------------------------------------------------------------
+# The product path: communicator + iterator live in the library (csrc/iterate.cu); Python only
+# passes pointers.  The step loops further down are kept as the readable mirror the tests compare
+# the library against.
+# ---------------------------------------------------------------------------------------------
+class Comm:
+    """b200_comm: an NCCL communicator created by the library on a context's stream.  `exchange`
+    carries rank 0's 128-byte id to the other ranks: a callable bytes -> bytes (identity on one
+    rank); with torch.distributed initialised the default broadcasts it."""
+
+    def __init__(self, pkg, ctx, rank: int, world: int, exchange: Callable | None = None):
+        import ctypes as C
+        self.pkg, self.ctx, self.rank, self.world = pkg, ctx, rank, world
+        L = pkg.lib()
+        ident = (C.c_ubyte * pkg.COMM_ID_BYTES)()
+        if rank == 0:
+            pkg.check(L.b200_comm_get_unique_id(ident), "b200_comm_get_unique_id")
+        if exchange is None:
+            def exchange(b):
+                import torch.distributed as dist
+                box = [b]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+        got = exchange(bytes(ident))
+        ident = (C.c_ubyte * pkg.COMM_ID_BYTES).from_buffer_copy(got)
+        self.h = C.c_void_p()
+        pkg.check(L.b200_comm_create(ctx.h, ident, rank, world, C.byref(self.h)), "b200_comm_create")
+
+    def nccl_version(self) -> int:
+        import ctypes as C
+        v = C.c_int(0)
+        self.pkg.check(self.pkg.lib().b200_comm_info(self.h, None, None, C.byref(v)), "b200_comm_info")
+        return v.value
+
+    def check(self) -> None:
+        """Poll for an asynchronous NCCL error (a dead peer, a failed link): raises B200Error."""
+        self.pkg.check(self.pkg.lib().b200_comm_check(self.h), "b200_comm_check")
+
+    def allreduce_sum(self, buf_ptr: int, count: int) -> None:
+        self.pkg.check(self.pkg.lib().b200_comm_allreduce_sum_f64(self.h, buf_ptr, count), "b200_comm_allreduce_sum_f64")
+
+    def allgather(self, full_ptr: int, count_per_rank: int) -> None:
+        self.pkg.check(self.pkg.lib().b200_comm_allgather_f64(self.h, full_ptr, count_per_rank), "b200_comm_allgather_f64")
+
+    def close(self) -> None:
+        if self.h:
+            self.pkg.lib().b200_comm_destroy(self.h)
+            self.h = None
+
+
+class Iterator:
+    """b200_iterator: the power iteration run by the library (launch-graph replay, NCCL from C).
+
+    matrix: SellMatrix (sigma = 1, int32 pointers) or CsrMatrix of this rank's row block.
+    x_ptrs: x_ptrs[b][r] = device pointer of x buffer b of rank r as this process sees it
+            (PeerBuffers.ptrs[:2] for mode 'fused'; for 'allgather' only [b][rank] is read)."""
+
+    def __init__(self, pkg, ctx, comm: Comm | None, matrix, blocks: RowBlocks, rank: int, world: int,
+                 x_ptrs, mode: str = "fused", halo=None, graph_steps: int = 10):
+        import ctypes as C
+        self.pkg, self.ctx, self.matrix, self.comm = pkg, ctx, matrix, comm
+        L = pkg.lib()
+        n_local = blocks.bounds(rank)[1] - blocks.bounds(rank)[0]
+        blk = pkg.BlockF64()
+        if hasattr(matrix, "row_indices"):
+            assert matrix.perm is None and matrix.row_indices is not None, "SELL-32, sigma = 1, int32 pointers"
+            blk.format, blk.n_slices = pkg.FORMAT_SELL, matrix.n_slices
+            blk.ptr, blk.indices, blk.data = matrix.row_indices.ptr, matrix.cols.ptr, matrix.data.ptr
+        else:
+            blk.format, blk.n_slices = pkg.FORMAT_CSR, 0
+            blk.ptr, blk.indices, blk.data = matrix.ptr.ptr, matrix.cols.ptr, matrix.coo.values("f8").ptr
+            blk.csr_plan = matrix.plan()
+        blk.n_rows = n_local
+        d = pkg.IterDesc()
+        d.mode = {"fused": pkg.ITER_FUSED, "allgather": pkg.ITER_ALLGATHER}[mode]
+        d.world, d.rank, d.rows_per_rank, d.graph_steps = world, rank, blocks.count, graph_steps
+        self._tables = [(C.c_void_p * world)(*[int(p) if p else None for p in x_ptrs[b]]) for b in range(2)]
+        d.x[0] = C.cast(self._tables[0], C.POINTER(C.c_void_p))
+        d.x[1] = C.cast(self._tables[1], C.POINTER(C.c_void_p))
+        if halo is not None:
+            self._lo, self._hi = (C.c_int * world)(*halo[0]), (C.c_int * world)(*halo[1])
+            d.halo_lo, d.halo_hi = C.cast(self._lo, C.POINTER(C.c_int)), C.cast(self._hi, C.POINTER(C.c_int))
+        self.h = C.c_void_p()
+        pkg.check(L.b200_iterator_create(ctx.h, comm.h if comm else None, C.byref(blk), C.byref(d), C.byref(self.h)),
+                  "b200_iterator_create")
+
+    def run(self, steps: int) -> None:
+        self.pkg.check(self.pkg.lib().b200_iterator_run(self.h, steps), "b200_iterator_run")
+
+    def norm(self) -> float:
+        import ctypes as C
+        v = C.c_double(0.0)
+        self.pkg.check(self.pkg.lib().b200_iterator_norm(self.h, C.byref(v)), "b200_iterator_norm")
+        return v.value
+
+    def state(self):
+        """(steps issued, device pointer of the current x buffer, kernels + collectives issued)."""
+        import ctypes as C
+        k, x, n = C.c_ulonglong(0), C.c_void_p(), C.c_ulonglong(0)
+        self.pkg.check(self.pkg.lib().b200_iterator_state(self.h, C.byref(k), C.byref(x), C.byref(n)), "b200_iterator_state")
+        return k.value, x.value, n.value
+
+    def close(self) -> None:
+        if self.h:
+            self.pkg.lib().b200_iterator_destroy(self.h)
+            self.h = None
+
+
+# ---------------------------------------------------------------------------------------------
 # Fused variant: the SpMV kernel itself stores its y-block into every rank's next-x buffer over
 # NVLink (peer memory mapped with CUDA IPC) -- no all-gather, no pack, no separate scale pass.
 # ---------------------------------------------------------------------------------------------
@@ -128,7 +236,7 @@ class PeerBuffers:
     all_gather_object)."""
     SYNC_BLOCK_BYTES = 16384  # B200_SYNC_BLOCK_BYTES
 
-    def __init__(self, pkg, ctx, blocks: RowBlocks, rank: int, world: int):
+    def __init__(self, pkg, ctx, blocks: RowBlocks, rank: int, world: int, all_gather_object=None):
         import ctypes as C
         import numpy as np
         self.pkg, self.ctx, self.rank, self.world = pkg, ctx, rank, world
@@ -145,9 +253,11 @@ class PeerBuffers:
             handles.append(bytes(h))
         gathered = [handles]
         if world > 1:
-            import torch.distributed as dist
+            if all_gather_object is None:
+                import torch.distributed as dist
+                all_gather_object = dist.all_gather_object
             gathered = [None] * world
-            dist.all_gather_object(gathered, handles)
+            all_gather_object(gathered, handles)
         self._opened = []
         self.ptrs = []  # ptrs[b][r] = device pointer of buffer b of rank r, valid in THIS process
         for b in range(3):

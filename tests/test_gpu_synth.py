@@ -226,6 +226,47 @@ def test_fused_power_iteration_one_gpu(ctx):
     tctx.close()
 
 
+@pytest.mark.parametrize("mode,graph_steps", [("fused", 0), ("fused", 6), ("allgather", 0), ("allgather", 6)])
+def test_library_iterator_one_gpu(ctx, mode, graph_steps):
+    """b200_iterator_* (the C-ABI power iteration: steps issued by the library, optionally replayed
+    from a launch graph) against the CPU power iteration, in both formulations, CSR and SELL blocks,
+    and in pieces (7 + 30 + 4 steps: direct steps, graph replays, a direct remainder)."""
+    nx, ny, nz, steps = 24, 20, 18, 41
+    n, rows, cols, vals = laplace7(nx, ny, nz)
+    blocks = pkg.equal_row_blocks(n, 1)
+    x0 = np.zeros(blocks.padded)
+    x0[:n] = np.random.default_rng(1).uniform(0, 1, n)
+    ptr, _ = O.build_csr(n, rows)
+    x = x0[:n].copy()
+    for _ in range(steps):
+        y = O.spmv_csr(n, ptr, cols, vals, x)
+        nrm = np.linalg.norm(y)
+        x = y / nrm
+    csr = pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, n, n, rows, cols, vals))
+    mats = [pkg.SellMatrix(csr, np.float64)] + ([csr] if mode == "allgather" else [])
+    for mat in mats:
+        bufs = [ctx.array(x0), ctx.zeros(blocks.padded, np.float64)]
+        it = pkg.Iterator(pkg, ctx, None, mat, blocks, 0, 1, [[bufs[0].ptr], [bufs[1].ptr]], mode=mode,
+                          graph_steps=graph_steps)
+        for part in (7, 30, 4):
+            it.run(part)
+        norm = it.norm()
+        k, xptr, launches = it.state()
+        assert k == steps and xptr == bufs[steps % 2].ptr
+        assert launches == steps * (1 if mode == "fused" else 3)
+        assert abs(norm - nrm) <= 1e-12 * nrm
+        got = bufs[steps % 2].download()[:n]
+        if mode == "fused":
+            got = got / norm          # the fused path leaves A x_{k-1} / ||x_{k-1}||, scaled by the next step
+        assert np.max(np.abs(got - x)) <= 1e-12
+        it.close()
+    # argument checks: a communicator is required exactly when world > 1, graph_steps must be even
+    with pytest.raises(pkg.B200Error):
+        pkg.Iterator(pkg, ctx, None, mats[0], pkg.equal_row_blocks(n, 2), 0, 2, [[1, 1], [1, 1]], mode=mode)
+    with pytest.raises(pkg.B200Error):
+        pkg.Iterator(pkg, ctx, None, mats[0], blocks, 0, 1, [[bufs[0].ptr], [bufs[1].ptr]], mode=mode, graph_steps=3)
+
+
 def test_halo_limited_exchange_three_emulated_ranks(ctx):
     """b200_spmv_sell_halo_f64: three row blocks of a 7-point Laplacian run one after the other on ONE
     GPU, each storing into the next-x buffers of all three 'ranks' but only the rows the destination
