@@ -300,6 +300,462 @@ def cpu_arm(n_rows, n_cols, rows, cols, vals, x, dtype, kind, reps, warm):
 
 
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank: int) -> None:
+    """Multi-rank runs: pin this process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any
+    pinned host memory is allocated, so that every rank's host<->device copies stay on its own socket
+    instead of all ranks sharing rank 0's.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
+class Dist:
+    """torch.distributed over NCCL as plumbing: barriers and the max / sum over ranks of the timings."""
+
+    def __init__(self, world: int, local_rank: int):
+        self.world, self.dist, self.torch = world, None, None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist, self.torch = dist, torch
+
+    def barrier(self, ctx=None):
+        if ctx is not None:
+            ctx.sync()
+        if self.dist is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="max"):
+        if self.dist is None:
+            return [float(v) for v in values]
+        t = self.torch.tensor([float(v) for v in values], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def column_range(pkg, ctx, cols):
+    """[lo, hi] = the columns a row block reads (b200_minmax_i32): all of x that has to be on the device."""
+    import ctypes as C
+    lo, hi = C.c_int(0), C.c_int(0)
+    pkg.check(pkg.lib().b200_minmax_i32(ctx.h, cols.ptr, cols.n, C.byref(lo), C.byref(hi)), "b200_minmax_i32")
+    return lo.value, hi.value
+
+
+def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col_hi, dtype, steps, flops_step):
+    """The metric through the C ABI with HOST buffers: per format, pinned-host x -> device, SpMV,
+    y -> pinned host, with the format arrays uploaded once beforehand as the reference driver does
+    (csr.c:183-193).  Only the column range [col_lo, col_hi] the row block reads is uploaded (the
+    kernels are handed the base pointer of a virtual full-length x), so the bytes per rank do not grow
+    with the number of ranks."""
+    import ctypes as C
+    L = pkg.lib()
+    V = np.dtype(dtype).itemsize
+    n_x = col_hi - col_lo + 1
+    x_slice = x.download()[col_lo:col_hi + 1]
+
+    def make_queue(q):
+        hx, hy = C.c_void_p(), C.c_void_p()
+        pkg.check(L.b200_host_alloc_pinned(n_x * V, C.byref(hx)), "pinned x")
+        pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy)), "pinned y")
+        np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(n_x * V,)).view(dtype)[:] = x_slice
+        xin = q.empty(n_x, dtype)
+        # x[c] for c in [col_lo, col_hi] resolves into xin: a view whose base sits col_lo entries earlier
+        view = pkg.DeviceArray.from_ptr(q, xin.ptr - col_lo * V, n_cols, dtype)
+        return dict(ctx=q, hx=hx, hy=hy, xin=xin, view=view)
+
+    q1 = make_queue(ctx)
+    ctx2 = pkg.Context(local_rank)
+    q2 = make_queue(ctx2)
+
+    def call(f, m, q):
+        m.ctx = q["ctx"]
+        pkg.check(L.b200_memcpy_h2d_async(q["ctx"].h, q["xin"].ptr, q["hx"], n_x * V), "h2d x")
+        m.spmv(q["view"], y[f])
+        pkg.check(L.b200_memcpy_d2h_async(q["ctx"].h, q["hy"], y[f].ptr, n_rows * V), "d2h y")
+
+    def step_one_queue():
+        for f, m in mats.items():
+            call(f, m, q1)
+        ctx.sync()
+
+    # the same five calls on TWO in-order queues of the same device, formats alternating: PCIe is full
+    # duplex, so the y download of one call overlaps the x upload and kernel of the next
+    csr_on_two = "csr" in mats and mats["csr"].plan_info().stream_tiles > 0  # its plan serves one queue only
+    owner = {f: (q1 if (i % 2 == 0 or (f == "csr" and csr_on_two)) else q2) for i, f in enumerate(mats)}
+
+    def step_two_queues():
+        for f, m in mats.items():
+            call(f, m, owner[f])
+        ctx.sync()
+        ctx2.sync()
+
+    for _ in range(2):
+        step_one_queue()
+    D.barrier(ctx)
+    a, b = ctx.event(), ctx.event()
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(steps):
+        step_one_queue()
+    b.record()
+    D.barrier(ctx)
+    one_ms = a.elapsed_ms_until(b) / steps
+    one_wall = (time.perf_counter() - t0) * 1e3 / steps
+    for _ in range(2):
+        step_two_queues()
+    D.barrier(ctx)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_two_queues()
+    D.barrier(ctx)
+    two_wall = (time.perf_counter() - t0) * 1e3 / steps
+    for m in mats.values():
+        m.ctx = ctx
+    one_ms, one_wall, two_wall = D.reduce([one_ms, one_wall, two_wall], "max")
+    h2d, d2h = D.reduce([len(mats) * n_x * V, len(mats) * n_rows * V], "sum")
+    best = min(one_ms, two_wall)
+    ctx2.sync()
+    for q in (q1, q2):
+        L.b200_host_free_pinned(q["hx"])
+        L.b200_host_free_pinned(q["hy"])
+    del q1, q2
+    ctx2.close()
+    return {"value": round(flops_step / (best * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": round(best, 4), "steps": steps,
+            "x_columns_uploaded_per_rank": int(n_x), "x_columns_total": int(n_cols),
+            "one_queue": {"ms_per_step": round(one_ms, 4), "wall_ms_per_step": round(one_wall, 4),
+                          "gflops": round(flops_step / (one_ms * 1e-3) * 1e-9, 2)},
+            "two_queues": {"wall_ms_per_step": round(two_wall, 4),
+                           "gflops": round(flops_step / (two_wall * 1e-3) * 1e-9, 2)},
+            "what": "per format: pinned-host x (only the column range this rank's row block reads, b200_minmax_i32) "
+                    "-> device, SpMV through the C ABI, y -> pinned host; format arrays uploaded once before the "
+                    "timed region, as the reference driver does (csr.c:183-193). value = the better of one in-order "
+                    "queue (CUDA events) and two queues with alternating formats (wall clock, both drained); max "
+                    "over ranks"}
+
+
+def time_formats(ctx, D, mats, x, y, steps, warmup, local_rank=None):
+    """W warm-up steps, then K timed steps (one SpMV per format and step): per-format CUDA events
+    inside, whole-region events outside, barrier + sync on both sides."""
+    for _ in range(warmup):
+        for f in mats:
+            mats[f].spmv(x, y[f])
+    D.barrier(ctx)
+    ev = {f: [(ctx.event(), ctx.event()) for _ in range(steps)] for f in mats}
+    e0, e1 = ctx.event(), ctx.event()
+    clk = ClockSampler(local_rank) if local_rank is not None else None
+    if clk:
+        clk.__enter__()
+    D.barrier(ctx)
+    e0.record()
+    for s in range(steps):
+        for f, m in mats.items():
+            ev[f][s][0].record()
+            m.spmv(x, y[f])
+            ev[f][s][1].record()
+    e1.record()
+    D.barrier(ctx)
+    if clk:
+        clk.__exit__()
+    total_ms = e0.elapsed_ms_until(e1)
+    per_ms = {f: float(np.mean([a.elapsed_ms_until(b) for a, b in ev[f]])) for f in mats}
+    return total_ms / steps, per_ms, clk
+
+
+def format_table(names, per_ms, bytes_alg, nnz, peak):
+    fm = {}
+    for f in names:
+        gbs = bytes_alg[f] / (per_ms[f] * 1e-3) * 1e-9
+        fm[f] = {"ms": round(per_ms[f], 5), "gflops": round(2.0 * nnz / (per_ms[f] * 1e-3) * 1e-9, 2),
+                 "alg_bytes": int(bytes_alg[f]), "gbs": round(gbs, 1),
+                 "frac_measured": round(gbs / peak, 4), "frac_nominal_8TBs": round(gbs / NOMINAL_HBM_GBS, 4)}
+    return fm
+
+
+def strong_section(pkg, ctx, D, args, rank, world, dtype, peak):
+    """STRONG scaling of the same five-format step: the fixed (--rows-per-gpu)-row banded matrix is cut
+    into `world` nnz-balanced, 32-aligned row blocks by b200_partition_rows; x replicated, no
+    collective.  The K steps are one launch-graph replay (at 8 ranks a kernel lasts ~25 us)."""
+    n = args.rows_per_gpu
+    npr = BANDED["nnz_per_row"]
+    ptr_host = (np.arange(n + 1, dtype=np.int64) * npr).astype(np.int32)
+    cuts = pkg.partition_rows(ptr_host, world, 32)
+    r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+    coo, x = build_banded_device(pkg, ctx, n, r0, r1 - r0, dtype)
+    allm = pkg.build_all(coo, dtype)
+    allm["csr"].plan()
+    mats = {f: allm[f] for f in FORMATS}
+    y = {f: ctx.zeros(r1 - r0, dtype) for f in mats}
+    steps = max(10, min(args.steps, 100))
+    for f in mats:
+        mats[f].spmv(x, y[f])
+    with ctx.record_graph() as g:
+        for _ in range(steps):
+            for f in mats:
+                mats[f].spmv(x, y[f])
+    g.launch()
+    D.barrier(ctx)
+    e0, e1 = ctx.event(), ctx.event()
+    e0.record()
+    g.launch()
+    e1.record()
+    D.barrier(ctx)
+    (ms,) = D.reduce([e0.elapsed_ms_until(e1) / steps], "max")
+    (nnz_total,) = D.reduce([coo.nnz], "sum")
+    (bytes_max,) = D.reduce([sum(m.nbytes(dtype) for m in mats.values())], "max")
+    flops = 2.0 * nnz_total * len(mats)
+    return {"value": round(flops / (ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "scaling": "strong",
+            "ms_per_step": round(ms, 5), "steps": steps, "n_gpus": world,
+            "workload": f"the fixed {n}-row banded matrix ({int(nnz_total)} nnz) cut into {world} row block(s) by "
+                        "b200_partition_rows (nnz-balanced, cuts multiples of 32); x replicated; no collective",
+            "cuts": [int(c) for c in cuts], "alg_bytes_per_step_max_rank": int(bytes_max),
+            "gbs_max_rank": round(bytes_max / (ms * 1e-3) * 1e-9, 1),
+            "frac_measured_max_rank": round(bytes_max / (ms * 1e-3) * 1e-9 / peak, 4),
+            "method": "K steps recorded into one launch graph, one replay timed with CUDA events, max over ranks; "
+                      "the five formats of a step evict each other from L2 (sum of arrays > L2 up to 8 ranks)"}
+
+
+def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False, oracle_check=True):
+    """BASELINE configs[4]: power iteration on the 7-point Laplacian, fp64, rows partitioned over the
+    ranks (weak scaling: grid x grid x nz_per_gpu rows per rank; 8 ranks of 400 x 400 x 50 = 400^3).
+    Two formulations run for the SAME number of steps from the SAME x0 and must agree:
+      fused      SELL kernel + halo-limited peer stores + one 256-byte all-reduce (the product path)
+      allgather  CSR SpMV, sum of squares, all-reduce, scale, in-place ncclAllGather (what north_star names)
+    Both are issued by the library (b200_iterator_*: launch graph of G steps, NCCL called from C)."""
+    import ctypes as C
+    L = pkg.lib()
+    ctx = pkg.Context(local_rank)
+    nx = ny = args.grid
+    nz = args.nz_per_gpu * world
+    n = nx * ny * nz
+    blocks = pkg.equal_row_blocks(n, world, align=32)
+    lo, hi = blocks.bounds(rank)
+    n_local = hi - lo
+    nnz = L.b200_gen_laplace7_nnz(nx, ny, nz, lo, n_local)
+    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_laplace7_coo(ctx.h, nx, ny, nz, lo, n_local, rows.ptr, cols.ptr, vals.ptr), "gen laplace7")
+    pkg.check(L.b200_offset_i32(ctx.h, rows.ptr, nnz, -lo), "rebase rows")
+    coo = pkg.CooMatrix(ctx, n_local, n, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo)
+    csr.plan()
+    sell = pkg.SellMatrix(csr, np.float64)
+    comm = pkg.Comm(pkg, ctx, rank, world) if world > 1 else None
+    bufs = pkg.PeerBuffers(pkg, ctx, blocks, rank, world)
+    ranges = pkg.exchange_col_ranges(pkg, ctx, coo.cols, lo, world)
+    halo = pkg.halo_rows(ranges, blocks, rank)
+    halo_bytes = 8 * sum(h - l for d, (l, h) in enumerate(zip(*halo)) if d != rank)
+    G = 10
+    K = max(G, min(steps, 200) // G * G)
+    warm = 1 + 2 * G    # step 0 is always direct; two replays record + warm the graph of this parity
+
+    def start_vector():
+        ctx.sync()
+        D.barrier(ctx)
+        pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[0].ptr, n, 11, 0.0, 1.0), "gen x0")
+        bufs.local[1].fill_bytes(0)
+        D.barrier(ctx)
+
+    def run(mode, matrix, h, graph_steps=G):
+        start_vector()
+        it = pkg.Iterator(pkg, ctx, comm, matrix, blocks, rank, world, bufs.ptrs[:2], mode=mode, halo=h,
+                          graph_steps=graph_steps)
+        it.run(warm)
+        D.barrier(ctx)
+        n0 = it.state()[2]
+        e0, e1 = ctx.event(), ctx.event()
+        e0.record()
+        it.run(K)
+        e1.record()
+        D.barrier(ctx)
+        ms = e0.elapsed_ms_until(e1) / K
+        norm = it.norm()
+        launches = it.state()[2] - n0
+        it.close()
+        return ms, norm, launches
+
+    with ClockSampler(local_rank) as clk:
+        fused_ms, fused_norm, fused_launches = run("fused", sell, halo)
+    ag_ms, ag_norm, _ = run("allgather", csr, None)
+    direct_ms, direct_norm, _ = run("fused", sell, halo, graph_steps=0)   # same steps, launch by launch
+    full_ms = None
+    if extras:
+        full_ms, _, _ = run("fused", sell, None)                           # every row to every rank
+
+    # the SpMV kernel by itself (no exchange partner: one destination, its own buffer), same buffers
+    start_vector()
+    one = (C.c_void_p * 1)(bufs.local[1].ptr)
+    acc = ctx.zeros(32, np.float64)
+
+    def kernel_alone():
+        pkg.check(L.b200_spmv_sell_halo_f64(ctx.h, sell.data.ptr, sell.cols.ptr, bufs.local[0].ptr, sell.row_indices.ptr,
+                                            32, sell.n_slices, n_local, None, acc.ptr, one, 1, rank * blocks.count,
+                                            None, None), "spmv alone")
+    for _ in range(3):
+        kernel_alone()
+    a, b = ctx.event(), ctx.event()
+    a.record()
+    for _ in range(20):
+        kernel_alone()
+    b.record()
+    ctx.sync()
+    spmv_ms = a.elapsed_ms_until(b) / 20
+    ycsr = ctx.zeros(n_local, np.float64)
+    for _ in range(3):
+        csr.spmv(bufs.local[0], ycsr)
+    a.record()
+    for _ in range(20):
+        csr.spmv(bufs.local[0], ycsr)
+    b.record()
+    ctx.sync()
+    csr_ms = a.elapsed_ms_until(b) / 20
+
+    # e2e: this rank's block of x0 from pinned host memory, K steps, the norm and the block back to the host
+    hx = C.c_void_p()
+    pkg.check(L.b200_host_alloc_pinned(blocks.count * 8, C.byref(hx)), "pinned x block")
+    start_vector()
+    pkg.check(L.b200_memcpy_d2h(ctx.h, hx, bufs.local[0].ptr + 8 * rank * blocks.count, 8 * blocks.count), "x0 block")
+    it = pkg.Iterator(pkg, ctx, comm, sell, blocks, rank, world, bufs.ptrs[:2], mode="fused", halo=halo, graph_steps=G)
+    it.run(warm)
+    D.barrier(ctx)
+    t0 = time.perf_counter()
+    pkg.check(L.b200_memcpy_h2d_async(ctx.h, it.state()[1] + 8 * rank * blocks.count, hx, 8 * blocks.count), "h2d x block")
+    it.run(K)
+    e2e_norm = it.norm()
+    pkg.check(L.b200_memcpy_d2h(ctx.h, hx, it.state()[1] + 8 * rank * blocks.count, 8 * blocks.count), "d2h x block")
+    D.barrier(ctx)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    it.close()
+    L.b200_host_free_pinned(hx)
+
+    fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms = D.reduce([fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms], "max")
+    (nnz_total,) = D.reduce([nnz], "sum")
+    (halo_max,) = D.reduce([halo_bytes], "max")
+    if full_ms is not None:
+        (full_ms,) = D.reduce([full_ms], "max")
+    norms = D.reduce([fused_norm, ag_norm, direct_norm, -fused_norm, -ag_norm], "max")
+    same_on_all_ranks = norms[0] == -norms[3] and norms[1] == -norms[4]
+    rel = abs(fused_norm - ag_norm) / abs(ag_norm)
+    rel_direct = abs(fused_norm - direct_norm) / abs(ag_norm)
+    parity_ok = bool(rel <= 1e-10 and rel_direct <= 1e-10 and same_on_all_ranks)
+    peak, peak_src = measured_peak()
+    alg = sell.nbytes(np.float64)
+    flops = 2.0 * nnz_total
+    out = {
+        "ms_per_step": round(fused_ms, 5), "value": round(flops / (fused_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
+        "steps": K, "warmup": warm, "n_gpus": world, "scaling": "weak",
+        "workload": f"power iteration, 7-point Laplacian {nx}x{ny}x{nz} = {n} rows, {int(nnz_total)} nnz, fp64, "
+                    f"{world} row block(s) of {n_local} rows",
+        "exchange": "fused: SELL-32 kernel stores each y row into the x buffers of the ranks that read it (own block + "
+                    "halo planes, CUDA IPC peer memory) + one 256-byte ncclAllReduce per step; all issued by "
+                    f"b200_iterator_run as a launch graph of {G} steps",
+        "halo_bytes_sent_per_step_max_rank": int(halo_max),
+        "gpu_launches": int(fused_launches),
+        "direct_launches_no_graph": {"ms_per_step": round(direct_ms, 5)},
+        "nccl_allgather_formulation": {"ms_per_step": round(ag_ms, 5), "gflops": round(flops / (ag_ms * 1e-3) * 1e-9, 2),
+                                       "what": "CSR SpMV into the rank's segment, sum of squares, 1-element all-reduce, "
+                                               "scale, in-place ncclAllGather; same launch-graph replay"},
+        "fused_full_broadcast": None if full_ms is None else {"ms_per_step": round(full_ms, 5)},
+        "norm_fused": fused_norm, "norm_allgather": ag_norm, "norm_fused_direct": direct_norm,
+        "rel_diff": rel, "parity_tol": 1e-10, "parity_ok": parity_ok,
+        "parity": "same x0 (seeded), same step count in every run; |norm_fused - norm_allgather| <= 1e-10 * norm, the "
+                  "graph replay equals the launch-by-launch run, every rank holds the same norms",
+        "split_ms": {"spmv_kernel_alone": round(spmv_ms, 5), "exchange_and_norm": round(max(fused_ms - spmv_ms, 0.0), 5),
+                     "csr_stream_kernel_alone": round(csr_ms, 5)},
+        "roofline": {"bound": "hbm", "kernel": "sell32 fused (alone)", "achieved": round(alg / (spmv_ms * 1e-3) * 1e-9, 1),
+                     "peak": peak, "unit": "GB/s", "frac": round(alg / (spmv_ms * 1e-3) * 1e-9 / peak, 4),
+                     "alg_bytes": int(alg), "traffic": ncu_traffic("laplace-iter", "f64", "sell_fused", n_local),
+                     "peak_source": peak_src},
+        "e2e": {"value": round(flops / (e2e_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "ms_per_step": round(e2e_ms, 5),
+                "h2d_bytes_per_step": int(8 * blocks.count * world / K), "d2h_bytes_per_step": int((8 * blocks.count + 8) * world / K),
+                "norm": e2e_norm,
+                "what": f"per rank: its x block from pinned host memory -> device, {K} steps, the norm and the block back "
+                        "to pinned host memory; wall clock / steps, max over ranks"},
+        "clocks": clk.summary(),
+    }
+    if not parity_ok:
+        out["parity_failure"] = {"rel_fused_vs_allgather": rel, "rel_graph_vs_direct": rel_direct,
+                                 "same_on_all_ranks": same_on_all_ranks}
+
+    # N = 1: the same code on an 80^3 grid against the CPU restatement (SURVEY 8d config 5); the
+    # restatement's timing is the section's cpu_baseline
+    if oracle_check and world == 1 and rank == 0 and not args.no_cpu_baseline:
+        out["oracle_80cubed"] = iterated_oracle_check(pkg, ctx)
+    bufs.close()
+    if comm:
+        comm.close()
+    ctx.close()
+    return out
+
+
+def iterated_oracle_check(pkg, ctx, g=80, steps=50):
+    """Power iteration on a g^3 Laplacian: the library's fused iterator on the GPU vs the CPU
+    restatement (oracle CSR SpMV + numpy norm), same x0 (the generators have bit-identical host twins)."""
+    from oracle import binding as O
+    L = pkg.lib()
+    n = g * g * g
+    nnz = L.b200_gen_laplace7_nnz(g, g, g, 0, n)
+    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_laplace7_coo(ctx.h, g, g, g, 0, n, rows.ptr, cols.ptr, vals.ptr), "gen laplace7")
+    coo = pkg.CooMatrix(ctx, n, n, rows, cols, vals)
+    sell = pkg.SellMatrix(pkg.CsrMatrix(coo), np.float64)
+    blocks = pkg.equal_row_blocks(n, 1)
+    x0 = np.zeros(blocks.padded)
+    pkg.check(L.b200_gen_uniform_f64_host(x0.ctypes.data, n, 11, 0.0, 1.0), "gen x0 host")
+    b = [ctx.array(x0), ctx.zeros(blocks.padded, np.float64)]
+    it = pkg.Iterator(pkg, ctx, None, sell, blocks, 0, 1, [[b[0].ptr], [b[1].ptr]], mode="fused", graph_steps=10)
+    it.run(steps)
+    gpu_norm = it.norm()
+    it.close()
+    rh, ch, vh = rows.download(), cols.download(), vals.download()
+    O.lib().orc_set_threads(os.cpu_count() or 1)
+    ptr, _ = O.build_csr(n, rh)
+    x = x0[:n].copy()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = O.spmv_csr(n, ptr, ch, vh, x)
+        cpu_norm = float(np.linalg.norm(y))
+        x = y / cpu_norm
+    sec = time.perf_counter() - t0
+    rel = abs(gpu_norm - cpu_norm) / cpu_norm
+    return {"grid": f"{g}^3", "steps": steps, "norm_gpu": gpu_norm, "norm_cpu_oracle": cpu_norm, "rel_diff": rel,
+            "ok": bool(rel <= 1e-10),
+            "cpu_baseline": {"value": round(2.0 * nnz * steps / sec * 1e-9, 3), "unit": "GFLOP/s",
+                             "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": f"{steps} power-iteration steps on the {g}^3 Laplacian ({nnz} nnz), oracle CSR SpMV "
+                                       "(-O3, OpenMP) + numpy norm"}}
+
+
+def ncu_traffic(workload, dname, kernel, n_rows):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload
+    (profiles/ncu_traffic.json); None for workloads / sizes that were not captured."""
+    try:
+        cap = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        for c in cap if isinstance(cap, list) else [cap]:
+            if c["workload"] == workload and c["dtype"] == dname and c.get("rows", 2097152) == n_rows:
+                return c["traffic_bytes"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     capture_stdout()
     ap = argparse.ArgumentParser()
@@ -312,9 +768,12 @@ def main():
     ap.add_argument("--rmat-edge-factor", type=int, default=16)
     ap.add_argument("--rmat-max-sell-bytes", type=float, default=24e9,
                     help="rmat: skip running a SELL variant whose padded arrays exceed this")
-    ap.add_argument("--grid", type=int, default=400, help="laplace-iter: nx = ny")
-    ap.add_argument("--nz-per-gpu", type=int, default=50, help="laplace-iter: z planes per rank")
-    ap.add_argument("--iter-format", default="csr", choices=["csr", "sell"])
+    ap.add_argument("--rmat-sigmas", default="1,32,256,4096,65536,R")
+    ap.add_argument("--l2-persist", type=int, default=None, choices=[0, 1],
+                    help="pin x in L2 with an access-policy window (default: on for banded/cant, A/B reported for rmat)")
+    ap.add_argument("--grid", type=int, default=400, help="laplace-iter / iterated: nx = ny")
+    ap.add_argument("--nz-per-gpu", type=int, default=50, help="laplace-iter / iterated: z planes per rank")
+    ap.add_argument("--iter-extras", action="store_true", help="laplace-iter: also time the full-broadcast variant")
     ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
     ap.add_argument("--rows-per-gpu", type=int, default=2097152)
     ap.add_argument("--cant-copies", type=int, default=7,
@@ -322,6 +781,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="banded: skip the fp64 pass and the `strong` / `iterated` sections (kernel A/B runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -330,7 +791,6 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dtype = np.dtype(np.float32 if (args.dtype or ("f32" if args.workload == "banded" else "f64")) == "f32"
                      else np.float64)
-    dname = "f32" if dtype == np.float32 else "f64"
 
     from __graft_entry__ import load_package
     pkg = load_package()
@@ -339,18 +799,20 @@ def main():
         if rank != 0:
             return 0
         return reference_arm(pkg, args, dtype)
+    if world > 1:
+        bind_to_gpu_numa(local_rank)
     if args.workload == "laplace-iter":
         return laplace_iter_arm(pkg, args, rank, world, local_rank)
     if args.workload == "rmat":
         return rmat_arm(pkg, args, rank, world, local_rank)
+    return spmv_arm(pkg, args, rank, world, local_rank, dtype)
 
-    # ---------------- the B200 arm ----------------
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+def spmv_arm(pkg, args, rank, world, local_rank, dtype):
+    """The default line: one SpMV in each of the five formats per step (banded = BASELINE configs[2],
+    weak scaling; cant = configs[1])."""
+    dname = "f32" if dtype == np.float32 else "f64"
+    D = Dist(world, local_rank)
     ctx = pkg.Context(local_rank)
     L = pkg.lib()
 
@@ -369,15 +831,14 @@ def main():
         workload = "cant-shaped stand-in (BASELINE configs[1]): 62451 x 62451, 4325625 nnz, x = ramp"
     nnz = coo.nnz
 
-    def build_set(coo_m):
-        allm = pkg.build_all(coo_m, dtype)
+    def build_set(coo_m, dt=dtype):
+        allm = pkg.build_all(coo_m, dt)
         allm["csr"].plan()
         # "ell" = the kernel on the reference's row-major arrays (fastest ELL kernel on B200); the
         # column-major thread-per-row kernel is measured next to it
         # "cmrs_packed" = the derived 4+V bytes/entry layout (row_in_strip folded into the column word),
         # measured next to the reference two-array layout, never in the headline
-        return ({"coo": allm["coo"], "csr": allm["csr"], "ell": allm["ell"], "sell": allm["sell"],
-                 "cmrs": allm["cmrs"]}, {"ell_colmajor": allm["ellcm"], "cmrs_packed": allm["cmrs"].packed()})
+        return ({f: allm[f] for f in FORMATS}, {"ell_colmajor": allm["ellcm"], "cmrs_packed": allm["cmrs"].packed()})
 
     # The cant-shaped formats (53-70 MB each) fit in the 126 MB L2.  "Inputs larger than L2" is
     # restored by ROTATION: n_copies independent copies of every format's arrays (own COO triples,
@@ -391,7 +852,9 @@ def main():
     mats, extra = sets[0]
     y = {f: ctx.zeros(n_rows, dtype) for f in list(mats) + list(extra)}
     bytes_alg = {f: m.nbytes(dtype) for f, m in {**mats, **extra}.items()}
-    ctx.set_l2_persist(x)
+    l2_persist = args.l2_persist != 0
+    if l2_persist:
+        ctx.set_l2_persist(x)
     ctx.sync()
     launch_no = [0]
 
@@ -403,37 +866,9 @@ def main():
     # launch (leaves the L2 full of DIRTY lines whose write-back competes with the kernel's reads)
     flush = ctx.empty(256 << 20, np.uint8) if args.workload == "cant" else None
 
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            import torch
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-
     overlap = None
     if n_copies == 1:
-        for _ in range(args.warmup):
-            for f in mats:
-                mats[f].spmv(x, y[f])
-        barrier()
-
-        # timed region: K steps; per-format events inside, whole-region events outside
-        ev = {f: [(ctx.event(), ctx.event()) for _ in range(args.steps)] for f in mats}
-        e0, e1 = ctx.event(), ctx.event()
-        with ClockSampler(local_rank) as clk:
-            barrier()
-            e0.record()
-            for s in range(args.steps):
-                for f, m in mats.items():
-                    ev[f][s][0].record()
-                    m.spmv(x, y[f])
-                    ev[f][s][1].record()
-            e1.record()
-            barrier()
-        total_ms = e0.elapsed_ms_until(e1)
-        per_ms = {f: float(np.mean([a.elapsed_ms_until(b) for a, b in ev[f]])) for f in mats}
-        step_ms = total_ms / args.steps
+        step_ms, per_ms, clk = time_formats(ctx, D, mats, x, y, args.steps, args.warmup, local_rank)
     else:
         # A cant-sized SpMV lasts ~10 us, less than this Python loop needs to issue one launch, so the
         # launches are recorded into CUDA graphs (b200_graph_*) and replayed:
@@ -453,6 +888,18 @@ def main():
                     next_set()[which][f].spmv(x, y[f])
             return g
 
+        def time_graph(g, reps, per):
+            g.launch()
+            out = []
+            for _ in range(reps):
+                a, b = ctx.event(), ctx.event()
+                a.record()
+                g.launch()
+                b.record()
+                ctx.sync()
+                out.append(a.elapsed_ms_until(b) / per)
+            return float(np.mean(out))
+
         for f in mats:  # un-graphed pass over every copy first: loads the kernels, warms the plans
             for st in sets:
                 st[0][f].spmv(x, y[f])
@@ -463,24 +910,13 @@ def main():
         e0, e1 = ctx.event(), ctx.event()
         with ClockSampler(local_rank) as clk:
             g_warm.launch()
-            barrier()
+            D.barrier(ctx)
             e0.record()
             g_steps.launch()
             e1.record()
-            barrier()
+            D.barrier(ctx)
             total_ms = e0.elapsed_ms_until(e1)
-            per_ms = {}
-            for f in mats:
-                g_fmt[f].launch()
-                reps = []
-                for _ in range(5):
-                    a, b = ctx.event(), ctx.event()
-                    a.record()
-                    g_fmt[f].launch()
-                    b.record()
-                    ctx.sync()
-                    reps.append(a.elapsed_ms_until(b) / n_f)
-                per_ms[f] = float(np.mean(reps))
+            per_ms = {f: time_graph(g_fmt[f], 5, n_f) for f in mats}
         step_ms = total_ms / args.steps
 
         # the same graphs recorded with launch overlap on (b200_ctx_set_launch_overlap: programmatic
@@ -491,25 +927,15 @@ def main():
         g_fmt_o = {f: record_format(f, 0, n_f) for f in mats}
         ctx.set_launch_overlap(False)
         g_steps_o.launch()
-        barrier()
+        D.barrier(ctx)
         e0.record()
         g_steps_o.launch()
         e1.record()
-        barrier()
-        overlap = {"ms_per_step": e0.elapsed_ms_until(e1) / args.steps, "formats": {}}
-        for f in mats:
-            g_fmt_o[f].launch()
-            reps = []
-            for _ in range(5):
-                a, b = ctx.event(), ctx.event()
-                a.record()
-                g_fmt_o[f].launch()
-                b.record()
-                ctx.sync()
-                reps.append(a.elapsed_ms_until(b) / n_f)
-            overlap["formats"][f] = float(np.mean(reps))
+        D.barrier(ctx)
+        overlap = {"ms_per_step": e0.elapsed_ms_until(e1) / args.steps,
+                   "formats": {f: time_graph(g_fmt_o[f], 5, n_f) for f in mats}}
 
-    # extra (untimed for the headline): the column-major ELL kernel, same method
+    # extra (untimed for the headline): the column-major ELL kernel and packed CMRS, same method
     for f in extra:
         if n_copies == 1:
             for _ in range(3):
@@ -524,14 +950,7 @@ def main():
         else:
             for st in sets:
                 st[1][f].spmv(x, y[f])
-            g = record_format(f, 1, n_f)
-            g.launch()
-            a, b = ctx.event(), ctx.event()
-            a.record()
-            g.launch()
-            b.record()
-            ctx.sync()
-            per_ms[f] = a.elapsed_ms_until(b) / n_f
+            per_ms[f] = time_graph(record_format(f, 1, n_f), 1, n_f)
 
     # context for the L2-sized workload, never in the headline: (1) the previous methodology, a
     # 256 MiB memset before every launch; (2) the same arrays back to back, L2-resident (what an
@@ -560,133 +979,57 @@ def main():
             ms = a.elapsed_ms_until(b) / 20
             warm[f] = {"ms": round(ms, 5), "gbs_algorithmic": round(bytes_alg[f] / (ms * 1e-3) * 1e-9, 1)}
 
-    if dist is not None:
-        import torch
-        t = torch.tensor([step_ms] + [per_ms[f] for f in mats], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t[0])
-        for i, f in enumerate(mats):
-            per_ms[f] = float(t[1 + i])
+    red = D.reduce([step_ms] + [per_ms[f] for f in mats], "max")
+    step_ms = red[0]
+    for i, f in enumerate(mats):
+        per_ms[f] = red[1 + i]
 
     peak, peak_src = measured_peak()
     flops_step = 2.0 * nnz * len(mats) * world
     value = flops_step / (step_ms * 1e-3) * 1e-9
-    fm = {}
-    for f in list(mats) + list(extra):
-        gbs = bytes_alg[f] / (per_ms[f] * 1e-3) * 1e-9
-        fm[f] = {"ms": round(per_ms[f], 5), "gflops": round(2.0 * nnz / (per_ms[f] * 1e-3) * 1e-9, 2),
-                 "alg_bytes": int(bytes_alg[f]), "gbs": round(gbs, 1),
-                 "frac_measured": round(gbs / peak, 4), "frac_nominal_8TBs": round(gbs / NOMINAL_HBM_GBS, 4)}
+    fm = format_table(list(mats) + list(extra), per_ms, bytes_alg, nnz, peak)
     dom = max(mats, key=lambda f: per_ms[f])
-    # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this very
-    # workload (profiles/ncu_traffic.json); null for workloads that were not captured
-    traffic = None
-    try:
-        cap = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-        for c in cap if isinstance(cap, list) else [cap]:
-            if c["workload"] == args.workload and c["dtype"] == dname and world == 1 and c.get("rows", 2097152) == n_rows:
-                traffic = c["traffic_bytes"].get(dom)
-    except Exception:
-        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": fm[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": fm[dom]["frac_measured"], "traffic": traffic, "peak_source": peak_src,
-                "per_format_frac": {f: fm[f]["frac_measured"] for f in mats}}
+                "frac": fm[dom]["frac_measured"],
+                "traffic": ncu_traffic(args.workload, dname, dom, n_rows) if world == 1 else None,
+                "peak_source": peak_src, "per_format_frac": {f: fm[f]["frac_measured"] for f in mats}}
 
     # ---------------- e2e: host x in, host y out, through the C ABI, matrix resident ----------
     e2e = None
+    col_lo, col_hi = column_range(pkg, ctx, coo.cols)
+    steps_e = max(3, min(args.steps, 20))
     if not args.no_e2e:
-        import ctypes as C
-        V = dtype.itemsize
-        hx, hy = C.c_void_p(), C.c_void_p()
-        pkg.check(L.b200_host_alloc_pinned(n_cols * V, C.byref(hx)), "pinned x")
-        pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy)), "pinned y")
-        x_host = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(n_cols * V,)).view(dtype)
-        x_host[:] = x.download()
-        xin = ctx.empty(n_cols, dtype)
-        steps_e = max(3, min(args.steps, 20))
+        e2e = measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col_hi, dtype, steps_e, flops_step)
 
-        def e2e_step():
-            for f, m in mats.items():
-                pkg.check(L.b200_memcpy_h2d_async(ctx.h, xin.ptr, hx, n_cols * V), "h2d x")
-                m.spmv(xin, y[f])
-                pkg.check(L.b200_memcpy_d2h_async(ctx.h, hy, y[f].ptr, n_rows * V), "d2h y")
-            ctx.sync()
-
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        a, b = ctx.event(), ctx.event()
-        a.record()
-        for _ in range(steps_e):
-            e2e_step()
-        b.record()
-        barrier()
-        e2e_ms = a.elapsed_ms_until(b) / steps_e
-        wall_ms = (time.perf_counter() - t0) * 1e3 / steps_e
-        if dist is not None:
-            import torch
-            t = torch.tensor([e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms, wall_ms = float(t[0]), float(t[1])
-        # the same five calls issued on TWO in-order queues (contexts) of the same device, formats
-        # alternating: PCIe is full duplex, so the y download of one call overlaps the x upload and
-        # kernel of the next.  Wall clock with both queues drained on both sides (events live on one
-        # stream only).
-        ctx2 = pkg.Context(local_rank)
-        hx2, hy2 = C.c_void_p(), C.c_void_p()
-        pkg.check(L.b200_host_alloc_pinned(n_cols * V, C.byref(hx2)), "pinned x2")
-        pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy2)), "pinned y2")
-        C.memmove(hx2, hx, n_cols * V)
-        xin2 = ctx2.empty(n_cols, dtype)
-        queues = [(ctx, xin, hx, hy), (ctx2, xin2, hx2, hy2)]
-        owner = {f: queues[i % 2] for i, f in enumerate(mats)}
-
-        def e2e_step2():
-            for f, m in mats.items():
-                q, xq, hxq, hyq = owner[f]
-                m.ctx = q
-                pkg.check(L.b200_memcpy_h2d_async(q.h, xq.ptr, hxq, n_cols * V), "h2d x")
-                m.spmv(xq, y[f])
-                pkg.check(L.b200_memcpy_d2h_async(q.h, hyq, y[f].ptr, n_rows * V), "d2h y")
-            ctx.sync()
-            ctx2.sync()
-
-        for _ in range(2):
-            e2e_step2()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps_e):
-            e2e_step2()
-        barrier()
-        wall2_ms = (time.perf_counter() - t0) * 1e3 / steps_e
-        for m in mats.values():
-            m.ctx = ctx
-        if dist is not None:
-            import torch
-            t = torch.tensor([wall2_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            wall2_ms = float(t[0])
-        best_ms = min(e2e_ms, wall2_ms)
-        e2e = {"value": round(flops_step / (best_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
-               "h2d_bytes_per_step": int(len(mats) * n_cols * V * world),
-               "d2h_bytes_per_step": int(len(mats) * n_rows * V * world),
-               "ms_per_step": round(best_ms, 4), "steps": steps_e,
-               "one_queue": {"ms_per_step": round(e2e_ms, 4), "wall_ms_per_step": round(wall_ms, 4),
-                             "gflops": round(flops_step / (e2e_ms * 1e-3) * 1e-9, 2)},
-               "two_queues": {"wall_ms_per_step": round(wall2_ms, 4),
-                              "gflops": round(flops_step / (wall2_ms * 1e-3) * 1e-9, 2)},
-               "what": "per format: pinned-host x -> device, SpMV through the C ABI, y -> pinned host; format "
-                       "arrays uploaded once before the timed region, as the reference driver does (csr.c:183-193). "
-                       "value = the better of one in-order queue (CUDA events) and two queues with alternating "
-                       "formats (wall clock, both drained)"}
-        ctx2.sync()
-        del xin2
-        L.b200_host_free_pinned(hx)
-        L.b200_host_free_pinned(hy)
-        L.b200_host_free_pinned(hx2)
-        L.b200_host_free_pinned(hy2)
-        ctx2.close()
+    # ---------------- fp64 pass over the same matrix (the reference's own arithmetic) ----------
+    f64 = None
+    if args.workload == "banded" and dtype == np.float32 and not args.no_extras:
+        del sets, extra
+        for f in FORMATS:
+            if f not in ("coo", "csr"):
+                mats[f] = None       # release the fp32 ELL / SELL copies before building the fp64 ones
+        d64 = np.dtype(np.float64)
+        m64, _ = build_set(coo, d64)
+        x64 = ctx.empty(n_cols, d64)
+        pkg.check(L.b200_gen_uniform_f64(ctx.h, x64.ptr, n_cols, BANDED["x_seed"], 0.0, 1.0), "gen x")
+        y64 = {f: ctx.zeros(n_rows, d64) for f in m64}
+        if l2_persist:
+            ctx.set_l2_persist(x64)
+        k64 = max(10, min(args.steps, 50))
+        s64, p64, _ = time_formats(ctx, D, m64, x64, y64, k64, args.warmup)
+        red = D.reduce([s64] + [p64[f] for f in m64], "max")
+        s64 = red[0]
+        for i, f in enumerate(m64):
+            p64[f] = red[1 + i]
+        b64 = {f: m.nbytes(d64) for f, m in m64.items()}
+        f64 = {"value": round(flops_step / (s64 * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "ms_per_step": round(s64, 5),
+               "steps": k64, "dtype": "f64", "formats": format_table(list(m64), p64, b64, nnz, peak),
+               "what": "the same matrix and step in fp64, the reference's only arithmetic (what --impl reference times)"}
+        if not args.no_e2e:
+            f64["e2e"] = measure_e2e(pkg, ctx, D, local_rank, m64, y64, x64, n_rows, n_cols, col_lo, col_hi, d64,
+                                     steps_e, flops_step)
+        del m64, y64, x64
+        ctx.set_l2_persist(None)
 
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ---------
     cpu = None
@@ -703,6 +1046,14 @@ def main():
                "cores": threads, "cpu_model": cpu_model(), "omp_wait_policy": os.environ.get("OMP_WAIT_POLICY"),
                "kind": kind, "dtype": cdt, "sample": sample, "per_format_gflops": detail}
 
+    # ---------------- the sections only a multi-GPU run can fill with meaning ------------------
+    strong = iterated = None
+    if args.workload == "banded" and not args.no_extras:
+        del mats, y, coo, x
+        strong = strong_section(pkg, ctx, D, args, rank, world, dtype, peak)
+        ctx.sync()
+        iterated = iterated_section(pkg, D, args, rank, world, local_rank, min(args.steps, 100))
+
     if rank == 0:
         out = {
             "metric": "SpMV GFLOP/s, aggregate over the five formats (COO, CSR, ELL, SELL-32, CMRS); "
@@ -710,9 +1061,10 @@ def main():
             "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dname, "data": "synthetic",
-            "config": {"workload": workload, "formats": list(mats), "nnz_per_gpu": int(nnz),
+            "config": {"workload": workload, "formats": list(FORMATS), "nnz_per_gpu": int(nnz),
                        "rows_per_gpu": int(n_rows), "cols": int(n_cols),
                        "partition": f"row blocks, {world} rank(s), x replicated, no collective",
+                       "l2_persist_x": bool(l2_persist),
                        "cache": (f"inputs larger than L2 by rotation: {n_copies} independent copies of every format's "
                                  f"arrays ({min(bytes_alg.values()) >> 20}-{max(bytes_alg.values()) >> 20} MiB each), launch i "
                                  f"reads copy i mod {n_copies}; no flush; the K steps are one CUDA-graph replay" if n_copies > 1 else
@@ -727,12 +1079,11 @@ def main():
                             for f, ms in overlap["formats"].items()}}),
             "formats_flush_each_launch_context_only": flushed,
             "formats_warm_l2_context_only": warm, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(args.steps * len(mats)), "clocks": clk.summary(),
+            "f64": f64, "strong": strong, "iterated": iterated,
+            "gpu_launches": int(args.steps * len(FORMATS)), "clocks": clk.summary(),
         }
         emit_json(out)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     ctx.close()
     return 0
 
@@ -742,17 +1093,13 @@ def rmat_arm(pkg, args, rank, world, local_rank):
     removal), fp32, CSR vs SELL-32-sigma sweep (+ COO, CMRS), rows partitioned nnz-balanced over the
     ranks (STRONG scaling: the global matrix is fixed), x replicated, no collective."""
     import ctypes as C
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D = Dist(world, local_rank)
     ctx = pkg.Context(local_rank)
     L = pkg.lib()
     scale, ef, abc, seed = args.rmat_scale, args.rmat_edge_factor, (0.57, 0.19, 0.19), 5
     n = 1 << scale
     dtype = np.dtype(np.float32 if (args.dtype or "f32") == "f32" else np.float64)
+    V = dtype.itemsize
 
     def candidates(r0, cnt):
         c = C.c_longlong(0)
@@ -791,24 +1138,16 @@ def rmat_arm(pkg, args, rank, world, local_rank):
     info, st = csr.plan_info(), csr.row_stats()
     y = ctx.zeros(n_rows, dtype)
 
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            import torch
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-
     def time_mat(m):
         for _ in range(args.warmup):
             m.spmv(x, y)
-        barrier()
+        D.barrier(ctx)
         a, b = ctx.event(), ctx.event()
         a.record()
         for _ in range(args.steps):
             m.spmv(x, y)
         b.record()
-        barrier()
+        D.barrier(ctx)
         return a.elapsed_ms_until(b) / args.steps
 
     peak, peak_src = measured_peak()
@@ -820,20 +1159,34 @@ def rmat_arm(pkg, args, rank, world, local_rank):
         results[name] = dict(ms=ms, alg_bytes=int(alg), nnz=int(nnz), **(extra or {}))
         order.append(name)
 
+    # x (n * V bytes: 64 MB in fp32) fits the 126 MB L2: pin it with an access-policy window
+    # (b200_ctx_set_l2_persist) unless --l2-persist 0; the A/B against the unpinned run is reported
+    persist = args.l2_persist != 0
+    cmrs = pkg.CmrsMatrix(csr)
+    ab = {}
     with ClockSampler(local_rank) as clk:
+        ctx.set_l2_persist(None)
+        for name, m in (("csr", csr), ("coo", coo), ("cmrs", cmrs)):
+            ab[name] = {"no_persist_ms": time_mat(m)}
+        if persist:
+            ctx.set_l2_persist(x)
         record("csr", csr)
         record("coo", coo)
-        record("cmrs", pkg.CmrsMatrix(csr))
-        for sigma in (1, 32, 256, 4096, 65536, n_rows):
+        record("cmrs", cmrs)
+        for name in ab:
+            ab[name]["persist_ms" if persist else "no_persist_again_ms"] = results[name]["ms"]
+        record("cmrs_packed", cmrs.packed())
+        for tok in [t for t in args.rmat_sigmas.split(",") if t]:
+            sigma = n_rows if tok == "R" else int(tok)
             total = C.c_longlong(0)
             sp = ctx.empty(L.b200_sell_num_slices(n_rows, 32) + 1, np.int64)
             perm = ctx.empty(n_rows, np.int32)
             pkg.check(L.b200_build_sell_ptr(ctx.h, csr.ptr.ptr, n_rows, 32, sigma, perm.ptr, sp.ptr,
                                             C.byref(total)), "sell ptr")
-            name = f"sell_sigma{sigma if sigma != n_rows else 'R'}"
+            name = f"sell_sigma{tok}"
             pad = total.value / max(nnz, 1)
             del sp, perm
-            if total.value * (4 + dtype.itemsize) > args.rmat_max_sell_bytes:
+            if total.value * (4 + V) > args.rmat_max_sell_bytes:
                 results[name] = dict(ms=None, padding_factor=round(pad, 3), skipped="padded arrays exceed --rmat-max-sell-bytes")
                 order.append(name)
                 continue
@@ -842,16 +1195,8 @@ def rmat_arm(pkg, args, rank, world, local_rank):
             del m
     # max over ranks per format, sum of nnz (strong scaling: the job is the whole matrix)
     names = [k for k in order if results[k].get("ms") is not None]
-    ms = np.array([results[k]["ms"] for k in names])
-    tot = np.array([float(nnz)])
-    if dist is not None:
-        import torch
-        t = torch.tensor(ms, device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.cpu().numpy()
-        t2 = torch.tensor(tot, device="cuda", dtype=torch.float64)
-        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
-        tot = t2.cpu().numpy()
+    ms = D.reduce([results[k]["ms"] for k in names], "max")
+    (tot,) = D.reduce([float(nnz)], "sum")
     fm = {}
     for k in order:
         r = results[k]
@@ -860,10 +1205,51 @@ def rmat_arm(pkg, args, rank, world, local_rank):
             continue
         t_ms = float(ms[names.index(k)])
         gbs = r["alg_bytes"] / (r["ms"] * 1e-3) * 1e-9  # this rank's own bytes / own time
-        fm[k] = {"ms": round(t_ms, 5), "gflops": round(2.0 * tot[0] / (t_ms * 1e-3) * 1e-9, 2),
+        fm[k] = {"ms": round(t_ms, 5), "gflops": round(2.0 * tot / (t_ms * 1e-3) * 1e-9, 2),
                  "alg_bytes_rank0": r["alg_bytes"], "gbs_rank0": round(gbs, 1), "frac_measured_rank0": round(gbs / peak, 4)}
         if "padding_factor" in r:
             fm[k]["padding_factor"] = r["padding_factor"]
+
+    # e2e: host x in, host y out through the C ABI (CSR, COO, CMRS), matrix resident
+    e2e = None
+    if not args.no_e2e:
+        mats3 = {"csr": csr, "coo": coo, "cmrs": cmrs}
+        y3 = {f: y for f in mats3}
+        col_lo, col_hi = column_range(pkg, ctx, coo.cols)
+        e2e = measure_e2e(pkg, ctx, D, local_rank, mats3, y3, x, n_rows, n, col_lo, col_hi, dtype,
+                          max(3, min(args.steps, 10)), 2.0 * tot * len(mats3))
+        e2e["formats"] = list(mats3)
+
+    # CPU baseline (rank 0, N = 1): the oracle port's CSR / COO / CMRS on the first rows of the same matrix
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as O
+        sr = min(1 << 20, n_rows)
+        ptr_h = csr.ptr.download(sr + 1)
+        k = int(ptr_h[sr])
+        rh, ch, vh = rows.download(k), cols.download(k), vals.download(k)
+        xh = x.download().astype(np.float64)
+        threads = os.cpu_count() or 1
+        O.lib().orc_set_threads(threads)
+        sp_h, ris_h = O.build_cmrs(sr, rh)
+        v_t, x_t = vh.astype(dtype), xh.astype(dtype)
+        runs = {"csr": lambda: O.spmv_csr(sr, ptr_h, ch, v_t, x_t, dtype=dtype),
+                "coo": lambda: O.spmv_coo(sr, rh, ch, v_t, x_t, dtype=dtype),
+                "cmrs": lambda: O.spmv_cmrs(sr, sp_h, ris_h, ch, v_t, x_t, dtype=dtype)}
+        per = {}
+        for f, run in runs.items():
+            run()
+            best = float("inf")
+            for _ in range(3):
+                t0 = time.perf_counter()
+                run()
+                best = min(best, time.perf_counter() - t0)
+            per[f] = best
+        cpu = {"value": round(2.0 * k / per["csr"] * 1e-9, 3), "unit": "GFLOP/s", "cores": threads, "cpu_model": cpu_model(),
+               "kind": "port", "dtype": "f32" if dtype == np.float32 else "f64",
+               "sample": f"first {sr} rows ({k} nnz) of the same R-MAT matrix, oracle CSR (value), COO and CMRS, best of 3",
+               "per_format_gflops": {f: round(2.0 * k / t * 1e-9, 3) for f, t in per.items()}}
+
     if rank == 0:
         best_sell = min((k for k in names if k.startswith("sell")), key=lambda k: fm[k]["ms"], default=None)
         out = {
@@ -873,205 +1259,51 @@ def rmat_arm(pkg, args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": fm["csr"]["ms"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
             "config": {"workload": f"R-MAT power-law (BASELINE configs[3]): scale {scale} = {n} rows, edge factor {ef}, "
-                                   f"(a,b,c,d)=(0.57,0.19,0.19,0.05), diagonal added, duplicates removed: {int(tot[0])} nnz; "
+                                   f"(a,b,c,d)=(0.57,0.19,0.19,0.05), diagonal added, duplicates removed: {int(tot)} nnz; "
                                    f"{world} nnz-balanced row block(s), x replicated, no collective",
                        "rank0": {"rows": int(n_rows), "nnz": int(nnz), "mean_len": round(info.mean_len, 2),
                                  "max_len": int(st.max_len), "csr_kernel": "nnz-split stream" if info.stream_tiles else
                                  f"vector, {info.lanes_per_row} lanes/row + {info.n_long_rows} long rows"},
-                       "ell": f"not run: K = longest row = {int(st.max_len)} would need {n_rows * st.max_len * (4 + dtype.itemsize) / 1e12:.1f} TB",
+                       "ell": f"not run: K = longest row = {int(st.max_len)} would need {n_rows * st.max_len * (4 + V) / 1e12:.1f} TB",
+                       "l2_persist_x": bool(persist),
                        "cache": "inputs larger than L2, no flush"},
             "formats": fm, "best_sell": best_sell,
+            "l2_persist_ab_rank0": {k: {kk: round(vv, 5) for kk, vv in v.items()} for k, v in ab.items()},
             "roofline": {"bound": "hbm", "kernel": "csr", "achieved": fm["csr"]["gbs_rank0"], "peak": peak, "unit": "GB/s",
-                         "frac": fm["csr"]["frac_measured_rank0"], "traffic": None, "peak_source": peak_src},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": int(args.steps * len(names)), "clocks": clk.summary(),
+                         "frac": fm["csr"]["frac_measured_rank0"],
+                         "traffic": ncu_traffic("rmat", "f32" if dtype == np.float32 else "f64", "csr", n_rows) if world == 1 else None,
+                         "peak_source": peak_src,
+                         "note": "the x gather is random: this workload is bound by L1/L2 sector traffic of the gather, not "
+                                 "by HBM (profiles/r2_ncu_rmat_summary.md)"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(args.steps * len(names)), "clocks": clk.summary(),
         }
         emit_json(out)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     ctx.close()
     return 0
 
 
 def laplace_iter_arm(pkg, args, rank, world, local_rank):
-    """BASELINE configs[4]: iterated SpMV (power iteration) on the 7-point Laplacian, fp64, rows
-    partitioned over the ranks, NCCL all-gather of x once per step.  Weak scaling: every rank owns
-    grid x grid x nz_per_gpu rows (400 x 400 x 50 = 8 M rows, 55.7 M nnz); 8 ranks = 400^3."""
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = pkg.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
-    L = pkg.lib()
-    nx = ny = args.grid
-    nz = args.nz_per_gpu * world
-    n = nx * ny * nz
-    blocks = pkg.equal_row_blocks(n, world, align=32)
-    lo, hi = blocks.bounds(rank)
-    n_local = hi - lo
-    nnz = L.b200_gen_laplace7_nnz(nx, ny, nz, lo, n_local)
-    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
-    pkg.check(L.b200_gen_laplace7_coo(ctx.h, nx, ny, nz, lo, n_local, rows.ptr, cols.ptr, vals.ptr), "gen laplace7")
-    pkg.check(L.b200_offset_i32(ctx.h, rows.ptr, nnz, -lo), "rebase rows")
-    coo = pkg.CooMatrix(ctx, n_local, n, rows, cols, vals)
-    fmt = args.iter_format
-    csr = pkg.CsrMatrix(coo)
-    mat = csr if fmt == "csr" else pkg.SellMatrix(csr, np.float64)
-    if fmt == "csr":
-        csr.plan()
-    x_cur = torch.zeros(blocks.padded, dtype=torch.float64, device="cuda")
-    x_next = torch.zeros_like(x_cur)
-    pkg.check(L.b200_gen_uniform_f64(ctx.h, x_cur.data_ptr(), n, 11, 0.0, 1.0), "gen x0")
-    calls = pkg.gpu_callables(pkg, ctx, mat, n_local)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    res = pkg.power_iteration(x_cur=x_cur, x_next=x_next, rank=rank, blocks=blocks, steps=args.warmup, **calls)
-    x_cur, x_next = (res.x, x_next if res.x is x_cur else x_cur)
-    sync_all()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        sync_all()
-        t0.record()
-        res = pkg.power_iteration(x_cur=x_cur, x_next=x_next, rank=rank, blocks=blocks, steps=args.steps, **calls)
-        t1.record()
-        sync_all()
-    step_ms = t0.elapsed_time(t1) / args.steps
-
-    # fused variant (SELL only): the SpMV kernel stores its y-block into every rank's next-x buffer
-    # over NVLink (CUDA IPC peer pointers); one 1-element all-reduce per step is all that is left
-    fused_ms = None
-    fused_norm = None
-    fused_full_ms = None
-    fused_halo_ms = None
-    ring_ms = None
-    halo_bytes = None
-    if fmt == "sell":
-        bufs = pkg.PeerBuffers(pkg, ctx, blocks, rank, world)
-        # halo-limited exchange (default): every rank learns which of its rows the others read as
-        # columns (min/max column of each block, exchanged once) and the kernel stores only those
-        ranges = pkg.exchange_col_ranges(pkg, ctx, coo.cols, lo, world)
-        halo = pkg.halo_rows(ranges, blocks, rank)
-        halo_bytes = 8 * sum(h - l for d, (l, h) in enumerate(zip(*halo)) if d != rank)
-
-        def fused_run(h):
-            pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[0].ptr, n, 11, 0.0, 1.0), "gen x0")
-            pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[1].ptr, n, 11, 0.0, 1.0), "gen x0")
-            sync_all()
-            r0 = pkg.power_iteration_fused(pkg, ctx, mat, bufs, rank, blocks, args.warmup + (args.warmup % 2), halo=h)
-            sync_all()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            r1 = pkg.power_iteration_fused(pkg, ctx, mat, bufs, rank, blocks, args.steps, first_step=r0.next_step,
-                                           acc=r0.acc, halo=h)
-            f1.record()
-            sync_all()
-            return f0.elapsed_time(f1) / args.steps, r1.norm
-
-        fused_full_ms, _ = fused_run(None)
-        fused_halo_ms, fused_halo_norm = fused_run(halo)
-
-        # ring: no collective call in the loop; flags + partial sums travel through peer memory
-        def ring_run():
-            pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[bufs.ring_step % 2].ptr, n, 11, 0.0, 1.0), "gen x0")
-            sync_all()
-            pkg.power_iteration_ring(pkg, ctx, mat, bufs, rank, blocks, args.warmup + (args.warmup % 2), halo=halo)
-            sync_all()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            r1 = pkg.power_iteration_ring(pkg, ctx, mat, bufs, rank, blocks, args.steps, halo=halo)
-            f1.record()
-            sync_all()
-            return f0.elapsed_time(f1) / args.steps, r1.norm
-
-        ring_ms, ring_norm = ring_run()
-        fused_ms, fused_norm = fused_halo_ms, fused_halo_norm   # the product path
-        bufs.close()
-
-    # split: SpMV alone and the all-gather alone, same buffers (explains the step time)
-    seg = x_next[rank * blocks.count:(rank + 1) * blocks.count]
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10):
-        calls["spmv_local"](x_cur, seg)
-    b.record()
-    sync_all()
-    spmv_ms = a.elapsed_time(b) / 10
-    a.record()
-    for _ in range(10):
-        calls["all_gather_inplace"](x_next, seg)
-    b.record()
-    sync_all()
-    gather_ms = a.elapsed_time(b) / 10
-
-    t = torch.tensor([step_ms, spmv_ms, gather_ms, float(nnz), fused_ms or 0.0, fused_full_ms or 0.0,
-                      float(halo_bytes or 0), ring_ms or 0.0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        step_ms, spmv_ms, gather_ms, nnz_total = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tsum[3])
-        fused_ms = float(tmax[4]) if fused_ms is not None else None
-        fused_full_ms = float(tmax[5]) if fused_full_ms is not None else None
-        halo_bytes = int(tmax[6]) if halo_bytes is not None else None
-        ring_ms = float(tmax[7]) if ring_ms is not None else None
-    else:
-        nnz_total = float(nnz)
-    nccl_ms = step_ms
-    if fused_ms is not None:  # the product path when available; the NCCL formulation is reported next to it
-        step_ms = fused_ms
-    peak, peak_src = measured_peak()
-    alg = mat.nbytes(np.float64)
-    gbs = alg / (spmv_ms * 1e-3) * 1e-9
+    """BASELINE configs[4] as the headline: the `iterated` section of the default line, printed as the
+    line itself (more steps, optionally the full-broadcast variant)."""
+    D = Dist(world, local_rank)
+    it = iterated_section(pkg, D, args, rank, world, local_rank, args.steps, extras=args.iter_extras)
     if rank == 0:
+        oc = it.get("oracle_80cubed")
         out = {
             "metric": "SpMV GFLOP/s inside the power iteration (2*nnz flops per step; step = SpMV + exchange of x "
                       "+ norm all-reduce)",
-            "value": round(2.0 * nnz_total / (step_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 5),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"iterated SpMV (BASELINE configs[4]): 7-point Laplacian {nx}x{ny}x{nz} = {n} rows, "
-                                   f"{int(nnz_total)} nnz, fp64, {fmt.upper()}, {world} row block(s), NCCL all-gather of x per step",
-                       "rows_per_gpu": int(n_local), "nnz_per_gpu": int(nnz),
-                       "cache": "inputs larger than L2 (0.7 GB matrix + 2 x 64 MB x per GPU per world rank), no flush"},
-            "exchange": ("fused, halo-limited: the SpMV kernel stores each y row into the x buffers of the ranks that "
-                         "read it (its own + neighbours) over NVLink (CUDA IPC) + one 256-byte NCCL all-reduce"
-                         if fused_ms is not None else "NCCL all_gather_into_tensor (in place)"),
-            "ring_no_collective": (None if ring_ms is None else
-                                   {"ms_per_step": round(ring_ms, 5),
-                                    "gflops": round(2.0 * nnz_total / (ring_ms * 1e-3) * 1e-9, 2),
-                                    "what": "same halo-limited kernel + a one-warp kernel that hands over ||y||^2 partial "
-                                            "sums and 'step done' flags through peer memory instead of the all-reduce "
-                                            "(b200_spmv_sell_ring_f64); opt-in: measured slower than the all-reduce at "
-                                            "2 GPUs"}),
-            "fused_full_broadcast": (None if fused_full_ms is None else
-                                     {"ms_per_step": round(fused_full_ms, 5),
-                                      "gflops": round(2.0 * nnz_total / (fused_full_ms * 1e-3) * 1e-9, 2),
-                                      "what": "same kernel, every row to every rank (what an all-gather moves)"}),
-            "halo_bytes_sent_per_step_max_rank": halo_bytes,
-            "nccl_allgather_formulation": {"ms_per_step": round(nccl_ms, 5),
-                                           "gflops": round(2.0 * nnz_total / (nccl_ms * 1e-3) * 1e-9, 2),
-                                           "split_ms": {"spmv": round(spmv_ms, 5), "all_gather": round(gather_ms, 5),
-                                                        "other (sumsq, all-reduce, scale)":
-                                                            round(max(nccl_ms - spmv_ms - gather_ms, 0.0), 5)},
-                                           "eigenvalue_estimate": res.norm},
-            "split_ms": {"spmv": round(spmv_ms, 5), "exchange + norm": round(max(step_ms - spmv_ms, 0.0), 5)},
-            "eigenvalue_estimate": fused_norm if fused_ms is not None else res.norm,
-            "roofline": {"bound": "hbm", "kernel": fmt, "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src},
-            "cpu_baseline": None, "e2e": None,
-            "gpu_launches": int(args.steps * (1 if fused_ms is not None else 3)), "clocks": clk.summary(),
+            "value": it["value"], "unit": "GFLOP/s", "n_gpus": world, "steps": it["steps"], "warmup": it["warmup"],
+            "ms_per_step": it["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "iterated SpMV (BASELINE configs[4]): " + it["workload"],
+                       "cache": "inputs larger than L2 (0.7 GB matrix per GPU), no flush"},
+            "iterated": it, "roofline": it["roofline"], "e2e": it["e2e"],
+            "cpu_baseline": oc["cpu_baseline"] if oc else None,
+            "gpu_launches": it["gpu_launches"], "clocks": it["clocks"],
         }
         emit_json(out)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 

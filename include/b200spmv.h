@@ -344,8 +344,8 @@ int b200_partition_rows(const int *ptr_host, int n_rows, int n_parts, int align,
  * sumsq_out (device, zeroed by the caller; NULL = skip), one atomic per block.  SELL-32, reference
  * chunk pointers, no permutation.  The caller orders steps with one small all-reduce of those
  * slots (which it needs anyway for the norm): no other launch is needed per step.
- * Alignment: every dst[i] must be 16-byte aligned and dst_offset even (row pairs travel as one
- * 16-byte store); anything else is rejected with B200_ERR_INVALID_VALUE. */
+ * A warp stores its chunk's 32 rows as one contiguous 256-byte write per destination; dst[i] only
+ * needs the natural 8-byte alignment of a double array (checked: B200_ERR_INVALID_VALUE). */
 #define B200_SUMSQ_SLOTS 32
 int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                              const int *row_indices, int chunk, int n_slices, int n_rows,
@@ -446,7 +446,7 @@ typedef struct {
     int world, rank;
     long long rows_per_rank; /* multiple of 32, >= n_rows: rank r's block sits at r*rows_per_rank of x */
     double *const *x[2];    /* x[b][r]: x buffer b (two alternate) of rank r as THIS process sees it, each
-                             * world*rows_per_rank doubles, 16-byte aligned; x[0][rank] holds the start
+                             * world*rows_per_rank doubles; x[0][rank] holds the start
                              * vector.  B200_ITER_ALLGATHER reads only x[b][rank] */
     const int *halo_lo, *halo_hi; /* FUSED: b200_halo_rows output (world entries); NULL, NULL = every row
                              * to every rank */

@@ -26,6 +26,50 @@ namespace {
 
 constexpr int kBlock = 256;
 
+// Narrow chunks (width <= kNarrowW columns: stencil matrices, 7 columns for the 7-point Laplacian).
+// The 128-bit mapping below gives such a chunk only one or two groups per lane -- a chain of
+// dependent round trips (pointer -> group -> gather -> group -> gather) on a warp that moves 2.7 KB --
+// and its gathers touch 4 columns x 2 lines per instruction.  Here lane L owns row L (the reference's
+// mapping, kernels/Sigma_C.cl:8-15): ALL of the chunk's columns are loaded at once (w coalesced 128-
+// byte index loads and 128/256-byte value loads), then all w gathers (each 32 consecutive rows of one
+// column: 2-3 lines), then the FMAs.  Two round trips per chunk, whatever w; the result is already
+// "lane = row", so the store is one coalesced 128/256-byte write.
+constexpr int kNarrowW = 8;
+
+template <typename T, bool OVL>
+__device__ __forceinline__ T narrow_chunk_dot(const T *__restrict__ dp, const int *__restrict__ ip,
+                                              const T *__restrict__ x, int w, int lane, bool &waited)
+{
+    int c[kNarrowW];
+    T v[kNarrowW];
+#pragma unroll
+    for (int k = 0; k < kNarrowW; ++k) {
+        c[k] = 0;
+        v[k] = T(0);
+        if (k < w) {
+            c[k] = ld_stream(ip + 32 * k + lane);
+            v[k] = ld_stream(dp + 32 * k + lane);
+        }
+    }
+    // 0 at run time (column indices are >= 0), but it makes every gather wait for ALL loads above
+    int hold = 0;
+#pragma unroll
+    for (int k = 0; k < kNarrowW; ++k)
+        hold |= c[k] & (sizeof(T) == 8 ? __double2hiint((double)v[k]) : __float_as_int((float)v[k]));
+    hold >>= 31;
+    pdl_wait_once<OVL>(waited);
+    T xv[kNarrowW];
+#pragma unroll
+    for (int k = 0; k < kNarrowW; ++k) xv[k] = ld_xo<OVL>(x, c[k] + hold);  // unused slots: x[0] * 0
+    T a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < kNarrowW; k += 2) {
+        a0 += v[k] * xv[k];
+        a1 += v[k + 1] * xv[k + 1];
+    }
+    return a0 + a1;
+}
+
 // Columns [seg*wmax, (seg+1)*wmax) of one chunk.  seg == 0 is the main pass (plain store, wmax = 0
 // means the whole chunk); seg > 0 are the extra segments of chunks wider than wmax columns
 // (power-law inputs: a hub row makes one chunk 10^5 columns wide), listed by the plan and
@@ -70,6 +114,13 @@ sell32_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *
         }
         const int *ip = idx + chunk_base;
         const T *dp = data + chunk_base;
+        if (WPC == 1 && !EXTRA && wmax == 0 && n_groups <= 8 * kNarrowW) {  // warp-uniform
+            const T a = narrow_chunk_dot<T, OVL>(dp, ip, x, (int)(n_groups >> 3), lane, waited);
+            pdl_wait_once<OVL>(waited);
+            const long long r = slice * 32 + lane;
+            if (r < n_out) y[perm ? perm[r] : r] = a;
+            return;
+        }
         for (long long g0 = g_begin + 32 * part + lane; g0 < n_groups; g0 += 32 * WPC * U) {
             IVec4 c[U];
             Vec4<T> v[U];
@@ -436,60 +487,53 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     // 1/||x||: one coalesced load of the 32 partial sums per warp, folded with shuffles
     T alpha = 1;
     if (scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
-    T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    T mine = 0;  // row `lane` of this warp's chunk
     if (active) {
         const long long chunk_base = slice_ptr[slice];
         const long long n_groups = ((long long)slice_ptr[slice + 1] - chunk_base) >> 2;
         const int *ip = idx + chunk_base;
         const T *dp = data + chunk_base;
-        // one group per lane and round trip: a 7-point-stencil chunk is only 56 groups, and the
-        // batched form (58 registers) measured slower here (0.196 vs 0.189 ms per step)
+        if (n_groups <= 8 * kNarrowW) {  // warp-uniform: stencil-width chunk, lane = row (see narrow_chunk_dot)
+            bool waited = true;
+            mine = narrow_chunk_dot<T, false>(dp, ip, x, (int)(n_groups >> 3), lane, waited);
+        } else {
+            T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
 #pragma unroll 4
-        for (long long g = lane; g < n_groups; g += 32) {
-            IVec4 c;
-            Vec4<T> v;
-            c.load(ip + (g << 2));
-            v.load(dp + (g << 2));
-            acc0 += v.v[0] * ld_x(x, c.v[0]);
-            acc1 += v.v[1] * ld_x(x, c.v[1]);
-            acc2 += v.v[2] * ld_x(x, c.v[2]);
-            acc3 += v.v[3] * ld_x(x, c.v[3]);
-        }
-    }
-#pragma unroll
-    for (int off = 8; off <= 16; off <<= 1) {
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
-        acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
-        acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
-        acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
-    }
-    // lanes 0-7 hold rows 4L..4L+3; re-deal them so that lane j < 16 holds rows 2j, 2j+1: the warp
-    // then writes its 32 results as ONE contiguous 256-byte store per destination (full NVLink
-    // packets instead of 32 scattered 8-byte writes)
-    const int src = lane >> 1;
-    const T b0 = __shfl_sync(0xffffffffu, acc0, src), b1 = __shfl_sync(0xffffffffu, acc1, src);
-    const T b2 = __shfl_sync(0xffffffffu, acc2, src), b3 = __shfl_sync(0xffffffffu, acc3, src);
-    T sq = 0;
-    if (active && lane < 16) {
-        const T lo = ((lane & 1) ? b2 : b0) * alpha, hi = ((lane & 1) ? b3 : b1) * alpha;
-        const long long r = slice * 32 + lane * 2;
-        if (r < n_rows) sq += lo * lo;
-        if (r + 1 < n_rows) sq += hi * hi;
-        // fully unrolled with a static index: dst lives in the constant bank; a runtime-indexed
-        // loop would copy the whole struct to local memory in every thread (ncu: +70 % instructions)
-#pragma unroll
-        for (int d = 0; d < kMaxPeers; ++d) {
-            if (d < n_dst) {
-                T *out = dst.p[d] + dst_offset + r;
-                const long long first = dst.lo[d], last = min((long long)dst.hi[d], (long long)n_rows);
-                if (r >= first && r + 1 < last) {
-                    *reinterpret_cast<double2 *>(out) = make_double2(lo, hi);
-                } else {
-                    if (r >= first && r < last) out[0] = lo;
-                    if (r + 1 >= first && r + 1 < last) out[1] = hi;
-                }
+            for (long long g = lane; g < n_groups; g += 32) {
+                IVec4 c;
+                Vec4<T> v;
+                c.load(ip + (g << 2));
+                v.load(dp + (g << 2));
+                acc0 += v.v[0] * ld_x(x, c.v[0]);
+                acc1 += v.v[1] * ld_x(x, c.v[1]);
+                acc2 += v.v[2] * ld_x(x, c.v[2]);
+                acc3 += v.v[3] * ld_x(x, c.v[3]);
             }
+#pragma unroll
+            for (int off = 8; off <= 16; off <<= 1) {
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+                acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
+                acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
+            }
+            // lanes 0-7 hold rows 4L..4L+3; re-deal them so that lane j holds row j
+            const int src = lane >> 2;
+            const T b0 = __shfl_sync(0xffffffffu, acc0, src), b1 = __shfl_sync(0xffffffffu, acc1, src);
+            const T b2 = __shfl_sync(0xffffffffu, acc2, src), b3 = __shfl_sync(0xffffffffu, acc3, src);
+            mine = (lane & 2) ? ((lane & 1) ? b3 : b2) : ((lane & 1) ? b1 : b0);
         }
+    }
+    mine *= alpha;
+    const long long r = slice * 32 + lane;
+    T sq = 0;
+    if (active && r < n_rows) {
+        sq = mine * mine;
+        // the warp writes its 32 results as ONE contiguous 256-byte store per destination (full NVLink
+        // packets).  Fully unrolled with a static index: dst lives in the constant bank; a
+        // runtime-indexed loop would copy the whole struct to local memory in every thread
+#pragma unroll
+        for (int d = 0; d < kMaxPeers; ++d)
+            if (d < n_dst && r >= dst.lo[d] && r < dst.hi[d]) dst.p[d][dst_offset + r] = mine;
     }
     if (sumsq_out) {
         sq = subwarp_sum<32>(sq);
@@ -837,10 +881,10 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         d.hi[i] = i < n_dst ? (dst_row_hi ? dst_row_hi[i] : n_rows) : 0;
     }
     for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.p[i], "null destination buffer");
-    // the kernel writes row pairs as one 16-byte store: a misaligned destination would raise a
-    // sticky misaligned-address fault on every rank instead of an error here
-    B200_REQUIRE((dst_offset & 1) == 0, "dst_offset must be even (row pairs are stored as 16-byte words)");
-    for (int i = 0; i < n_dst; ++i) B200_REQUIRE(aligned16(d.p[i]), "destination buffers must be 16-byte aligned");
+    // rows are stored as 8-byte words (lane = row, 256 contiguous bytes per warp): any double-aligned
+    // destination and any offset are fine
+    for (int i = 0; i < n_dst; ++i)
+        B200_REQUIRE((reinterpret_cast<uintptr_t>(d.p[i]) & 7) == 0, "destination buffers must be 8-byte aligned");
     for (int i = 0; i < n_dst; ++i) B200_REQUIRE(d.lo[i] >= 0, "negative row range");
     PeerSync sync;
     memset(&sync, 0, sizeof sync);
