@@ -350,35 +350,36 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-def column_range(pkg, ctx, cols):
-    """[lo, hi] = the columns a row block reads (b200_minmax_i32): all of x that has to be on the device."""
-    import ctypes as C
-    lo, hi = C.c_int(0), C.c_int(0)
-    pkg.check(pkg.lib().b200_minmax_i32(ctx.h, cols.ptr, cols.n, C.byref(lo), C.byref(hi)), "b200_minmax_i32")
-    return lo.value, hi.value
+def column_segments(pkg, ctx, cols, n_cols, block_log2=12):
+    """[(first column, count), ...]: the parts of x a row block reads, as runs of used 4096-column
+    blocks (b200_used_column_blocks).  A banded shard reads one window of x -- two when the band wraps
+    around the matrix edge -- so the host -> device bytes per rank do not grow with the number of ranks."""
+    nb = (n_cols + (1 << block_log2) - 1) >> block_log2
+    used = np.zeros(nb, np.uint8)
+    pkg.check(pkg.lib().b200_used_column_blocks(ctx.h, cols.ptr, cols.n, n_cols, block_log2, used.ctypes.data),
+              "b200_used_column_blocks")
+    edges = np.flatnonzero(np.diff(np.concatenate(([0], used, [0]))))
+    return [(int(s) << block_log2, min(int(e) << block_log2, n_cols) - (int(s) << block_log2))
+            for s, e in zip(edges[0::2], edges[1::2])]
 
 
-def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col_hi, dtype, steps, flops_step):
+def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, segments, dtype, steps, flops_step):
     """The metric through the C ABI with HOST buffers: per format, pinned-host x -> device, SpMV,
     y -> pinned host, with the format arrays uploaded once beforehand as the reference driver does
-    (csr.c:183-193).  Only the column range [col_lo, col_hi] the row block reads is uploaded (the
-    kernels are handed the base pointer of a virtual full-length x), so the bytes per rank do not grow
-    with the number of ranks."""
+    (csr.c:183-193).  x lives in pinned host memory in full; only the column segments the row block
+    reads (column_segments) are uploaded, so the bytes per rank do not grow with the number of ranks."""
     import ctypes as C
     L = pkg.lib()
     V = np.dtype(dtype).itemsize
-    n_x = col_hi - col_lo + 1
-    x_slice = x.download()[col_lo:col_hi + 1]
+    n_up = sum(c for _, c in segments)
+    x_host = x.download()
 
     def make_queue(q):
         hx, hy = C.c_void_p(), C.c_void_p()
-        pkg.check(L.b200_host_alloc_pinned(n_x * V, C.byref(hx)), "pinned x")
+        pkg.check(L.b200_host_alloc_pinned(n_cols * V, C.byref(hx)), "pinned x")
         pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy)), "pinned y")
-        np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(n_x * V,)).view(dtype)[:] = x_slice
-        xin = q.empty(n_x, dtype)
-        # x[c] for c in [col_lo, col_hi] resolves into xin: a view whose base sits col_lo entries earlier
-        view = pkg.DeviceArray.from_ptr(q, xin.ptr - col_lo * V, n_cols, dtype)
-        return dict(ctx=q, hx=hx, hy=hy, xin=xin, view=view)
+        np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(n_cols * V,)).view(dtype)[:] = x_host
+        return dict(ctx=q, hx=hx, hy=hy, xin=q.zeros(n_cols, dtype))
 
     q1 = make_queue(ctx)
     ctx2 = pkg.Context(local_rank)
@@ -386,8 +387,9 @@ def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col
 
     def call(f, m, q):
         m.ctx = q["ctx"]
-        pkg.check(L.b200_memcpy_h2d_async(q["ctx"].h, q["xin"].ptr, q["hx"], n_x * V), "h2d x")
-        m.spmv(q["view"], y[f])
+        for first, count in segments:
+            pkg.check(L.b200_memcpy_h2d_async(q["ctx"].h, q["xin"].ptr + first * V, q["hx"].value + first * V, count * V), "h2d x")
+        m.spmv(q["xin"], y[f])
         pkg.check(L.b200_memcpy_d2h_async(q["ctx"].h, q["hy"], y[f].ptr, n_rows * V), "d2h y")
 
     def step_one_queue():
@@ -429,7 +431,7 @@ def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col
     for m in mats.values():
         m.ctx = ctx
     one_ms, one_wall, two_wall = D.reduce([one_ms, one_wall, two_wall], "max")
-    h2d, d2h = D.reduce([len(mats) * n_x * V, len(mats) * n_rows * V], "sum")
+    h2d, d2h = D.reduce([len(mats) * n_up * V, len(mats) * n_rows * V], "sum")
     best = min(one_ms, two_wall)
     ctx2.sync()
     for q in (q1, q2):
@@ -440,15 +442,16 @@ def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col
     return {"value": round(flops_step / (best * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": round(best, 4), "steps": steps,
-            "x_columns_uploaded_per_rank": int(n_x), "x_columns_total": int(n_cols),
+            "x_columns_uploaded_per_rank": int(n_up), "x_columns_total": int(n_cols),
+            "x_segments_rank0": [list(sg) for sg in segments[:8]],
             "one_queue": {"ms_per_step": round(one_ms, 4), "wall_ms_per_step": round(one_wall, 4),
                           "gflops": round(flops_step / (one_ms * 1e-3) * 1e-9, 2)},
             "two_queues": {"wall_ms_per_step": round(two_wall, 4),
                            "gflops": round(flops_step / (two_wall * 1e-3) * 1e-9, 2)},
-            "what": "per format: pinned-host x (only the column range this rank's row block reads, b200_minmax_i32) "
-                    "-> device, SpMV through the C ABI, y -> pinned host; format arrays uploaded once before the "
-                    "timed region, as the reference driver does (csr.c:183-193). value = the better of one in-order "
-                    "queue (CUDA events) and two queues with alternating formats (wall clock, both drained); max "
+            "what": "per format: x from pinned host memory -> device (only the 4096-column blocks this rank's row block "
+                    "reads, b200_used_column_blocks), SpMV through the C ABI, y -> pinned host; format arrays uploaded "
+                    "once before the timed region, as the reference driver does (csr.c:183-193). value = the better of one "
+                    "in-order queue (CUDA events) and two queues with alternating formats (wall clock, both drained); max "
                     "over ranks"}
 
 
@@ -919,13 +922,15 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
             per_ms = {f: time_graph(g_fmt[f], 5, n_f) for f in mats}
         step_ms = total_ms / args.steps
 
-        # the same graphs recorded with launch overlap on (b200_ctx_set_launch_overlap: programmatic
-        # dependent launch -- every kernel streams its matrix arrays while its predecessor drains and
-        # touches x / y only after it has finished).  Reported next to the in-order numbers.
-        ctx.set_launch_overlap(True)
+        # The numbers above are the library's default: back-to-back SpMV launches on the library's own
+        # queue are programmatic dependents (every kernel streams its matrix arrays while its predecessor
+        # drains and touches x / y only after it has finished; anything else entering the queue -- an upload,
+        # a build, an event -- makes the next launch fully ordered again).  The same graphs recorded with
+        # b200_ctx_set_launch_overlap(0), i.e. strictly one kernel after the other, are reported next to them.
+        ctx.set_launch_overlap(False)
         g_steps_o = record_steps(args.steps)
         g_fmt_o = {f: record_format(f, 0, n_f) for f in mats}
-        ctx.set_launch_overlap(False)
+        ctx.set_launch_overlap(True)
         g_steps_o.launch()
         D.barrier(ctx)
         e0.record()
@@ -996,10 +1001,10 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
 
     # ---------------- e2e: host x in, host y out, through the C ABI, matrix resident ----------
     e2e = None
-    col_lo, col_hi = column_range(pkg, ctx, coo.cols)
+    segments = column_segments(pkg, ctx, coo.cols, n_cols)
     steps_e = max(3, min(args.steps, 20))
     if not args.no_e2e:
-        e2e = measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, col_lo, col_hi, dtype, steps_e, flops_step)
+        e2e = measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, segments, dtype, steps_e, flops_step)
 
     # ---------------- fp64 pass over the same matrix (the reference's own arithmetic) ----------
     f64 = None
@@ -1026,7 +1031,7 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
                "steps": k64, "dtype": "f64", "formats": format_table(list(m64), p64, b64, nnz, peak),
                "what": "the same matrix and step in fp64, the reference's only arithmetic (what --impl reference times)"}
         if not args.no_e2e:
-            f64["e2e"] = measure_e2e(pkg, ctx, D, local_rank, m64, y64, x64, n_rows, n_cols, col_lo, col_hi, d64,
+            f64["e2e"] = measure_e2e(pkg, ctx, D, local_rank, m64, y64, x64, n_rows, n_cols, segments, d64,
                                      steps_e, flops_step)
         del m64, y64, x64
         ctx.set_l2_persist(None)
@@ -1070,9 +1075,10 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
                                  f"reads copy i mod {n_copies}; no flush; the K steps are one CUDA-graph replay" if n_copies > 1 else
                                  "inputs larger than L2 (0.8-1.6 GB per format), no flush")},
             "formats": fm,
-            "launch_overlap": (None if overlap is None else {
-                "what": "same K-step graph with b200_ctx_set_launch_overlap(1): kernels are programmatic dependents "
-                        "(matrix arrays streamed while the previous launch drains; x read / y written after it ends)",
+            "launch_overlap_off": (None if overlap is None else {
+                "what": "same K-step graph with b200_ctx_set_launch_overlap(0): strictly one kernel after the other "
+                        "(the default lets back-to-back SpMV launches stream their matrix arrays while the previous one "
+                        "drains; x is read / y written only after it has ended)",
                 "ms_per_step": round(overlap["ms_per_step"], 5),
                 "value": round(flops_step / (overlap["ms_per_step"] * 1e-3) * 1e-9, 2),
                 "formats": {f: {"ms": round(ms, 5), "frac_measured": round(bytes_alg[f] / (ms * 1e-3) * 1e-9 / peak, 4)}
@@ -1215,8 +1221,7 @@ def rmat_arm(pkg, args, rank, world, local_rank):
     if not args.no_e2e:
         mats3 = {"csr": csr, "coo": coo, "cmrs": cmrs}
         y3 = {f: y for f in mats3}
-        col_lo, col_hi = column_range(pkg, ctx, coo.cols)
-        e2e = measure_e2e(pkg, ctx, D, local_rank, mats3, y3, x, n_rows, n, col_lo, col_hi, dtype,
+        e2e = measure_e2e(pkg, ctx, D, local_rank, mats3, y3, x, n_rows, n, column_segments(pkg, ctx, coo.cols, n), dtype,
                           max(3, min(args.steps, 10)), 2.0 * tot * len(mats3))
         e2e["formats"] = list(mats3)
 

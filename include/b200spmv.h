@@ -70,14 +70,18 @@ int b200_ctx_device(const b200_ctx *ctx, int *device);
  * bytes = 0 clears the window.  New: the OpenCL reference has no equivalent. */
 int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes);
 
-/* Launch overlap (new; programmatic dependent launch).  With enable != 0 the CSR / ELL / SELL / CMRS
- * launches on this context may START before earlier work on its queue has finished: they stream
- * their row pointers and the first batch of indices/values at once and read `vect` / write `output`
- * only after everything queued before them has completed.  Results are unchanged; the ~2 us of launch
- * ramp and drain between consecutive small launches (a cant-sized SpMV lasts ~12 us) overlap.
- * Contract: while it is enabled the caller must not enqueue work that WRITES a matrix array (uploads,
- * builds, packs) directly before an SpMV that reads it without a b200_sync in between.  Default off:
- * the in-order semantics of the reference's queue (csr.c:115). */
+/* Launch overlap (new; programmatic dependent launch).  With overlap on, an SpMV launch (CSR / ELL /
+ * SELL / CMRS / COO, launches of at most a few waves) that DIRECTLY follows another SpMV launch on this
+ * context may start before its predecessor has finished: it streams its row pointers and first batch of
+ * indices / values at once and reads `vect` / writes `output` only after everything queued before it has
+ * completed.  Results are unchanged; the ~2 us of launch ramp and drain between consecutive small
+ * launches (a cant-sized SpMV lasts ~12 us) overlap.  It is safe by construction: any other call that
+ * enters the context -- an upload, a build, a pack, a memset, an event, a graph launch -- makes the next
+ * SpMV launch fully ordered again, so matrix arrays are never read before they are written.
+ * Default: ON for contexts that own their queue (b200_ctx_create: only library calls enqueue there),
+ * OFF for b200_ctx_create_on_stream (foreign kernels on that stream could write a matrix array between
+ * two SpMV launches without the library knowing); enable = 0 gives the strict in-order queue of the
+ * reference (csr.c:115). */
 int b200_ctx_set_launch_overlap(b200_ctx *ctx, int enable);
 
 /* Tuning hooks (new).  Every kernel-selection heuristic can be overridden per context: `name` is one
@@ -215,9 +219,14 @@ int b200_spmv_sell64_f32(b200_ctx *ctx, const float *data, const int *indices, c
  * reference writes height outputs per strip unconditionally, Cmrs.cl:38-41, quirk q5).
  * height <= 32. */
 typedef struct b200_cmrs_plan b200_cmrs_plan; /* strips longer than 8192 entries (power-law hubs) are
-                                               * split over several warps; NULL = never split */
+                                               * split over several warps; NULL = never split.  When the
+                                               * strip lengths are skewed (longest > 32 x mean) the plan
+                                               * also prepares the nnz-split kernel: warps own 512-entry
+                                               * tiles instead of strips, rows accumulate like COO rows
+                                               * (atomics at run ends); *n_tiles > 0 says so */
 int b200_cmrs_plan_create(b200_ctx *ctx, const int *strip_ptr, int n_strips, b200_cmrs_plan **plan);
 int b200_cmrs_plan_extra_items(const b200_cmrs_plan *plan, int *n_items);
+int b200_cmrs_plan_stream_tiles(const b200_cmrs_plan *plan, int *n_tiles);
 int b200_cmrs_plan_destroy(b200_cmrs_plan *plan);
 int b200_spmv_cmrs_f64(b200_ctx *ctx, const double *data, const int *indices, const int *strip_ptr,
                        const int *row_in_strip, const double *vect, double *output, int n_strips,
@@ -380,6 +389,12 @@ int b200_spmv_sell_ring_f64(b200_ctx *ctx, const double *data, const int *indice
                             void *const *sync_blocks, int my_rank, unsigned long long step);
 /* min and max of a device int array (host outputs): the column range a row block reads */
 int b200_minmax_i32(b200_ctx *ctx, const int *a, long long n, int *min_out, int *max_out);
+/* which blocks of 2^block_log2 consecutive columns a row block reads (host output, one byte per column
+ * block, ceil(n_cols / 2^block_log2) bytes: 1 = some entry has its column there).  What a caller that
+ * keeps x on the host has to upload before an SpMV of this block -- a banded shard reads a window of x
+ * (two windows when the band wraps around), not the whole vector. */
+int b200_used_column_blocks(b200_ctx *ctx, const int *cols, long long nnz, int n_cols, int block_log2,
+                            unsigned char *used_host);
 /* CUDA IPC plumbing for the peers' buffers (allocations made with b200_malloc) */
 int b200_ipc_get_handle(b200_ctx *ctx, void *dptr, unsigned char handle[64]);
 int b200_ipc_open_handle(b200_ctx *ctx, const unsigned char handle[64], void **peer_dptr);

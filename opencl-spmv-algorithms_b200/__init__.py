@@ -115,6 +115,7 @@ SIGNATURES = {
     "b200_spmv_sell64_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b200_cmrs_plan_create": (_i, [_vp, _vp, _i, _vpp]),
     "b200_cmrs_plan_extra_items": (_i, [_vp, C.POINTER(_i)]),
+    "b200_cmrs_plan_stream_tiles": (_i, [_vp, C.POINTER(_i)]),
     "b200_cmrs_plan_destroy": (_i, [_vp]),
     "b200_spmv_cmrs_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_spmv_cmrs_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -156,6 +157,7 @@ SIGNATURES = {
     "b200_spmv_sell_halo_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
     "b200_spmv_sell_ring_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _ll, _vp, _vp, _vp, _i, _u64]),
     "b200_minmax_i32": (_i, [_vp, _vp, _ll, C.POINTER(_i), C.POINTER(_i)]),
+    "b200_used_column_blocks": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "b200_ipc_get_handle": (_i, [_vp, _vp, _vp]),
     "b200_ipc_open_handle": (_i, [_vp, _vp, _vpp]),
     "b200_ipc_close_handle": (_i, [_vp, _vp]),

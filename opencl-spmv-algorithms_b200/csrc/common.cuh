@@ -41,6 +41,10 @@ struct b200_ctx {
     bool watch_saved;      // watch_flag as it was when b200_graph_begin started recording
     bool overlap;          // b200_ctx_set_launch_overlap: SpMV kernels are launched as programmatic
                            // dependents (they stream their matrix arrays while earlier work drains)
+    mutable bool needs_order;  // something other than an SpMV launch entered this context since the last
+                           // SpMV launch (an upload, a build, a memset, an event ...): the next SpMV launch
+                           // is then fully stream-ordered, never a programmatic dependent -- only
+                           // back-to-back SpMV launches overlap, so matrix arrays are never read early
 };
 // scratch[kWatchFlag]: set by a kernel whose mbarrier wait ran into its spin limit (never expected;
 // reported by the next b200_sync / b200_memcpy_d2h instead of hanging the device)
@@ -78,6 +82,7 @@ static inline int b200_ctx_enter(const b200_ctx *ctx)
     }
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return b200_cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    ctx->needs_order = true;
     return B200_SUCCESS;
 }
 #define B200_ENTER(ctx)                          \
@@ -85,6 +90,20 @@ static inline int b200_ctx_enter(const b200_ctx *ctx)
         int rc__ = b200_ctx_enter(ctx);          \
         if (rc__) return rc__;                   \
     } while (0)
+// the SpMV entry points: entering does not by itself break a chain of overlapping launches
+#define B200_ENTER_SPMV(ctx)                                     \
+    do {                                                         \
+        const bool order__ = (ctx) ? (ctx)->needs_order : true;  \
+        int rc__ = b200_ctx_enter(ctx);                          \
+        if (rc__) return rc__;                                   \
+        (ctx)->needs_order = order__;                            \
+    } while (0)
+// launch overlap applies to launches of at most a few waves: there the ~2 us of ramp and drain
+// between kernels matter (a cant-sized SpMV lasts ~10 us); a 1 GB matrix keeps the plain kernels
+static inline bool ovl_on(const b200_ctx *ctx, long long threads)
+{
+    return ctx->overlap && threads <= 8ll * ctx->sm_count * 2048;
+}
 
 // value of a tuning hook, or `dflt` when it is unset
 static inline int opt_or(const b200_ctx *ctx, b200_opt o, int dflt)
@@ -106,10 +125,11 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 static inline unsigned ceil_div_u(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
-// Launch on the context's stream; with ctx->overlap the kernel is a programmatic dependent of the
-// previous kernel on the stream (see pdl_wait below).
+// Launch on the context's stream; ovl = the kernel is an OVL variant (see pdl_wait below): it becomes
+// a programmatic dependent of the previous kernel on the stream, unless anything but SpMV launches
+// entered the context since (needs_order).
 template <typename... KArgs, typename... Args>
-static inline cudaError_t b200_launch(const b200_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+static inline cudaError_t b200_launch(const b200_ctx *ctx, bool ovl, void (*kernel)(KArgs...), dim3 grid, dim3 block,
                                       size_t smem, Args... args)
 {
     cudaLaunchConfig_t cfg;
@@ -122,8 +142,10 @@ static inline cudaError_t b200_launch(const b200_ctx *ctx, void (*kernel)(KArgs.
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = ctx->overlap ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    cfg.numAttrs = (ovl && !ctx->needs_order) ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (ovl) ctx->needs_order = false;  // the chain (re)starts here: this kernel waits before touching x / y
+    return e;
 }
 
 // ---------------------------------------------------------------------------------------

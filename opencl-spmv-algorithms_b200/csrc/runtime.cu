@@ -114,7 +114,11 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool own, b200_ctx *
     c->host_scratch = nullptr;
     c->watch_flag = false;
     c->watch_saved = false;
-    c->overlap = false;
+    // launch overlap is on by default on the library's own queue (only library calls enqueue there,
+    // and every one of them but the SpMV launches sets needs_order); a caller-owned stream may carry
+    // foreign kernels that write matrix arrays, so there it stays opt-in
+    c->overlap = own;
+    c->needs_order = true;
     for (int o = 0; o < OPT_COUNT; ++o) {  // the only getenv calls of the library
         const char *e = getenv(b200_opt_names[o]);
         c->opt[o] = (e && *e) ? atoi(e) : kOptUnset;

@@ -511,19 +511,20 @@ int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data,
                    int n_rows, int long_threshold, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
+    const bool ovl = ovl_on(ctx, (long long)n_rows * LPR);
     const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), false, OPT_CSR_UNROLL);
     if (!vec)
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
-                               : b200_launch(ctx, csr_vector_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else if (u == 4)
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
-                               : b200_launch(ctx, csr_vector_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else if (u == 2)
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
-                               : b200_launch(ctx, csr_vector_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, csr_vector_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
-                               : b200_launch(ctx, csr_vector_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -533,7 +534,7 @@ int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, 
                   int n_rows, const b200_csr_plan *plan)
 {
     B200_TRACE("b200 spmv csr");
-    B200_ENTER(ctx);
+    B200_ENTER_SPMV(ctx);
     B200_REQUIRE(ptr && x && y && n_rows >= 0, "bad argument");
     if (n_rows == 0) return B200_SUCCESS;
     b200_csr_plan *tmp = nullptr;
@@ -599,19 +600,20 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
                    int row_size, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
+    const bool ovl = ovl_on(ctx, (long long)n_rows * LPR);
     const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), true, OPT_ELL_UNROLL);
     if (!vec)
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
-                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else if (u == 4)
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
-                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else if (u == 2)
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
-                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else
-        B200_CUDA(ctx->overlap ? b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
-                               : b200_launch(ctx, ell_rowmajor_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -621,7 +623,7 @@ int spmv_ell_impl(b200_ctx *ctx, const T *data, const int *col, const T *x, T *y
                   int row_size)
 {
     B200_TRACE("b200 spmv ell");
-    B200_ENTER(ctx);
+    B200_ENTER_SPMV(ctx);
     B200_REQUIRE(x && y && n_rows >= 0 && row_size >= 0, "bad argument");
     if (n_rows == 0) return B200_SUCCESS;
     B200_REQUIRE(row_size == 0 || (data && col), "null data/indices");

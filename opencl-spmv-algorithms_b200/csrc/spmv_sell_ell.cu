@@ -721,7 +721,8 @@ template <typename T, typename P>
 int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *y, const P *slice_ptr,
                    int chunk, int n_slices, int n_out, const int *perm, const b200_sell_plan *plan)
 {
-    B200_ENTER(ctx);
+    B200_TRACE("b200 spmv sell");
+    B200_ENTER_SPMV(ctx);
     B200_REQUIRE(x && y && slice_ptr && n_slices >= 0 && n_out >= 0, "bad argument");
     if (chunk != 32) {
         b200_set_error("SELL chunk must be 32 (warp-aligned), got %d", chunk);
@@ -778,12 +779,13 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             const int v = opt_or(ctx, OPT_SELL_UNROLL, 0);
             if (v == 1 || v == 2 || v == 4) u = v;
         }
+        const bool ovl = ovl_on(ctx, (long long)n_slices * 32 * wpc);
 #define B200_SELL_MAIN(W, UU)                                                                              \
-    B200_CUDA(ctx->overlap                                                                                   \
-                  ? b200_launch(ctx, sell32_kernel<T, P, false, W, UU, true>,                                \
+    B200_CUDA(ovl                                                                                   \
+                  ? b200_launch(ctx, ovl, sell32_kernel<T, P, false, W, UU, true>,                                \
                                 dim3(ceil_div_u((long long)n_slices * 32 * W, kBlock)), dim3(kBlock), 0, data, idx, x, \
                                 y, slice_ptr, n_slices, n_out, perm, wmax, nullptr)                          \
-                  : b200_launch(ctx, sell32_kernel<T, P, false, W, UU, false>,                               \
+                  : b200_launch(ctx, ovl, sell32_kernel<T, P, false, W, UU, false>,                               \
                                 dim3(ceil_div_u((long long)n_slices * 32 * W, kBlock)), dim3(kBlock), 0, data, idx, x, \
                                 y, slice_ptr, n_slices, n_out, perm, wmax, nullptr))
 #define B200_SELL_MAIN_U(W)                  \

@@ -191,6 +191,14 @@ inline unsigned capped_grid(const b200_ctx *ctx, long long n)
     return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+__global__ void col_blocks_kernel(const int *__restrict__ a, long long n, int shift, unsigned char *__restrict__ used)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = a[i] >> shift;
+        if (!used[b]) used[b] = 1;  // many threads store the same 1: benign
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -336,6 +344,28 @@ int b200_sumsq_f64(b200_ctx *ctx, const double *y, long long n, double *acc_devi
     if (n == 0) return B200_SUCCESS;
     sumsq_kernel<<<capped_grid(ctx, n), kBlock, 0, ctx->stream>>>(y, n, acc_device);
     B200_LAUNCH_CHECK();
+    return B200_SUCCESS;
+}
+
+int b200_used_column_blocks(b200_ctx *ctx, const int *cols, long long nnz, int n_cols, int block_log2,
+                            unsigned char *used_host)
+{
+    B200_ENTER(ctx);
+    B200_REQUIRE(nnz >= 0 && n_cols >= 0 && block_log2 >= 0 && block_log2 < 31 && used_host && (nnz == 0 || cols), "bad argument");
+    const size_t n_blocks = ((size_t)n_cols + ((size_t)1 << block_log2) - 1) >> block_log2;
+    memset(used_host, 0, n_blocks);
+    if (nnz == 0 || n_blocks == 0) return B200_SUCCESS;
+    unsigned char *d = nullptr;
+    B200_CUDA(cudaMalloc(&d, n_blocks));
+    cudaError_t e = cudaMemsetAsync(d, 0, n_blocks, ctx->stream);
+    if (e == cudaSuccess) {
+        col_blocks_kernel<<<capped_grid(ctx, nnz), kBlock, 0, ctx->stream>>>(cols, nnz, block_log2, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(used_host, d, n_blocks, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return b200_cuda_fail(e, "b200_used_column_blocks", __FILE__, __LINE__);
     return B200_SUCCESS;
 }
 

@@ -267,6 +267,12 @@ class CmrsMatrix:
         check(lib().b200_cmrs_plan_extra_items(self.plan(), C.byref(n)), "b200_cmrs_plan_extra_items")
         return n.value
 
+    def plan_stream_tiles(self) -> int:
+        """> 0: the plan found skewed strip lengths and selected the nnz-split kernel."""
+        n = C.c_int(0)
+        check(lib().b200_cmrs_plan_stream_tiles(self.plan(), C.byref(n)), "b200_cmrs_plan_stream_tiles")
+        return n.value
+
     def spmv(self, x: DeviceArray, y: DeviceArray, use_plan: bool = True) -> None:
         v = self.csr.coo.values(x.dtype)
         fn = getattr(lib(), "b200_spmv_cmrs_" + suffix(x.dtype))

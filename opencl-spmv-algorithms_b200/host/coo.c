@@ -23,6 +23,10 @@ int main(int argc, char *argv[])
 {
     driver_options opt;
     if (driver_parse_args(argc, argv, "databases/cant.mtx", &opt)) return OtherError;
+    if (opt.iters > 0) {
+        fprintf(stderr, "the iterated mode (--iters / --gpus) is implemented by csr and sigma_c\n");
+        return OtherError;
+    }
 
     int number_of_devices = 0;
     if (b200_get_device_count(&number_of_devices) != B200_SUCCESS) {

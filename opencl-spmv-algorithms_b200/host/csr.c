@@ -24,6 +24,17 @@ int main(int argc, char *argv[])
 {
     driver_options opt;
     if (driver_parse_args(argc, argv, "databases/cant-sorted.mtx", &opt)) return OtherError;
+    /* --iters K [--gpus N]: where the reference's device loop breaks after the first GPU (csr.c:279),
+     * this one goes on -- power iteration over N devices, CSR SpMV + ncclAllGather of x */
+    if (opt.iters > 0) {
+        if (opt.synthetic) return driver_run_iterated(&opt, NULL, B200_FORMAT_CSR, "csr");
+        host_matrix hm;
+        int lrc = driver_load_matrix(&opt, &hm);
+        if (lrc != Success) return lrc;
+        lrc = driver_run_iterated(&opt, &hm, B200_FORMAT_CSR, "csr");
+        driver_free_matrix(&hm);
+        return lrc;
+    }
 
     int number_of_devices = 0;
     if (b200_get_device_count(&number_of_devices) != B200_SUCCESS) {

@@ -26,6 +26,10 @@ int main(int argc, char *argv[])
     host_matrix m;
     device_triples d;
     if (driver_parse_args(argc, argv, "databases/cant-sorted.mtx", &opt)) return OtherError;
+    if (opt.iters > 0) {
+        fprintf(stderr, "the iterated mode (--iters / --gpus) is implemented by csr and sigma_c\n");
+        return OtherError;
+    }
     int rc = driver_load_matrix(&opt, &m);
     if (rc != Success) return rc;
     const int number_of_rows = m.n_rows, number_of_nonzeroes = m.nnz;

@@ -37,6 +37,11 @@ typedef struct {
     int expand_symmetric; /* --expand-symmetric  mirror the off-diagonal entries of a symmetric file (default:
                              ignore the banner's symmetry, as the reference does) */
     int cache;          /* --cache  keep "<matrix>.b200cache" (binary triples) next to the matrix */
+    /* iterated, multi-GPU mode (csr and sigma_c only; src/driver_iterate.c) */
+    int gpus;           /* --gpus N       devices device .. device+N-1, one host thread each (default 1) */
+    int iters;          /* --iters K      K power-iteration steps instead of the single SpMV (default 0 = off) */
+    int json;           /* --json         one JSON line instead of the text block */
+    const char *synthetic; /* --synthetic laplace7:NXxNYxNZ  matrix generated on the devices, no file */
 } driver_options;
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt);
@@ -90,6 +95,11 @@ void driver_free_matrix(host_matrix *m);
 int driver_upload_triples(b200_ctx *ctx, const host_matrix *m, int use_f32, device_triples *d);
 void driver_free_triples(b200_ctx *ctx, device_triples *d);
 int driver_read_output(b200_ctx *ctx, const void *buffer_output, int n, int use_f32, double *output);
+
+/* the iterated mode: K steps of y = A x / ||x|| on opt->gpus devices (src/driver_iterate.c).  format =
+ * B200_FORMAT_SELL (fused kernel + halo exchange + all-reduce) or B200_FORMAT_CSR (SpMV + ncclAllGather);
+ * m = the loaded matrix, or NULL with --synthetic.  Returns a ReturnCode. */
+int driver_run_iterated(const driver_options *opt, const host_matrix *m, int format, const char *driver_name);
 
 /* prints "<what> error <status>" (+ the library's detail line) and yields the exit code */
 int report_b200_error(const char *what, int status);

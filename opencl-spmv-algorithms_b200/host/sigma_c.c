@@ -21,8 +21,16 @@ int main(int argc, char *argv[])
     host_matrix m;
     device_triples d;
     if (driver_parse_args(argc, argv, "databases/cant-sorted.mtx", &opt)) return OtherError;
+    /* --iters K [--gpus N]: where the reference's device loop breaks after the first GPU
+     * (sigma_c.c:375), this one goes on -- power iteration over N devices, fused SELL kernel */
+    if (opt.iters > 0 && opt.synthetic) return driver_run_iterated(&opt, NULL, B200_FORMAT_SELL, "sigma_c");
     int rc = driver_load_matrix(&opt, &m);
     if (rc != Success) return rc;
+    if (opt.iters > 0) {
+        rc = driver_run_iterated(&opt, &m, B200_FORMAT_SELL, "sigma_c");
+        driver_free_matrix(&m);
+        return rc;
+    }
     const int number_of_rows = m.n_rows, number_of_nonzeroes = m.nnz;
     const int max_rows_to_check = 32; /* C */
     const size_t V = opt.use_f32 ? sizeof(float) : sizeof(double);

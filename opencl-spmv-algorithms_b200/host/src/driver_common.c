@@ -31,6 +31,10 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     opt->rowmajor = 1;
     opt->expand_symmetric = 0;
     opt->cache = 0;
+    opt->gpus = 1;
+    opt->iters = 0;
+    opt->json = 0;
+    opt->synthetic = NULL;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
         const char *v = i + 1 < argc ? argv[i + 1] : NULL;
@@ -48,9 +52,19 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
         else if (!strcmp(a, "--colmajor")) opt->rowmajor = 0;
         else if (!strcmp(a, "--expand-symmetric")) opt->expand_symmetric = 1;
         else if (!strcmp(a, "--cache")) opt->cache = 1;
+        else if (!strcmp(a, "--gpus") && v) opt->gpus = atoi(argv[++i]);
+        else if (!strcmp(a, "--iters") && v) opt->iters = atoi(argv[++i]);
+        else if (!strcmp(a, "--json")) opt->json = 1;
+        else if (!strcmp(a, "--synthetic") && v) opt->synthetic = argv[++i];
         else goto bad;
     }
-    if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0) goto bad;
+    if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0 || opt->gpus < 1 || opt->gpus > DEVICES_DEFAULT_SIZE ||
+        opt->iters < 0)
+        goto bad;
+    if ((opt->gpus > 1 || opt->synthetic) && opt->iters == 0) {
+        fprintf(stderr, "--gpus / --synthetic belong to the iterated mode: give --iters K as well\n");
+        goto bad;
+    }
     set_value_bytes(opt->use_f32 ? 4 : 8);
     set_check_tolerance(opt->use_f32 ? 1e-5 : 1e-12);
     set_expand_symmetric(opt->expand_symmetric);
@@ -58,7 +72,8 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     return 0;
 bad:
     fprintf(stderr, "usage: %s [--matrix FILE.mtx] [--dtype f32|f64] [--sigma N] [--reps N] "
-                    "[--device D] [--no-cpu] [--rowmajor|--colmajor] [--expand-symmetric] [--cache]\n", argv[0]);
+                    "[--device D] [--no-cpu] [--rowmajor|--colmajor] [--expand-symmetric] [--cache]\n"
+                    "       iterated mode (csr, sigma_c): --iters K [--gpus N] [--synthetic laplace7:NXxNYxNZ] [--json]\n", argv[0]);
     return 1;
 }
 

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """sweep_variants.py -- times the tuning variants of every SpMV kernel in ONE process on one GPU.
 
-The kernels read their tuning hooks (B200_CSR_LANES, B200_CSR_UNROLL, B200_ELL_LANES,
-B200_ELL_UNROLL, B200_SELL_WPC, B200_SELL_UNROLL, B200_COO_U, B200_CMRS_U) at launch time, so the
-sweep just sets the environment between launches.  Two workloads, both with cold L2 data:
+The tuning hooks (B200_CSR_LANES, B200_CSR_UNROLL, B200_ELL_LANES, B200_ELL_UNROLL, B200_SELL_WPC,
+B200_SELL_UNROLL, B200_COO_U, B200_CMRS_U, B200_CMRS_WPS) are per-context options
+(b200_ctx_set_option), so the sweep just sets them between launches.  Two workloads, both with cold
+L2 data:
 
   cant    cant-shaped stand-in, 62 451 rows (fits in L2): N independent copies of every format used in
           rotation, the launches of one variant recorded into a CUDA graph and replayed;
@@ -29,15 +30,15 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 HOOKS = ("B200_SELL_TMA", "B200_SELL_TMA_BLOCKS", "B200_CSR_LANES", "B200_CSR_UNROLL", "B200_ELL_LANES", "B200_ELL_UNROLL", "B200_SELL_WPC",
-         "B200_SELL_UNROLL", "B200_COO_U", "B200_CMRS_U", "B200_CSR_STREAM")
+         "B200_SELL_UNROLL", "B200_COO_U", "B200_CMRS_U", "B200_CMRS_WPS", "B200_CSR_STREAM")
 
 
 def variants(workload: str, args_no_tma: bool = False, tma_only: bool = False):
     small = workload == "cant"
     lanes = (2, 4, 8, 16) if small else (4, 8)
     out = {"coo": [{"B200_COO_U": u} for u in (1, 2, 4)],
-           "cmrs": [{"B200_CMRS_U": u} for u in (1, 2)],
-           "cmrs_packed": [{"B200_CMRS_U": u} for u in (1, 2)],
+           "cmrs": [{"B200_CMRS_U": u, "B200_CMRS_WPS": w} for u in (1, 2) for w in ((1, 2, 4) if small else (1,))],
+           "cmrs_packed": [{"B200_CMRS_U": u, "B200_CMRS_WPS": w} for u in (1, 2) for w in ((1, 2, 4) if small else (1,))],
            "csr": [{"B200_CSR_LANES": l, "B200_CSR_UNROLL": u} for l, u in itertools.product(lanes, (1, 2, 4))],
            "ell": [{"B200_ELL_LANES": l, "B200_ELL_UNROLL": u} for l, u in itertools.product(lanes, (1, 2, 4))],
            "sell": [{"B200_SELL_WPC": w, "B200_SELL_UNROLL": u}
@@ -54,11 +55,14 @@ def variants(workload: str, args_no_tma: bool = False, tma_only: bool = False):
     return out
 
 
+CTX = None
+
+
 def set_env(env):
     for k in HOOKS:
-        os.environ.pop(k, None)
+        CTX.set_option(k, None)
     for k, v in env.items():
-        os.environ[k] = str(v)
+        CTX.set_option(k, v)
 
 
 def main():
@@ -72,6 +76,7 @@ def main():
     ap.add_argument("--no-tma", action="store_true", help="skip the bulk-copy SELL variants")
     ap.add_argument("--tma-only", action="store_true", help="only the bulk-copy SELL variants (+ the default)")
     ap.add_argument("--overlap", action="store_true", help="b200_ctx_set_launch_overlap(1): PDL launches")
+    ap.add_argument("--only", default=None, help="comma-separated formats to sweep (default: all)")
     args = ap.parse_args()
     dtype = np.dtype(np.float32 if args.dtype == "f32" else np.float64)
 
@@ -79,6 +84,8 @@ def main():
     from __graft_entry__ import load_package
     pkg = load_package()
     ctx = pkg.Context(0)
+    global CTX
+    CTX = ctx
     peak, _ = bench.measured_peak()
 
     if args.workload == "cant":
@@ -113,6 +120,8 @@ def main():
 
     results = []
     for fmt, envs in variants(args.workload, args.no_tma, args.tma_only).items():
+        if args.only and fmt not in args.only.split(","):
+            continue
         nbytes = sets[0][fmt].nbytes(dtype)
         for env in envs:
             set_env(env)

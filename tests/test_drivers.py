@@ -280,3 +280,53 @@ def test_unmodified_reference_csr_on_full_cant_shape(cant_dir):
     O.prepare_ref_workdir(cant_dir)
     p = run(SHIM_BINS / "csr", cant_dir)
     assert p.returncode == 0 and "result is ok" in p.stdout.splitlines(), p.stdout + p.stderr
+
+
+def _gpu_count():
+    import ctypes
+    try:
+        from __graft_entry__ import load_package
+        n = ctypes.c_int(0)
+        return n.value if load_package().lib().b200_get_device_count(ctypes.byref(n)) == 0 else 0
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2, 4])
+def test_driver_iterated_mode(fem_small_dir, tmp_path, gpus):
+    """--iters K [--gpus N] [--json]: the power iteration issued from C (host thread per device, the
+    library's NCCL communicator and iterator).  sigma_c = fused SELL kernel + halo exchange, csr =
+    SpMV + ncclAllGather; both must agree with the driver's own serial CPU iteration (`ok`), with each
+    other, and across device counts; --synthetic generates the Laplacian on the devices."""
+    import json
+    if _gpu_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    bins = build_drivers()
+    mtx = str(fem_small_dir / "databases" / "cant-sorted.mtx")
+    norms = {}
+    for fmt in ("sigma_c", "csr"):
+        p = run(bins / fmt, tmp_path, "--matrix", mtx, "--iters", "40", "--gpus", str(gpus), "--json")
+        assert p.returncode == 0, p.stdout + p.stderr
+        rec = json.loads(p.stdout.strip().splitlines()[-1])
+        assert rec["ok"] is True and rec["checked"] is True and rec["gpus"] == gpus and rec["iters"] == 40
+        assert abs(rec["norm"] - rec["cpu_norm"]) <= 1e-10 * abs(rec["cpu_norm"])
+        norms[fmt] = rec["norm"]
+    assert abs(norms["sigma_c"] - norms["csr"]) <= 1e-10 * abs(norms["csr"])
+    # text output keeps the reference's vocabulary
+    p = run(bins / "sigma_c", tmp_path, "--matrix", mtx, "--iters", "12", "--gpus", str(gpus))
+    assert p.returncode == 0 and "result is ok" in p.stdout and "PERFORMANCE" in p.stdout, p.stdout + p.stderr
+    # the synthetic Laplacian: same eigenvalue estimate whatever the device count (power iteration from
+    # the same seeded x0), and equal to the one-device run of the other driver
+    p = run(bins / "sigma_c", tmp_path, "--synthetic", "laplace7:20x16x27", "--iters", "30", "--gpus", str(gpus), "--json")
+    assert p.returncode == 0, p.stdout + p.stderr
+    a = json.loads(p.stdout.strip().splitlines()[-1])
+    p = run(bins / "csr", tmp_path, "--synthetic", "laplace7:20x16x27", "--iters", "30", "--json")
+    assert p.returncode == 0, p.stdout + p.stderr
+    b = json.loads(p.stdout.strip().splitlines()[-1])
+    assert a["rows"] == b["rows"] == 20 * 16 * 27 and a["nnz"] == b["nnz"]
+    assert abs(a["norm"] - b["norm"]) <= 1e-10 * b["norm"] and 0 < a["norm"] < 12.0
+    # argument errors
+    assert run(bins / "coo", tmp_path, "--iters", "3").returncode == 4
+    assert run(bins / "csr", tmp_path, "--gpus", "2").returncode == 4          # --gpus without --iters
+    assert run(bins / "csr", tmp_path, "--iters", "3", "--gpus", "64").returncode == 4

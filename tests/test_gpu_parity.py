@@ -267,14 +267,94 @@ def test_cmrs_long_strips(ctx, dtype):
     x = np.random.default_rng(4).uniform(-1, 1, n_cols)
     y_ref = O.yref(n_rows, rows, cols, vals, x)
     coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    ctx.set_option("B200_CMRS_STREAM", 0)      # this test is about the strip-splitting plan
     m = pkg.CmrsMatrix(pkg.CsrMatrix(coo))
     # strip 0 (~49 000 entries) -> 5 extra segments, strip 41 (~20 000) -> 2, strip 74 (~8 230) -> 1
-    assert m.plan_extra_items() == 8
+    assert m.plan_extra_items() == 8 and m.plan_stream_tiles() == 0
     xd = ctx.array(x.astype(dtype))
     for use_plan in (True, False):
         yd = ctx.array(np.full(n_rows, np.nan, dtype))
         m.spmv(xd, yd, use_plan=use_plan)
         check_y(f"cmrs-long-plan{use_plan}", yd.download(), y_ref, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("height", [8, 5, 32])
+def test_cmrs_stream_kernel(ctx, dtype, height):
+    """The nnz-split CMRS kernel (skewed strip lengths: warps own 512-entry tiles, not strips): picked
+    by the plan on a hub-row matrix, forced on a ragged one; strips that span many tiles, tiles that
+    span many strips, EMPTY strips (runs of empty rows) in the middle and at the end, both layouts
+    (two arrays / packed) and both load-batch depths."""
+    rng = np.random.default_rng(77)
+    n_cols = 70000
+    x = rng.uniform(-1, 1, n_cols)
+    xd = ctx.array(x.astype(dtype))
+    # (a) hub rows: chosen automatically
+    n_rows = 600
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 10, 71,
+                                            long_rows=((3, 40000), (4, 9000), (333, 20000), (599, 8193)))
+    if height == 32:       # 19 strips of 32 rows: the hubs no longer stand out against the mean strip
+        ctx.set_option("B200_CMRS_STREAM", 1)
+    cmrs = pkg.CmrsMatrix(pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)), height=height)
+    assert cmrs.plan_stream_tiles() == -(-rows.size // 512)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    for u in (1, 2):
+        ctx.set_option("B200_CMRS_U", u)
+        for name, m in (("two-array", cmrs), ("packed", cmrs.packed())):
+            yd = ctx.array(np.full(n_rows, np.nan, dtype))
+            m.spmv(xd, yd)
+            check_y(f"cmrs-stream {name} U={u}", yd.download(), y_ref, dtype)
+    # (b) forced, with empty rows: 100 empty rows (= whole empty strips) after row 40, 3 short rows,
+    # 500 empty rows at the end
+    lens = np.concatenate([rng.integers(1, 90, 41), np.zeros(100, int), [700, 1, 2], rng.integers(0, 3, 300),
+                           [3000], np.zeros(500, int)])
+    n_rows = lens.size
+    rows = np.repeat(np.arange(n_rows, dtype=np.int32), lens)
+    cols = np.concatenate([np.sort(rng.choice(n_cols, int(k), replace=False)) for k in lens if k]).astype(np.int32)
+    vals = rng.uniform(-1, 1, rows.size)
+    ctx.set_option("B200_CMRS_STREAM", 1)
+    cmrs = pkg.CmrsMatrix(pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)), height=height)
+    assert cmrs.plan_stream_tiles() == -(-rows.size // 512)
+    yd = ctx.array(np.full(n_rows, np.nan, dtype))
+    cmrs.spmv(xd, yd)
+    check_y("cmrs-stream empty strips", yd.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sell_narrow_chunks(ctx, dtype):
+    """Chunks of at most 8 columns (stencil matrices) take the lane = row path of the SELL kernel: rows
+    of 1..8 entries, a chunk of exactly 8 next to one of 9 (the wide path), a partly empty last chunk,
+    sigma-sorted layouts, and the launch-overlap variant."""
+    n_rows, n_cols = 5003, 9000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 8, 55, long_rows=((100, 9), (4000, 40)))
+    x = np.random.default_rng(56).uniform(-1, 1, n_cols)
+    y_ref = O.yref(n_rows, rows, cols, vals, x)
+    csr = pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals))
+    xd = ctx.array(x.astype(dtype))
+    for sigma in (1, 64, 4096):
+        sell = pkg.SellMatrix(csr, dtype, sigma=sigma)
+        for wpc in (None, 1):
+            for overlap in (False, True):
+                ctx.set_option("B200_SELL_WPC", wpc)
+                ctx.set_launch_overlap(overlap)
+                yd = ctx.array(np.full(n_rows, np.nan, dtype))
+                sell.spmv(xd, yd)
+                ctx.set_launch_overlap(True)       # the default of a library-owned queue
+                check_y(f"sell-narrow sigma={sigma} wpc={wpc} overlap={overlap}", yd.download(), y_ref, dtype)
+
+
+def test_used_column_blocks(ctx):
+    """b200_used_column_blocks: which 2^k-column blocks of x a row block reads (what e2e callers upload)."""
+    rng = np.random.default_rng(5)
+    n_cols = 1 << 20
+    cols = np.concatenate([rng.integers(5000, 9000, 1000), rng.integers(n_cols - 3000, n_cols, 500), [0]]).astype(np.int32)
+    cd = ctx.array(cols)
+    for k in (0, 8, 12, 20):
+        used = np.full(((n_cols - 1) >> k) + 1, 7, np.uint8)
+        pkg.check(pkg.lib().b200_used_column_blocks(ctx.h, cd.ptr, cols.size, n_cols, k, used.ctypes.data), "used blocks")
+        want = np.zeros_like(used)
+        want[np.unique(cols >> k)] = 1
+        np.testing.assert_array_equal(used, want)
 
 
 @pytest.mark.parametrize("height", [1, 2, 5, 8, 16, 32])
@@ -391,7 +471,7 @@ VARIANT_HOOKS = {
     "ell": [{"B200_ELL_LANES": l, "B200_ELL_UNROLL": u} for l in (2, 4, 8, 16, 32) for u in (1, 2, 4)],
     "sell": [{"B200_SELL_WPC": w, "B200_SELL_UNROLL": u} for w in (1, 2, 4, 8) for u in (1, 2, 4)],
     "coo": [{"B200_COO_U": u} for u in (1, 2, 4)],
-    "cmrs": [{"B200_CMRS_U": u} for u in (1, 2)],
+    "cmrs": [{"B200_CMRS_U": u, "B200_CMRS_WPS": w} for u in (1, 2) for w in (1, 2, 4)],
 }
 
 
@@ -521,6 +601,7 @@ def test_launch_overlap_chain_is_bit_identical(ctx, dtype):
 
     for name, mat in m.items():
         a, b = ctx.array(x0), ctx.zeros(n, dtype)
+        ctx.set_launch_overlap(False)
         chain(mat, a, b)                                 # in order (also creates the plans)
         want = a.download()
         assert np.isfinite(want).all() and np.abs(want).max() > 0
@@ -535,7 +616,7 @@ def test_launch_overlap_chain_is_bit_identical(ctx, dtype):
             g.launch()
             got_graph = a3.download()
         finally:
-            ctx.set_launch_overlap(False)
+            ctx.set_launch_overlap(True)                 # the default of a library-owned queue
         if name == "coo":                                # atomics: same values up to summation order
             scale = np.abs(want).max()
             assert np.abs(got.astype(np.float64) - want).max() <= 100 * TOL[np.dtype(dtype)] * scale
@@ -543,3 +624,33 @@ def test_launch_overlap_chain_is_bit_identical(ctx, dtype):
         else:
             assert got.tobytes() == want.tobytes(), name
             assert got_graph.tobytes() == want.tobytes(), name
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_launch_overlap_is_fenced_by_everything_else(ctx, dtype):
+    """Launch overlap is on by default on a library-owned queue.  It must be invisible: an SpMV issued
+    right after an UPLOAD into a matrix array, a device-side BUILD or a memset must see the new data
+    although back-to-back SpMV launches may start early.  A multi-megabyte upload lasts far longer than a
+    kernel needs to start, so a kernel that streamed its matrix arrays early would read the old values."""
+    n_rows, n_cols = 40000, 40000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 20, 60, 123)
+    x = np.random.default_rng(124).uniform(-1, 1, n_cols)
+    coo = pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals)
+    xd = ctx.array(x.astype(dtype))
+    yd = ctx.zeros(n_rows, dtype)
+    csr = pkg.CsrMatrix(coo)
+    csr.plan()
+    vd = coo.values(dtype)
+    rng = np.random.default_rng(125)
+    for trial in range(6):
+        for _ in range(3):                    # a chain of overlapping launches is in flight ...
+            csr.spmv(xd, yd)
+        new_vals = rng.uniform(-1, 1, vals.size)
+        vd.upload(new_vals.astype(dtype))     # ... when the value array is overwritten (asynchronous copy)
+        csr.spmv(xd, yd)                      # must read the NEW values
+        check_y(f"csr after upload {trial}", yd.download(), O.yref(n_rows, rows, cols, new_vals, x), dtype)
+        # a device-side build between two launches: the SELL fill writes the arrays the next launch reads
+        coo.vals64.upload(new_vals)
+        sell = pkg.SellMatrix(csr, dtype)     # b200_build_sell_* kernels, no sync
+        sell.spmv(xd, yd)
+        check_y(f"sell after build {trial}", yd.download(), O.yref(n_rows, rows, cols, new_vals, x), dtype)
