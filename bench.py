@@ -565,8 +565,10 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
     ranges = pkg.exchange_col_ranges(pkg, ctx, coo.cols, lo, world)
     halo = pkg.halo_rows(ranges, blocks, rank)
     halo_bytes = 8 * sum(h - l for d, (l, h) in enumerate(zip(*halo)) if d != rank)
-    G = 10
-    K = max(G, min(steps, 200) // G * G)
+    # the K timed steps are ONE replay of a K-step launch graph: every replay of a graph that holds NCCL
+    # nodes ends in a host callback (~0.5 ms on this box), so short graphs pay it every few steps
+    K = max(10, min(steps, 200) // 2 * 2)
+    G = K
     warm = 1 + 2 * G    # step 0 is always direct; two replays record + warm the graph of this parity
 
     def start_vector():
@@ -668,7 +670,7 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
                     f"{world} row block(s) of {n_local} rows",
         "exchange": "fused: SELL-32 kernel stores each y row into the x buffers of the ranks that read it (own block + "
                     "halo planes, CUDA IPC peer memory) + one 256-byte ncclAllReduce per step; all issued by "
-                    f"b200_iterator_run as a launch graph of {G} steps",
+                    f"b200_iterator_run as ONE launch graph of {G} steps",
         "halo_bytes_sent_per_step_max_rank": int(halo_max),
         "gpu_launches": int(fused_launches),
         "direct_launches_no_graph": {"ms_per_step": round(direct_ms, 5)},
@@ -841,7 +843,12 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
         # column-major thread-per-row kernel is measured next to it
         # "cmrs_packed" = the derived 4+V bytes/entry layout (row_in_strip folded into the column word),
         # measured next to the reference two-array layout, never in the headline
-        return ({f: allm[f] for f in FORMATS}, {"ell_colmajor": allm["ellcm"], "cmrs_packed": allm["cmrs"].packed()})
+        extras = {"ell_colmajor": allm["ellcm"], "cmrs_packed": allm["cmrs"].packed()}
+        try:   # derived layout: 16-bit column deltas per SELL chunk (refused when a chunk spans > 65536 columns)
+            extras["sell_delta16"] = pkg.Sell16Matrix(allm["sell"])
+        except pkg.B200Error:
+            pass
+        return ({f: allm[f] for f in FORMATS}, extras)
 
     # The cant-shaped formats (53-70 MB each) fit in the 126 MB L2.  "Inputs larger than L2" is
     # restored by ROTATION: n_copies independent copies of every format's arrays (own COO triples,
@@ -907,7 +914,7 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
             for st in sets:
                 st[0][f].spmv(x, y[f])
         g_steps = record_steps(args.steps)
-        g_warm = record_steps(max(args.warmup, n_copies))
+        g_warm = g_steps     # warm-up = one full replay of the K-step graph (>= W steps, same clocks / caches)
         n_f = 4 * n_copies
         g_fmt = {f: record_format(f, 0, n_f) for f in mats}
         e0, e1 = ctx.event(), ctx.event()

@@ -47,6 +47,9 @@ enum {
     B200_ERR_COMM = 7    /* NCCL reported an error (synchronously, or asynchronously: b200_comm_check) */
 };
 
+/* the reference's five formats, in the order of its README */
+enum { B200_FORMAT_COO = 0, B200_FORMAT_CSR = 1, B200_FORMAT_ELL = 2, B200_FORMAT_SELL = 3, B200_FORMAT_CMRS = 4 };
+
 typedef struct b200_ctx b200_ctx;     /* cl_context + cl_command_queue */
 typedef struct b200_event b200_event; /* cl_event, but with device timestamps */
 
@@ -405,6 +408,65 @@ int b200_sumsq_f64(b200_ctx *ctx, const double *y, long long n, double *acc_devi
 
 
 /* =====================================================================================
+ * Fewer bytes, format advice, conversions (new).  Derived device layouts and helpers: the
+ * reference's arrays (sigma_c.c:40-43 etc.) stay the bit-exact build product.
+ * ===================================================================================== */
+
+/* SELL-32 with 16-bit column deltas ("sell16").  indices[j] = (chunk_base[s] + delta16[j]) mod n_cols
+ * for the entries j of chunk s; chunk_base[s] = the chunk's smallest column, or, when the chunk's band
+ * wraps around the matrix edge (periodic stencils), its smallest column in the upper half; padding
+ * slots ((column 0, value 0) in the format itself) get delta 0.  2 + V bytes per entry instead of 4 + V.
+ * Needs every chunk's columns to span at most 65536 modulo n_cols (banded / FEM matrices):
+ * B200_ERR_UNSUPPORTED otherwise.  sigma = 1 layout with int32 chunk pointers; delta16 has as many
+ * entries as indices. */
+int b200_sell_pack16_f64(b200_ctx *ctx, const double *data, const int *indices, const int *row_indices, int n_slices,
+                         int n_cols, int *chunk_base, unsigned short *delta16);
+int b200_sell_pack16_f32(b200_ctx *ctx, const float *data, const int *indices, const int *row_indices, int n_slices,
+                         int n_cols, int *chunk_base, unsigned short *delta16);
+int b200_spmv_sell16_f64(b200_ctx *ctx, const double *data, const unsigned short *delta16, const int *chunk_base,
+                         const double *vect, double *output, const int *row_indices, int chunk, int n_slices,
+                         int n_out, int n_cols);
+int b200_spmv_sell16_f32(b200_ctx *ctx, const float *data, const unsigned short *delta16, const int *chunk_base,
+                         const float *vect, float *output, const int *row_indices, int chunk, int n_slices,
+                         int n_out, int n_cols);
+
+/* Back to CSR on the device, so that any format converts to any other through CSR and the builders
+ * above.  Padding slots ((column 0, value 0)) are dropped.  ptr has n_rows + 1 entries; cols / vals may
+ * be NULL to get the row pointer (and *nnz) first and allocate; nnz may be NULL (no sync then). */
+int b200_ell_to_csr_f64(b200_ctx *ctx, const double *data, const int *indices, int n_rows, int row_size, int *ptr,
+                        int *cols, double *vals, long long *nnz);
+int b200_ell_to_csr_f32(b200_ctx *ctx, const float *data, const int *indices, int n_rows, int row_size, int *ptr,
+                        int *cols, float *vals, long long *nnz);
+int b200_sell_to_csr_f64(b200_ctx *ctx, const double *data, const int *indices, const int *row_indices, int n_rows,
+                         int *ptr, int *cols, double *vals, long long *nnz);
+int b200_sell_to_csr_f32(b200_ctx *ctx, const float *data, const int *indices, const int *row_indices, int n_rows,
+                         int *ptr, int *cols, float *vals, long long *nnz);
+/* CMRS keeps its entries in CSR order (cmrs.c:84-113): only the row pointer has to be rebuilt.
+ * B200_ERR_DOMAIN if the rows inside a strip are not sorted. */
+int b200_cmrs_to_csr_ptr(b200_ctx *ctx, const int *strip_ptr, const int *row_in_strip, int n_strips, int height,
+                         int n_rows, int *ptr);
+
+/* Format advice from the row statistics: algorithmic bytes per SpMV of every format for this matrix
+ * (SURVEY 8d formulas, V = value_bytes) and the format to use.  bytes[] is indexed by B200_FORMAT_*. */
+typedef struct {
+    int n_rows;
+    long long nnz;
+    int min_len, max_len;
+    double mean_len;
+    int skewed;                       /* max_len > 16 x mean_len: power-law-like, gather-bound */
+    double sell_padding;              /* padded / nnz at sigma = 1 */
+    double sell_padding_sigma65536;   /* ... with rows sorted in windows of 65536 */
+    long long bytes[5];
+    long long bytes_sell_sigma65536;
+    long long bytes_sell16;           /* sigma = 1 with 16-bit deltas (if the matrix allows them) */
+    int recommended;                  /* B200_FORMAT_* */
+    int recommended_sigma;            /* for SELL */
+    char reason[160];
+} b200_format_advice_t;
+int b200_format_advice(b200_ctx *ctx, const int *ptr, int n_rows, int n_cols, int value_bytes,
+                       b200_format_advice_t *advice);
+
+/* =====================================================================================
  * Iterated (power-iteration) mode behind the C ABI (new; SURVEY 8b viii, 8e).  The reference's
  * device loop enumerates up to 8 GPUs and breaks after the first (csr.c:12,22-30,279); here one
  * rank = one context = one GPU, ranks being processes (peers mapped with b200_ipc_*) or threads of
@@ -441,7 +503,6 @@ int b200_halo_rows(const int *col_min, const int *col_max, int world, int rank, 
                    long long n_rows_total, int *lo, int *hi);
 
 /* ---- iterator: `steps` steps of  y = A_r x / ||x||_2 ;  x <- y  on row-partitioned A ---- */
-enum { B200_FORMAT_COO = 0, B200_FORMAT_CSR = 1, B200_FORMAT_ELL = 2, B200_FORMAT_SELL = 3, B200_FORMAT_CMRS = 4 };
 typedef struct {            /* this rank's row block, fp64, GLOBAL column indices, device arrays */
     int format;             /* B200_FORMAT_CSR or B200_FORMAT_SELL (chunk 32, no permutation) */
     int n_rows;             /* rows of the block */

@@ -53,7 +53,17 @@ class IterDesc(C.Structure):
                 ("graph_steps", C.c_int)]
 
 
+class FormatAdvice(C.Structure):
+    """b200_format_advice_t."""
+    _fields_ = [("n_rows", C.c_int), ("nnz", C.c_longlong), ("min_len", C.c_int), ("max_len", C.c_int),
+                ("mean_len", C.c_double), ("skewed", C.c_int), ("sell_padding", C.c_double),
+                ("sell_padding_sigma65536", C.c_double), ("bytes", C.c_longlong * 5),
+                ("bytes_sell_sigma65536", C.c_longlong), ("bytes_sell16", C.c_longlong), ("recommended", C.c_int),
+                ("recommended_sigma", C.c_int), ("reason", C.c_char * 160)]
+
+
 FORMAT_COO, FORMAT_CSR, FORMAT_ELL, FORMAT_SELL, FORMAT_CMRS = range(5)
+FORMAT_NAMES = ("coo", "csr", "ell", "sell", "cmrs")
 ITER_FUSED, ITER_ALLGATHER = 0, 1
 COMM_ID_BYTES = 128
 
@@ -175,6 +185,16 @@ SIGNATURES = {
     "b200_iterator_norm": (_i, [_vp, C.POINTER(C.c_double)]),
     "b200_iterator_state": (_i, [_vp, C.POINTER(C.c_ulonglong), _vpp, C.POINTER(C.c_ulonglong)]),
     "b200_iterator_destroy": (_i, [_vp]),
+    "b200_sell_pack16_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "b200_sell_pack16_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "b200_spmv_sell16_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "b200_spmv_sell16_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "b200_ell_to_csr_f64": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_ll)]),
+    "b200_ell_to_csr_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_ll)]),
+    "b200_sell_to_csr_f64": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_ll)]),
+    "b200_sell_to_csr_f32": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_ll)]),
+    "b200_cmrs_to_csr_ptr": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200_format_advice": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(FormatAdvice)]),
     "b200_scale_f64": (_i, [_vp, _vp, _ll, _vp, _i]),
     "b200_sumsq_f64": (_i, [_vp, _vp, _ll, _vp]),
 }
@@ -388,7 +408,7 @@ class Event:
             pass
 
 
-from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, CmrsMatrix, CmrsPackedMatrix,  # noqa: E402,F401
-                      algorithmic_bytes, build_all, partition_rows)
+from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, Sell16Matrix, CmrsMatrix,  # noqa: E402,F401
+                      CmrsPackedMatrix, algorithmic_bytes, build_all, partition_rows)
 from .iterate import (Comm, Iterator, PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges,  # noqa: E402,F401
                       gpu_callables, halo_rows, power_iteration, power_iteration_ring, power_iteration_fused)

@@ -484,9 +484,10 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     const int lane = threadIdx.x & 31;
     const long long slice = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const bool active = slice < n_slices;  // no early return: the block reduces ||y||^2 together
-    // 1/||x||: one coalesced load of the 32 partial sums per warp, folded with shuffles
-    T alpha = 1;
-    if (scale2) alpha = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
+    // 1/||x||: one coalesced load of the 32 partial sums per warp, issued now and folded (shuffles +
+    // rsqrt) only after the dot product, so its latency hides behind the matrix loads
+    T scale_part = 0;
+    if (scale2) scale_part = __ldg(scale2 + lane);
     T mine = 0;  // row `lane` of this warp's chunk
     if (active) {
         const long long chunk_base = slice_ptr[slice];
@@ -523,7 +524,7 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
             mine = (lane & 2) ? ((lane & 1) ? b3 : b2) : ((lane & 1) ? b1 : b0);
         }
     }
-    mine *= alpha;
+    if (scale2) mine *= rsqrt(subwarp_sum<32>(scale_part));
     const long long r = slice * 32 + lane;
     T sq = 0;
     if (active && r < n_rows) {

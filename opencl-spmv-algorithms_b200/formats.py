@@ -19,7 +19,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import (Context, CsrPlanInfo, DeviceArray, RowStats, check, lib, suffix)
+from . import (Context, CsrPlanInfo, DeviceArray, FormatAdvice, RowStats, check, lib, suffix)
 
 I4 = 4
 
@@ -104,6 +104,13 @@ class CsrMatrix:
     def nbytes(self, dtype) -> int:
         V = np.dtype(dtype).itemsize
         return algorithmic_bytes("csr", V, n_rows=self.n_rows, n_cols=self.n_cols, nnz=self.nnz)
+
+    def advice(self, dtype) -> FormatAdvice:
+        """b200_format_advice: per-format bytes for this matrix and the format to use."""
+        a = FormatAdvice()
+        check(lib().b200_format_advice(self.ctx.h, self.ptr.ptr, self.n_rows, self.n_cols, np.dtype(dtype).itemsize,
+                                       C.byref(a)), "b200_format_advice")
+        return a
 
     def __del__(self):
         try:
@@ -238,6 +245,31 @@ class SellMatrix:
         return algorithmic_bytes("sell", self.dtype.itemsize, n_rows=self.n_rows,
                                  n_cols=self.n_cols, padded=self.total, n_slices=self.n_slices,
                                  ptr_bytes=8 if self.wide else 4, perm=self.perm is not None)
+
+
+class Sell16Matrix:
+    """SELL-32 with 16-bit column deltas (b200_sell_pack16_*): a derived layout of a sigma = 1
+    SellMatrix, 2 + V bytes per entry.  Raises B200Error(UNSUPPORTED) when a chunk spans > 65536 columns."""
+
+    def __init__(self, sell: "SellMatrix"):
+        assert sell.perm is None and sell.row_indices is not None, "sell16: sigma = 1, int32 chunk pointers"
+        self.ctx, self.sell, self.dtype = sell.ctx, sell, sell.dtype
+        self.n_rows, self.n_cols, self.nnz = sell.n_rows, sell.n_cols, sell.nnz
+        self.chunk_base = self.ctx.empty(sell.n_slices, np.int32)
+        self.delta16 = self.ctx.empty(sell.total, np.uint16)
+        fn = getattr(lib(), "b200_sell_pack16_" + suffix(self.dtype))
+        check(fn(self.ctx.h, sell.data.ptr, sell.cols.ptr, sell.row_indices.ptr, sell.n_slices, self.n_cols,
+                 self.chunk_base.ptr, self.delta16.ptr), "b200_sell_pack16")
+
+    def spmv(self, x: DeviceArray, y: DeviceArray, n_out: int | None = None) -> None:
+        s = self.sell
+        fn = getattr(lib(), "b200_spmv_sell16_" + suffix(self.dtype))
+        check(fn(self.ctx.h, s.data.ptr, self.delta16.ptr, self.chunk_base.ptr, x.ptr, y.ptr, s.row_indices.ptr, 32,
+                 s.n_slices, self.n_rows if n_out is None else n_out, self.n_cols), "b200_spmv_sell16")
+
+    def nbytes(self, dtype=None) -> int:
+        V, s = self.dtype.itemsize, self.sell
+        return s.total * (2 + V) + (s.n_slices + 1) * I4 + s.n_slices * I4 + (self.n_cols + self.n_rows) * V
 
 
 class CmrsMatrix:

@@ -654,3 +654,118 @@ def test_launch_overlap_is_fenced_by_everything_else(ctx, dtype):
         sell = pkg.SellMatrix(csr, dtype)     # b200_build_sell_* kernels, no sync
         sell.spmv(xd, yd)
         check_y(f"sell after build {trial}", yd.download(), O.yref(n_rows, rows, cols, new_vals, x), dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sell16_column_deltas_round_trip_and_spmv(ctx, dtype):
+    """SELL-32 with 16-bit column deltas: chunk_base + delta16 must reproduce the reference's 32-bit
+    indices bit for bit (padding slots -> the chunk base), the kernel must give the same bits as the
+    32-bit SELL kernel (same order of operations), for every load-batch depth; a chunk spanning more
+    than 65536 columns is refused."""
+    n_rows, n_cols = 4099, 300000
+    rng = np.random.default_rng(31)
+    lens = rng.integers(1, 70, n_rows)
+    centre = np.linspace(40000, n_cols - 40000, n_rows).astype(np.int64)
+    rows = np.repeat(np.arange(n_rows, dtype=np.int32), lens)
+    cols = np.concatenate([np.sort(rng.choice(np.arange(c - 30000, c + 30000) if r >= 64 else np.arange(1, 30000),
+                                              int(k), replace=False))
+                           for r, (c, k) in enumerate(zip(centre, lens))]).astype(np.int32)
+    first = np.flatnonzero(rows == 0)             # a REAL entry in column 0, with a non-zero value
+    cols[first] = np.sort(np.concatenate(([0], rng.choice(np.arange(1, 60000), first.size - 1, replace=False))))
+    r40 = np.flatnonzero(rows == 40)              # a band that wraps around the matrix edge (periodic stencil)
+    cols[r40] = np.sort(np.concatenate(([n_cols - 7], rng.choice(np.arange(0, 30000), r40.size - 1, replace=False))))
+    r5 = np.flatnonzero(rows == 5)
+    cols[r5] = np.sort(np.concatenate(([n_cols - 3], rng.choice(np.arange(0, 30000), r5.size - 1, replace=False))))
+    vals = rng.uniform(-1, 1, rows.size)
+    x = rng.uniform(-1, 1, n_cols)
+    csr = pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals))
+    sell = pkg.SellMatrix(csr, dtype)
+    s16 = pkg.Sell16Matrix(sell)
+    base = s16.chunk_base.download()
+    d16 = s16.delta16.download()
+    idx, dat, ri = sell.cols.download(), sell.data.download(), sell.row_indices.download()
+    real = (idx != 0) | (dat != 0)
+    chunk_of = np.repeat(np.arange(sell.n_slices), np.diff(ri))
+    np.testing.assert_array_equal((base[chunk_of][real] + d16[real].astype(np.int64)) % n_cols, idx[real])
+    assert np.all(d16[~real] == 0)
+    for s in range(2, sell.n_slices):             # (chunks 0 and 1 wrap, see below) base = smallest real column
+        sl = slice(ri[s], ri[s + 1])
+        r = real[sl]
+        assert base[s] == (idx[sl][r].min() if r.any() else 0)
+    assert base[1] > n_cols // 2                  # row 40 reaches back past column 0: the chunk's band wraps
+    xd = ctx.array(x.astype(dtype))
+    y32 = ctx.array(np.full(n_rows, np.nan, dtype))
+    ctx.set_option("B200_SELL_WPC", 1)
+    for u in (1, 2, 4):
+        ctx.set_option("B200_SELL_UNROLL", u)
+        sell.spmv(xd, y32)
+        y16 = ctx.array(np.full(n_rows, np.nan, dtype))
+        s16.spmv(xd, y16)
+        check_y(f"sell16 U={u}", y16.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+        assert y16.download().tobytes() == y32.download().tobytes()
+    assert s16.nbytes() == sell.nbytes() - 2 * sell.total + 4 * sell.n_slices
+    # too wide: a row touching both ends of a 300 000-column matrix
+    rows2, cols2, vals2 = random_sorted_matrix(64, n_cols, 2, 2, 32)
+    cols2[0], cols2[1] = 100000, 200000
+    wide = pkg.SellMatrix(pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, 64, n_cols, rows2, cols2, vals2)), dtype)
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.Sell16Matrix(wide)
+    assert e.value.status == pkg.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_conversions_back_to_csr(ctx, dtype):
+    """ELL / SELL / CMRS -> CSR on the device: the row pointer, columns and values of the original CSR
+    come back bit for bit (every format converts to every other through CSR and the builders)."""
+    import ctypes as C
+    L = pkg.lib()
+    suf = pkg.suffix(dtype)
+    n_rows, n_cols = 3001, 5000
+    rows, cols, vals = random_sorted_matrix(n_rows, n_cols, 1, 40, 41, long_rows=((7, 300), (3000, 2)))
+    m = pkg.build_all(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals), dtype)
+    ptr_ref = m["csr"].ptr.download()
+    vals_t = vals.astype(dtype)
+
+    def convert(fn, *args):
+        ptr = ctx.empty(n_rows + 1, np.int32)
+        nnz = C.c_longlong(0)
+        pkg.check(fn(ctx.h, *args, ptr.ptr, None, None, C.byref(nnz)), "to_csr (count)")
+        assert nnz.value == rows.size
+        c, v = ctx.empty(nnz.value, np.int32), ctx.empty(nnz.value, dtype)
+        pkg.check(fn(ctx.h, *args, ptr.ptr, c.ptr, v.ptr, None), "to_csr (fill)")
+        np.testing.assert_array_equal(ptr.download(), ptr_ref)
+        np.testing.assert_array_equal(c.download(), cols)
+        assert v.download().tobytes() == vals_t.tobytes()
+
+    ell, sell, cmrs = m["ell"], m["sell"], m["cmrs"]
+    convert(getattr(L, "b200_ell_to_csr_" + suf), ell.data.ptr, ell.cols.ptr, n_rows, ell.row_size)
+    convert(getattr(L, "b200_sell_to_csr_" + suf), sell.data.ptr, sell.cols.ptr, sell.row_indices.ptr, n_rows)
+    ptr = ctx.empty(n_rows + 1, np.int32)
+    pkg.check(L.b200_cmrs_to_csr_ptr(ctx.h, cmrs.strip_ptr.ptr, cmrs.row_in_strip.ptr, cmrs.n_strips, cmrs.height, n_rows,
+                                     ptr.ptr), "b200_cmrs_to_csr_ptr")
+    np.testing.assert_array_equal(ptr.download(), ptr_ref)
+
+
+def test_format_advice(ctx):
+    """b200_format_advice: per-format bytes equal the byte model of formats.py, regular matrices get the
+    format with the fewest bytes, power-law ones SELL-sigma or CSR, never ELL."""
+    # regular, uniform rows: CSR / SELL / ELL within a few bytes -> SELL
+    rows, cols, vals = random_sorted_matrix(4096, 5000, 24, 24, 51)
+    csr = pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, 4096, 5000, rows, cols, vals))
+    a = csr.advice(np.float32)
+    m = pkg.build_all(csr.coo, np.float32)
+    for i, f in enumerate(pkg.FORMAT_NAMES):
+        assert a.bytes[i] == m[f].nbytes(np.float32), f
+    assert a.bytes_sell16 == pkg.Sell16Matrix(m["sell"]).nbytes()
+    assert pkg.FORMAT_NAMES[a.recommended] == "sell" and not a.skewed and a.sell_padding == 1.0
+    # ragged rows (1..60): ELL and SELL pad, CSR has the fewest bytes
+    rows, cols, vals = random_sorted_matrix(4096, 5000, 1, 60, 52)
+    a = pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, 4096, 5000, rows, cols, vals)).advice(np.float64)
+    assert pkg.FORMAT_NAMES[a.recommended] == "csr" and a.bytes[pkg.FORMAT_ELL] > a.bytes[pkg.FORMAT_CSR]
+    # hub rows: skewed -> SELL sigma-sorted when sorting removes the padding
+    rows, cols, vals = random_sorted_matrix(70000, 70000, 1, 6, 53, long_rows=((5, 30000), (40000, 20000)))
+    a = pkg.CsrMatrix(pkg.CooMatrix.from_host(ctx, 70000, 70000, rows, cols, vals)).advice(np.float32)
+    assert a.skewed and pkg.FORMAT_NAMES[a.recommended] in ("sell", "csr") and pkg.FORMAT_NAMES[a.recommended] != "ell"
+    assert a.sell_padding > a.sell_padding_sigma65536 >= 1.0
+    assert (a.recommended_sigma == 65536) == (pkg.FORMAT_NAMES[a.recommended] == "sell")
+    assert a.reason.decode().startswith("skewed rows")
