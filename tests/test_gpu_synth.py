@@ -340,62 +340,3 @@ def test_halo_limited_exchange_three_emulated_ranks(ctx):
             assert np.all(got[outside] == SENTINEL), r
         assert not np.any(got[need_lo:need_hi] == SENTINEL)
 
-
-def test_ring_exchange_three_emulated_ranks(ctx):
-    """b200_spmv_sell_ring_f64: the same three emulated ranks, but no host-side all-reduce at all --
-    the ranks hand over partial sums of ||y||^2 and 'step done' flags through their sync blocks.  Each
-    emulated rank has its own context (stream) on the one GPU, so a rank's sync kernel can wait for the
-    others' flags while their kernels run: the data flow (flags, partial sums, halo stores, double
-    buffering) is the real one."""
-    import ctypes as C
-    L = pkg.lib()
-    nx, ny, nz, steps, G = 16, 12, 30, 24, 3
-    n, rows, cols, vals = laplace7(nx, ny, nz)
-    blocks = pkg.equal_row_blocks(n, G)
-    x0 = np.zeros(blocks.padded)
-    x0[:n] = np.random.default_rng(6).uniform(0, 1, n)
-    ptr, _ = O.build_csr(n, rows)
-    x = x0[:n].copy()
-    for _ in range(steps):
-        y = O.spmv_csr(n, ptr, cols, vals, x)
-        nrm = np.linalg.norm(y)
-        x = y / nrm
-    ctxs = [pkg.Context(0) for _ in range(G)]
-    sells, ranges, n_local = [], [], []
-    for r in range(G):
-        b0, b1 = blocks.bounds(r)
-        sel = slice(ptr[b0], ptr[b1])
-        coo = pkg.CooMatrix.from_host(ctxs[r], b1 - b0, n, rows[sel] - b0, cols[sel], vals[sel])
-        sells.append(pkg.SellMatrix(pkg.CsrMatrix(coo), np.float64))
-        ranges.append((int(cols[sel].min()), int(cols[sel].max())))
-        n_local.append(b1 - b0)
-    halos = [pkg.halo_rows(ranges, blocks, r) for r in range(G)]
-    bufs = [[ctxs[r].array(x0 if b == 0 else np.zeros(blocks.padded)) for b in range(2)] for r in range(G)]
-    sync = [ctxs[r].zeros(16384 // 8, np.float64) for r in range(G)]
-    sync_ptrs = (C.c_void_p * G)(*[s.ptr for s in sync])
-    for c in ctxs:
-        c.sync()
-    for k in range(steps):
-        cur, nxt = k % 2, (k + 1) % 2
-        for r in range(G):
-            dst = (C.c_void_p * G)(*[bufs[d][nxt].ptr for d in range(G)])
-            lo_a, hi_a = (C.c_int * G)(*halos[r][0]), (C.c_int * G)(*halos[r][1])
-            pkg.check(L.b200_spmv_sell_ring_f64(
-                ctxs[r].h, sells[r].data.ptr, sells[r].cols.ptr, bufs[r][cur].ptr, sells[r].row_indices.ptr, 32,
-                sells[r].n_slices, n_local[r], dst, G, r * blocks.count, lo_a, hi_a, sync_ptrs, r, k),
-                "b200_spmv_sell_ring_f64")
-    for c in ctxs:
-        c.sync()                                          # also reports a timed-out flag wait
-    last = steps - 1
-    at = 16 + (last & 1) * 16 * 32
-    for r in range(G):
-        words = sync[r].download()
-        assert np.array_equal(words[:G].view(np.uint64), np.full(G, steps, np.uint64))     # flags
-        norm = np.sqrt(words[at:at + G * 32].sum())
-        assert abs(norm - nrm) <= 1e-12 * nrm
-        b0, b1 = blocks.bounds(r)
-        own = bufs[r][steps % 2].download()[b0:b1]
-        assert np.max(np.abs(own / norm - x[b0:b1])) <= 1e-12
-    del sells, bufs, sync
-    for c in ctxs:
-        c.close()
