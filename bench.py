@@ -578,10 +578,10 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
         bufs.local[1].fill_bytes(0)
         D.barrier(ctx)
 
-    def run(mode, matrix, h, graph_steps=G):
+    def run(mode, matrix, h, graph_steps=G, mcast=None):
         start_vector()
         it = pkg.Iterator(pkg, ctx, comm, matrix, blocks, rank, world, bufs.ptrs[:2], mode=mode, halo=h,
-                          graph_steps=graph_steps)
+                          graph_steps=graph_steps, mcast=mcast)
         it.run(warm)
         D.barrier(ctx)
         n0 = it.state()[2]
@@ -600,6 +600,25 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
         fused_ms, fused_norm, fused_launches = run("fused", sell, halo)
     ag_ms, ag_norm, _ = run("allgather", csr, None)
     direct_ms, direct_norm, _ = run("fused", sell, halo, graph_steps=0)   # same steps, launch by launch
+    # the same kernel with the all-reduce + barrier done by the NVSwitch (multimem.red on a multicast block):
+    # two launches per step and no NCCL call; where the box cannot set multicast up this stays null
+    mc_ms = mc_norm = None
+    mc_note = "one rank: nothing to exchange"
+    if world > 1:
+        sup = C.c_int(0)
+        pkg.check(L.b200_mcast_supported(ctx.h, C.byref(sup)), "b200_mcast_supported")
+        (all_sup,) = D.reduce([-float(sup.value)], "max")
+        mc_note = "NVLink multicast not supported by the device / driver"
+        if all_sup == -1.0:
+            try:
+                mc = pkg.McastBlock(pkg, ctx, rank, world)
+                mc_ms, mc_norm, _ = run("fused_mcast", sell, halo, mcast=mc)
+                ctx.sync()
+                D.barrier(ctx)
+                mc.close()
+                mc_note = "ran"
+            except pkg.B200Error as e:
+                mc_note = f"multicast set-up refused: {e}"
     full_ms = None
     if extras:
         full_ms, _, _ = run("fused", sell, None)                           # every row to every rank
@@ -651,6 +670,8 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
     L.b200_host_free_pinned(hx)
 
     fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms = D.reduce([fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms], "max")
+    if mc_ms is not None:
+        (mc_ms,) = D.reduce([mc_ms], "max")
     (nnz_total,) = D.reduce([nnz], "sum")
     (halo_max,) = D.reduce([halo_bytes], "max")
     if full_ms is not None:
@@ -678,6 +699,10 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
                                        "what": "CSR SpMV into the rank's segment, sum of squares, 1-element all-reduce, "
                                                "scale, in-place ncclAllGather; same launch-graph replay"},
         "fused_full_broadcast": None if full_ms is None else {"ms_per_step": round(full_ms, 5)},
+        "nvswitch_multicast": {"ms_per_step": None if mc_ms is None else round(mc_ms, 5), "norm": mc_norm, "status": mc_note,
+                               "parity_ok": None if mc_norm is None else bool(abs(mc_norm - fused_norm) <= 1e-10 * abs(fused_norm)),
+                               "what": "same fused kernel; the 32 partial sums are all-reduced and the ranks synchronised "
+                                       "by multimem.red on a multicast block (b200_mcast_*): two launches per step, no NCCL"},
         "norm_fused": fused_norm, "norm_allgather": ag_norm, "norm_fused_direct": direct_norm,
         "rel_diff": rel, "parity_tol": 1e-10, "parity_ok": parity_ok,
         "parity": "same x0 (seeded), same step count in every run; |norm_fused - norm_allgather| <= 1e-10 * norm, the "

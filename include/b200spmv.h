@@ -494,6 +494,37 @@ int b200_comm_allgather_f64(b200_comm *comm, double *full_device, long long coun
 /* threads-of-one-process ranks: let this context's device store into `peer_device`'s allocations */
 int b200_ctx_enable_peer_access(b200_ctx *ctx, int peer_device);
 
+/* ---- NVSwitch multicast block (new): one 2 MiB block of every rank's GPU memory bound to
+ *      ONE multicast object; a multimem.red to its address is carried out by the switch on every GPU's
+ *      copy.  The iterated mode uses it for the per-step all-reduce of the 32 partial sums of ||y||^2 and
+ *      the barrier that orders the halo stores -- one 32-thread kernel per step, no NCCL call
+ *      (B200_ITER_FUSED_MCAST).  Needs NVLink multicast support (b200_mcast_supported); every entry point
+ *      returns B200_ERR_UNSUPPORTED where the driver, the device or the container's permissions lack it.
+ *      Set-up, in this order:  rank 0 b200_mcast_create;  other ranks b200_mcast_import_pid_fd (other
+ *      processes: rank 0's pid and the descriptor it got), b200_mcast_import_fd (a descriptor received over
+ *      a socket) or b200_mcast_share (threads of rank 0's process);  ALL ranks b200_mcast_add_device;
+ *      barrier;  ALL ranks b200_mcast_bind;  barrier;  use;  b200_mcast_destroy. ---- */
+typedef struct b200_mcast b200_mcast;
+int b200_mcast_supported(b200_ctx *ctx, int *supported);
+int b200_mcast_create(b200_ctx *ctx, int world, b200_mcast **mcast, int *export_fd /* may be NULL */);
+int b200_mcast_import_fd(b200_ctx *ctx, int world, int fd, b200_mcast **mcast);
+int b200_mcast_import_pid_fd(b200_ctx *ctx, int world, int owner_pid, int owner_fd, b200_mcast **mcast);
+int b200_mcast_share(b200_ctx *ctx, const b200_mcast *owner, b200_mcast **mcast);
+int b200_mcast_add_device(b200_mcast *mcast);
+int b200_mcast_bind(b200_mcast *mcast);
+/* the multicast address (stores / reductions reach every rank's copy) and this rank's own copy */
+int b200_mcast_pointers(const b200_mcast *mcast, void **multicast_ptr, void **local_ptr, size_t *bytes);
+/* the two 32-slot device arrays of a step: the accumulator the fused SpMV kernel adds ||y_r||^2 into
+ * (sumsq_out) and the sums over all ranks that b200_mcast_allreduce_barrier leaves for the next kernel
+ * (scale_sumsq) */
+int b200_mcast_step_buffers(const b200_mcast *mcast, double **sumsq_accumulator, const double **summed_over_ranks);
+/* one launch on the context's queue: all-reduce of the accumulator over the ranks through the switch
+ * (multimem.red), arrival signal to every rank, wait for all ranks.  Work queued after it sees every
+ * rank's stores of the step.  All ranks must call it the same number of times; a rank that never arrives
+ * is reported as B200_ERR_CUDA by the next b200_sync after 2 s, not a hang. */
+int b200_mcast_allreduce_barrier(b200_mcast *mcast);
+int b200_mcast_destroy(b200_mcast *mcast);
+
 /* which rows of rank `rank`'s block every rank reads as columns (host function).  col_min[d] /
  * col_max[d] = smallest / largest global column index in rank d's matrix block (b200_minmax_i32 over
  * its column array, exchanged once).  Blocks are equal: rank r owns rows [r*rows_per_rank,
@@ -515,7 +546,9 @@ typedef struct {            /* this rank's row block, fp64, GLOBAL column indice
 enum {
     B200_ITER_FUSED = 0,    /* SELL kernel stores y straight into the x buffers of the ranks that read
                              * it (b200_spmv_sell_halo_f64) + one 256-byte all-reduce per step */
-    B200_ITER_ALLGATHER = 1 /* SpMV -> sum of squares -> all-reduce -> scale -> in-place ncclAllGather */
+    B200_ITER_ALLGATHER = 1, /* SpMV -> sum of squares -> all-reduce -> scale -> in-place ncclAllGather */
+    B200_ITER_FUSED_MCAST = 2 /* B200_ITER_FUSED with the all-reduce + barrier done through NVSwitch multicast
+                               * (b200_mcast_allreduce_barrier) instead of NCCL: two launches per step */
 };
 typedef struct {
     int mode;               /* B200_ITER_* */
@@ -528,9 +561,10 @@ typedef struct {
                              * to every rank */
     int graph_steps;        /* 0: every step is issued as separate launches; G (even): steps are recorded
                              * once into a launch graph of G steps and replayed (first step always direct) */
+    b200_mcast *mcast;      /* B200_ITER_FUSED_MCAST: this rank's bound multicast block */
 } b200_iter_desc;
 typedef struct b200_iterator b200_iterator;
-int b200_iterator_create(b200_ctx *ctx, b200_comm *comm /* NULL iff world == 1 */, const b200_block_f64 *block,
+int b200_iterator_create(b200_ctx *ctx, b200_comm *comm /* NULL iff world == 1 or FUSED_MCAST */, const b200_block_f64 *block,
                          const b200_iter_desc *desc, b200_iterator **iterator);
 /* enqueue `steps` more steps (asynchronous; all ranks must call it with the same counts) */
 int b200_iterator_run(b200_iterator *iterator, int steps);

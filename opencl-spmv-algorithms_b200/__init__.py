@@ -50,7 +50,7 @@ class IterDesc(C.Structure):
     """b200_iter_desc."""
     _fields_ = [("mode", C.c_int), ("world", C.c_int), ("rank", C.c_int), ("rows_per_rank", C.c_longlong),
                 ("x", C.POINTER(C.c_void_p) * 2), ("halo_lo", C.POINTER(C.c_int)), ("halo_hi", C.POINTER(C.c_int)),
-                ("graph_steps", C.c_int)]
+                ("graph_steps", C.c_int), ("mcast", C.c_void_p)]
 
 
 class FormatAdvice(C.Structure):
@@ -64,7 +64,7 @@ class FormatAdvice(C.Structure):
 
 FORMAT_COO, FORMAT_CSR, FORMAT_ELL, FORMAT_SELL, FORMAT_CMRS = range(5)
 FORMAT_NAMES = ("coo", "csr", "ell", "sell", "cmrs")
-ITER_FUSED, ITER_ALLGATHER = 0, 1
+ITER_FUSED, ITER_ALLGATHER, ITER_FUSED_MCAST = 0, 1, 2
 COMM_ID_BYTES = 128
 
 _vp, _i, _ll, _u64, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_uint64, C.c_size_t
@@ -180,6 +180,17 @@ SIGNATURES = {
     "b200_comm_allgather_f64": (_i, [_vp, _vp, _ll]),
     "b200_ctx_enable_peer_access": (_i, [_vp, _i]),
     "b200_halo_rows": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _vp]),
+    "b200_mcast_supported": (_i, [_vp, C.POINTER(_i)]),
+    "b200_mcast_create": (_i, [_vp, _i, _vpp, C.POINTER(_i)]),
+    "b200_mcast_import_fd": (_i, [_vp, _i, _i, _vpp]),
+    "b200_mcast_import_pid_fd": (_i, [_vp, _i, _i, _i, _vpp]),
+    "b200_mcast_share": (_i, [_vp, _vp, _vpp]),
+    "b200_mcast_add_device": (_i, [_vp]),
+    "b200_mcast_bind": (_i, [_vp]),
+    "b200_mcast_pointers": (_i, [_vp, _vpp, _vpp, C.POINTER(_sz)]),
+    "b200_mcast_step_buffers": (_i, [_vp, _vpp, _vpp]),
+    "b200_mcast_allreduce_barrier": (_i, [_vp]),
+    "b200_mcast_destroy": (_i, [_vp]),
     "b200_iterator_create": (_i, [_vp, _vp, C.POINTER(BlockF64), C.POINTER(IterDesc), _vpp]),
     "b200_iterator_run": (_i, [_vp, _i]),
     "b200_iterator_norm": (_i, [_vp, C.POINTER(C.c_double)]),
@@ -410,5 +421,5 @@ class Event:
 
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, Sell16Matrix, CmrsMatrix,  # noqa: E402,F401
                       CmrsPackedMatrix, algorithmic_bytes, build_all, partition_rows)
-from .iterate import (Comm, Iterator, PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges,  # noqa: E402,F401
+from .iterate import (Comm, Iterator, McastBlock, PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges,  # noqa: E402,F401
                       gpu_callables, halo_rows, power_iteration, power_iteration_ring, power_iteration_fused)

@@ -128,6 +128,21 @@ int issue_step(b200_iterator *it, unsigned long long k)
     const int cur = (int)(k & 1), nxt = cur ^ 1;
     const long long offset = (long long)d.rank * d.rows_per_rank;
     int rc;
+    if (d.mode == B200_ITER_FUSED_MCAST) {
+        double *sums = nullptr;
+        const double *summed = nullptr;
+        rc = b200_mcast_step_buffers(d.mcast, &sums, &summed);
+        if (rc) return rc;
+        rc = b200_spmv_sell_halo_f64(ctx, a.data, a.indices, it->xs[cur][d.rank], a.ptr, 32, a.n_slices, a.n_rows,
+                                     k > 0 ? summed : nullptr, sums, it->xs[nxt].data(), d.world, offset,
+                                     it->halo_lo.empty() ? nullptr : it->halo_lo.data(),
+                                     it->halo_hi.empty() ? nullptr : it->halo_hi.data());
+        if (rc) return rc;
+        rc = b200_mcast_allreduce_barrier(d.mcast);  // sums over ranks through the switch + the barrier
+        if (rc) return rc;
+        it->launches += 2;
+        return B200_SUCCESS;
+    }
     if (d.mode == B200_ITER_FUSED) {
         double *sums = it->acc + cur * B200_SUMSQ_SLOTS;
         const double *scale = k > 0 ? it->acc + nxt * B200_SUMSQ_SLOTS : nullptr;  // slots of step k-1
@@ -312,17 +327,21 @@ int b200_iterator_create(b200_ctx *ctx, b200_comm *comm, const b200_block_f64 *b
     B200_REQUIRE(block && desc && iterator, "null argument");
     *iterator = nullptr;
     const b200_iter_desc &d = *desc;
-    B200_REQUIRE(d.mode == B200_ITER_FUSED || d.mode == B200_ITER_ALLGATHER, "unknown mode");
+    B200_REQUIRE(d.mode == B200_ITER_FUSED || d.mode == B200_ITER_ALLGATHER || d.mode == B200_ITER_FUSED_MCAST, "unknown mode");
     B200_REQUIRE(d.world >= 1 && d.rank >= 0 && d.rank < d.world, "bad rank / world");
-    B200_REQUIRE((d.world == 1) == (comm == nullptr), "give a communicator exactly when world > 1");
+    if (d.mode == B200_ITER_FUSED_MCAST) {
+        B200_REQUIRE(d.mcast != nullptr && comm == nullptr, "the multicast mode takes a bound b200_mcast block and no communicator");
+    } else {
+        B200_REQUIRE((d.world == 1) == (comm == nullptr), "give a communicator exactly when world > 1");
+    }
     B200_REQUIRE(!comm || (comm->world == d.world && comm->rank == d.rank && comm->ctx == ctx),
                  "communicator belongs to another rank / world / context");
     B200_REQUIRE(d.rows_per_rank >= block->n_rows && d.rows_per_rank % 32 == 0, "rows_per_rank must be a multiple of 32 and >= n_rows");
     B200_REQUIRE(d.x[0] && d.x[1], "null x buffer tables");
     B200_REQUIRE(d.graph_steps >= 0 && d.graph_steps % 2 == 0, "graph_steps must be even (the x buffers alternate)");
     B200_REQUIRE(block->format == B200_FORMAT_CSR || block->format == B200_FORMAT_SELL, "block format must be CSR or SELL");
-    B200_REQUIRE(d.mode != B200_ITER_FUSED || block->format == B200_FORMAT_SELL, "the fused exchange is a SELL-32 kernel");
-    B200_REQUIRE(d.mode != B200_ITER_FUSED || d.world <= 16, "the fused exchange serves at most 16 ranks");
+    B200_REQUIRE(d.mode == B200_ITER_ALLGATHER || block->format == B200_FORMAT_SELL, "the fused exchange is a SELL-32 kernel");
+    B200_REQUIRE(d.mode == B200_ITER_ALLGATHER || d.world <= 16, "the fused exchange serves at most 16 ranks");
     B200_REQUIRE((d.halo_lo == nullptr) == (d.halo_hi == nullptr), "give both halo arrays or neither");
     b200_iterator *it = new b200_iterator();
     it->ctx = ctx;
@@ -395,7 +414,9 @@ int b200_iterator_run(b200_iterator *it, int steps)
             }
             int rc = b200_graph_launch(ctx, it->graph[p]);
             if (rc) return rc;
-            const int per_step = it->d.mode == B200_ITER_FUSED ? (it->comm ? 2 : 1) : (it->comm ? 5 : 3);
+            const int per_step = it->d.mode == B200_ITER_FUSED_MCAST ? 2
+                                 : it->d.mode == B200_ITER_FUSED     ? (it->comm ? 2 : 1)
+                                                                     : (it->comm ? 5 : 3);
             it->launches += (unsigned long long)per_step * G;
             it->step += G;
             steps -= G;
@@ -418,8 +439,12 @@ int b200_iterator_norm(b200_iterator *it, double *norm)
     if (it->step == 0) return B200_SUCCESS;
     const int last = (int)((it->step - 1) & 1);
     double host[B200_SUMSQ_SLOTS];
-    const int n = it->d.mode == B200_ITER_FUSED ? B200_SUMSQ_SLOTS : 1;
+    const int n = it->d.mode == B200_ITER_ALLGATHER ? 1 : B200_SUMSQ_SLOTS;
     const double *src = it->d.mode == B200_ITER_FUSED ? it->acc + last * B200_SUMSQ_SLOTS : it->acc + last;
+    if (it->d.mode == B200_ITER_FUSED_MCAST) {
+        int rc0 = b200_mcast_step_buffers(it->d.mcast, nullptr, &src);  // the sums over ranks of the last step
+        if (rc0) return rc0;
+    }
     int rc = b200_memcpy_d2h(ctx, host, src, sizeof(double) * n);
     if (rc) return rc;
     if (it->comm) {

@@ -42,6 +42,8 @@ typedef struct {
     int iters;          /* --iters K      K power-iteration steps instead of the single SpMV (default 0 = off) */
     int json;           /* --json         one JSON line instead of the text block */
     const char *synthetic; /* --synthetic laplace7:NXxNYxNZ  matrix generated on the devices, no file */
+    int sync_mcast;     /* --sync mcast|nccl  (sigma_c) per-step all-reduce + barrier through NVSwitch multicast
+                           (b200_mcast_*) instead of NCCL (default nccl) */
 } driver_options;
 
 int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_options *opt);

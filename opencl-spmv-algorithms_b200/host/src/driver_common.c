@@ -35,6 +35,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
     opt->iters = 0;
     opt->json = 0;
     opt->synthetic = NULL;
+    opt->sync_mcast = 0;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
         const char *v = i + 1 < argc ? argv[i + 1] : NULL;
@@ -56,6 +57,12 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
         else if (!strcmp(a, "--iters") && v) opt->iters = atoi(argv[++i]);
         else if (!strcmp(a, "--json")) opt->json = 1;
         else if (!strcmp(a, "--synthetic") && v) opt->synthetic = argv[++i];
+        else if (!strcmp(a, "--sync") && v) {
+            ++i;
+            if (!strcmp(v, "mcast")) opt->sync_mcast = 1;
+            else if (!strcmp(v, "nccl")) opt->sync_mcast = 0;
+            else goto bad;
+        }
         else goto bad;
     }
     if (opt->reps < 1 || opt->sigma < 1 || opt->device < 0 || opt->gpus < 1 || opt->gpus > DEVICES_DEFAULT_SIZE ||
@@ -73,7 +80,7 @@ int driver_parse_args(int argc, char **argv, const char *default_matrix, driver_
 bad:
     fprintf(stderr, "usage: %s [--matrix FILE.mtx] [--dtype f32|f64] [--sigma N] [--reps N] "
                     "[--device D] [--no-cpu] [--rowmajor|--colmajor] [--expand-symmetric] [--cache]\n"
-                    "       iterated mode (csr, sigma_c): --iters K [--gpus N] [--synthetic laplace7:NXxNYxNZ] [--json]\n", argv[0]);
+                    "       iterated mode (csr, sigma_c): --iters K [--gpus N] [--synthetic laplace7:NXxNYxNZ] [--sync nccl|mcast] [--json]\n", argv[0]);
     return 1;
 }
 

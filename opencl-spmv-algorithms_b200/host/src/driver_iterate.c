@@ -39,6 +39,8 @@ typedef struct {
     int *status;          /* per rank: first failing ReturnCode */
     double *ms_per_step, *norm;
     unsigned long long *launches;
+    b200_mcast *mcast_owner; /* --sync mcast: rank 0's multicast object, shared by the other threads */
+    int *mcast_status;
 } shared_state;
 
 typedef struct {
@@ -160,6 +162,34 @@ static void *rank_main(void *argp)
     int cmin = 0, cmax = -1;
     if (rc == Success) RANK_TRY(b200_minmax_i32(ctx, (const int *)d_cols, nnz, &cmin, &cmax));
     if (rc == Success) RANK_TRY(b200_sync(ctx));
+    /* --sync mcast: the per-step all-reduce + barrier through NVSwitch multicast instead of NCCL.  Rank 0
+     * creates the object, the other threads share it; add (all) -> barrier -> bind (all) -> barrier. */
+    b200_mcast *mc = NULL;
+    const int want_mcast = opt->sync_mcast && world > 1 && s->format == B200_FORMAT_SELL;
+    if (want_mcast) {
+        int st = B200_SUCCESS;
+        if (r == 0) {
+            st = rc == Success ? b200_mcast_create(ctx, world, &mc, NULL) : B200_ERR_INVALID_VALUE;
+            s->mcast_owner = mc;
+            s->mcast_status[0] = st;
+        }
+        wait_all(s);
+        if (r != 0) st = (rc == Success && s->mcast_status[0] == B200_SUCCESS) ? b200_mcast_share(ctx, s->mcast_owner, &mc) : B200_ERR_INVALID_VALUE;
+        if (st == B200_SUCCESS && s->mcast_status[0] == B200_SUCCESS) st = b200_mcast_add_device(mc);
+        s->mcast_status[r] = st;
+        wait_all(s);
+        int all_ok = 1;
+        for (int p = 0; p < world; ++p) all_ok &= s->mcast_status[p] == B200_SUCCESS;
+        st = all_ok ? b200_mcast_bind(mc) : B200_ERR_UNSUPPORTED;
+        wait_all(s);
+        s->mcast_status[r] = st;
+        wait_all(s);
+        for (int p = 0; p < world; ++p) all_ok &= s->mcast_status[p] == B200_SUCCESS;
+        if (!all_ok && rc == Success) {
+            if (r == 0) fprintf(stderr, "NVSwitch multicast is not available here (%s): %s\n", b200_status_string(B200_ERR_UNSUPPORTED), b200_last_error());
+            rc = OpenCLDeviceError;
+        }
+    }
     s->x[0][r] = (double *)xb[0];
     s->x[1][r] = (double *)xb[1];
     s->col_min[r] = cmin;
@@ -170,12 +200,13 @@ static void *rank_main(void *argp)
         if (s->status[p] != Success && rc == Success) rc = s->status[p]; /* all ranks give up together */
 
     int *halo_lo = (int *)calloc((size_t)world, sizeof(int)), *halo_hi = (int *)calloc((size_t)world, sizeof(int));
-    if (rc == Success && world > 1) RANK_TRY(b200_comm_create(ctx, s->comm_id, r, world, &comm));
+    if (rc == Success && world > 1 && !want_mcast) RANK_TRY(b200_comm_create(ctx, s->comm_id, r, world, &comm));
     if (rc == Success) {
         RANK_TRY(b200_halo_rows(s->col_min, s->col_max, world, r, s->rows_per_rank, s->n_rows, halo_lo, halo_hi));
         b200_iter_desc d;
         memset(&d, 0, sizeof d);
-        d.mode = s->format == B200_FORMAT_SELL ? B200_ITER_FUSED : B200_ITER_ALLGATHER;
+        d.mode = s->format == B200_FORMAT_SELL ? (want_mcast ? B200_ITER_FUSED_MCAST : B200_ITER_FUSED) : B200_ITER_ALLGATHER;
+        d.mcast = want_mcast ? mc : NULL;
         d.world = world;
         d.rank = r;
         d.rows_per_rank = s->rows_per_rank;
@@ -207,6 +238,10 @@ static void *rank_main(void *argp)
     s->status[r] = rc;
 
     b200_iterator_destroy(it);
+    wait_all(s); /* nobody unbinds the multicast block while a peer's last step is still signalling */
+    if (r != 0) b200_mcast_destroy(mc);
+    wait_all(s);
+    if (r == 0) b200_mcast_destroy(mc);
     b200_comm_destroy(comm);
     b200_csr_plan_destroy(plan);
     wait_all(s); /* nobody frees a buffer a peer might still be storing into */
@@ -279,7 +314,7 @@ int driver_run_iterated(const driver_options *opt, const host_matrix *m, int for
     }
     const long long per = (s.n_rows + world - 1) / world;
     s.rows_per_rank = (per + 31) / 32 * 32;
-    if (world > 1) {
+    if (world > 1 && !(opt->sync_mcast && format == B200_FORMAT_SELL)) {
         int st = b200_comm_get_unique_id(s.comm_id);
         if (st != B200_SUCCESS) return report_b200_error("b200_comm_get_unique_id", st);
     }
@@ -295,6 +330,7 @@ int driver_run_iterated(const driver_options *opt, const host_matrix *m, int for
     s.ms_per_step = (double *)calloc((size_t)world, sizeof(double));
     s.norm = (double *)calloc((size_t)world, sizeof(double));
     s.launches = (unsigned long long *)calloc((size_t)world, sizeof(unsigned long long));
+    s.mcast_status = (int *)calloc((size_t)world, sizeof(int));
     pthread_t *threads = (pthread_t *)calloc((size_t)world, sizeof(pthread_t));
     rank_arg *args = (rank_arg *)calloc((size_t)world, sizeof(rank_arg));
     for (int r = 0; r < world; ++r) {
@@ -330,7 +366,10 @@ int driver_run_iterated(const driver_options *opt, const host_matrix *m, int for
                    "\"warmup\": %d, \"ms_per_step\": %.6f, \"gflops\": %.3f, \"norm\": %.17g, \"cpu_norm\": %s%.17g%s, \"checked\": %s, "
                    "\"ok\": %s, \"launches_rank0\": %llu, \"timing\": \"wall clock around b200_iterator_run + "
                    "b200_iterator_norm, barrier on both sides, max over ranks\"}\n",
-                   driver_name, format == B200_FORMAT_SELL ? "fused halo exchange + all-reduce" : "SpMV + ncclAllGather",
+                   driver_name,
+                   format == B200_FORMAT_SELL ? (opt->sync_mcast && world > 1 ? "fused halo exchange + NVSwitch multicast all-reduce"
+                                                                            : "fused halo exchange + all-reduce")
+                                              : "SpMV + ncclAllGather",
                    world, opt->iters, s.n_rows, nnz, DRIVER_ITER_WARMUP(opt->iters), ms, gflops, norm, checked ? "" : "\"", checked ? cpu_norm : 0.0,
                    checked ? "" : " (not run)\"", checked ? "true" : "false", ok ? "true" : "false", s.launches[0]);
         } else {
@@ -353,6 +392,7 @@ int driver_run_iterated(const driver_options *opt, const host_matrix *m, int for
     free(s.ms_per_step);
     free(s.norm);
     free(s.launches);
+    free(s.mcast_status);
     free(threads);
     free(args);
     return rc;

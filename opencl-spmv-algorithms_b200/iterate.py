@@ -168,6 +168,55 @@ class Comm:
             self.h = None
 
 
+class McastBlock:
+    """b200_mcast: this rank's share of an NVSwitch multicast block (all-reduce + barrier of the iterated
+    mode through multimem.red).  Collective constructor over `world` processes: rank 0 creates the
+    object and exports a file descriptor, the others fetch it with pidfd_getfd; `all_gather_object` and
+    `barrier` carry the set-up (torch.distributed by default).  Raises B200Error(UNSUPPORTED) on every
+    rank alike when the box cannot do it."""
+
+    def __init__(self, pkg, ctx, rank: int, world: int, all_gather_object=None, barrier=None):
+        import ctypes as C
+        import os
+        self.pkg, self.ctx, self.h = pkg, ctx, None
+        L = pkg.lib()
+        if all_gather_object is None or barrier is None:
+            import torch.distributed as dist
+            all_gather_object = all_gather_object or dist.all_gather_object
+            barrier = barrier or dist.barrier
+
+        def agree(status, where):
+            """every rank learns whether all ranks succeeded, so that nobody waits for a rank that gave up"""
+            box = [None] * world
+            all_gather_object(box, (status, pkg.lib().b200_last_error().decode(errors="replace") if status else ""))
+            bad = [(r, st, msg) for r, (st, msg) in enumerate(box) if st]
+            if bad:
+                self.close()
+                raise pkg.B200Error(bad[0][1], where, f"rank {bad[0][0]}: {bad[0][2]}")
+
+        h, fd = C.c_void_p(), C.c_int(-1)
+        status = L.b200_mcast_create(ctx.h, world, C.byref(h), C.byref(fd)) if rank == 0 else 0
+        if rank == 0 and status == 0:
+            self.h = h
+        box = [None] * world
+        all_gather_object(box, (os.getpid(), fd.value, status))
+        owner_pid, owner_fd, st0 = box[0]
+        if st0 == 0 and rank != 0:
+            status = L.b200_mcast_import_pid_fd(ctx.h, world, owner_pid, owner_fd, C.byref(h))
+            if status == 0:
+                self.h = h
+        agree(status or st0, "b200_mcast_create / import")
+        agree(L.b200_mcast_add_device(self.h), "b200_mcast_add_device")
+        barrier()
+        agree(L.b200_mcast_bind(self.h), "b200_mcast_bind")
+        barrier()
+
+    def close(self) -> None:
+        if self.h:
+            self.pkg.lib().b200_mcast_destroy(self.h)
+            self.h = None
+
+
 class Iterator:
     """b200_iterator: the power iteration run by the library (launch-graph replay, NCCL from C).
 
@@ -176,7 +225,7 @@ class Iterator:
             (PeerBuffers.ptrs[:2] for mode 'fused'; for 'allgather' only [b][rank] is read)."""
 
     def __init__(self, pkg, ctx, comm: Comm | None, matrix, blocks: RowBlocks, rank: int, world: int,
-                 x_ptrs, mode: str = "fused", halo=None, graph_steps: int = 10):
+                 x_ptrs, mode: str = "fused", halo=None, graph_steps: int = 10, mcast: "McastBlock | None" = None):
         import ctypes as C
         self.pkg, self.ctx, self.matrix, self.comm = pkg, ctx, matrix, comm
         L = pkg.lib()
@@ -192,7 +241,9 @@ class Iterator:
             blk.csr_plan = matrix.plan()
         blk.n_rows = n_local
         d = pkg.IterDesc()
-        d.mode = {"fused": pkg.ITER_FUSED, "allgather": pkg.ITER_ALLGATHER}[mode]
+        d.mode = {"fused": pkg.ITER_FUSED, "allgather": pkg.ITER_ALLGATHER, "fused_mcast": pkg.ITER_FUSED_MCAST}[mode]
+        if mode == "fused_mcast":
+            d.mcast, comm = mcast.h, None
         d.world, d.rank, d.rows_per_rank, d.graph_steps = world, rank, blocks.count, graph_steps
         self._tables = [(C.c_void_p * world)(*[int(p) if p else None for p in x_ptrs[b]]) for b in range(2)]
         d.x[0] = C.cast(self._tables[0], C.POINTER(C.c_void_p))

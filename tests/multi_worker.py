@@ -105,6 +105,37 @@ def main():
             check(f"{mode}/g{graph} whole vector gathered", float(np.max(np.abs(got[:n] - x))) <= 1e-12)
         it.close()
 
+    # the same fused kernel with the all-reduce + barrier done by the NVSwitch (multimem.red on a multicast
+    # block) instead of NCCL: two launches per step, no collective call.  Skipped (recorded) where the box
+    # cannot set a multicast object up.
+    sup = C.c_int(0)
+    pkg.check(L.b200_mcast_supported(ctx.h, C.byref(sup)), "b200_mcast_supported")
+    flags = [None] * world
+    dist.all_gather_object(flags, sup.value)
+    res["mcast"] = "not supported by the device / driver"
+    if all(flags):
+        try:
+            mc = pkg.McastBlock(pkg, ctx, rank, world, all_gather_object=dist.all_gather_object, barrier=dist.barrier)
+        except pkg.B200Error as e:
+            mc = None
+            res["mcast"] = f"set-up refused: {e}"
+        if mc is not None:
+            res["mcast"] = "ran"
+            for graph in (0, 4):
+                reset()
+                it = pkg.Iterator(pkg, ctx, None, sell, blocks, rank, world, bufs.ptrs[:2], mode="fused_mcast", halo=halo,
+                                  graph_steps=graph, mcast=mc)
+                it.run(7)
+                it.run(steps - 7)
+                norm = it.norm()
+                k, xptr, launches = it.state()
+                check(f"fused_mcast/g{graph} steps", k == steps and launches == 2 * steps, (k, launches))
+                verify(f"fused_mcast/g{graph}", norm, xptr, normalised=False)
+                it.close()
+            ctx.sync()
+            dist.barrier()
+            mc.close()
+
     # the sell all-gather formulation, SELL block
     reset()
     it = pkg.Iterator(pkg, ctx, comm, sell, blocks, rank, world, bufs.ptrs[:2], mode="allgather", graph_steps=2)

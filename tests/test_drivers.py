@@ -326,6 +326,16 @@ def test_driver_iterated_mode(fem_small_dir, tmp_path, gpus):
     b = json.loads(p.stdout.strip().splitlines()[-1])
     assert a["rows"] == b["rows"] == 20 * 16 * 27 and a["nnz"] == b["nnz"]
     assert abs(a["norm"] - b["norm"]) <= 1e-10 * b["norm"] and 0 < a["norm"] < 12.0
+    # --sync mcast: the all-reduce + barrier through NVSwitch multicast; same eigenvalue estimate, or a clean
+    # refusal (exit code 1) where the box cannot set a multicast object up
+    if gpus > 1:
+        p = run(bins / "sigma_c", tmp_path, "--synthetic", "laplace7:20x16x27", "--iters", "30", "--gpus", str(gpus),
+                "--sync", "mcast", "--json")
+        if p.returncode == 0:
+            c = json.loads(p.stdout.strip().splitlines()[-1])
+            assert "multicast" in c["mode"] and abs(c["norm"] - b["norm"]) <= 1e-10 * b["norm"], c
+        else:
+            assert p.returncode == 1 and "multicast is not available" in p.stderr, p.stdout + p.stderr
     # argument errors
     assert run(bins / "coo", tmp_path, "--iters", "3").returncode == 4
     assert run(bins / "csr", tmp_path, "--gpus", "2").returncode == 4          # --gpus without --iters

@@ -61,6 +61,7 @@ def run_world(world: int, tmp_path):
 def test_iterated_mode_and_sharded_spmv_on_two_real_gpus(tmp_path):
     res = run_world(2, tmp_path)
     assert res[0]["nccl_version"] >= 22000
+    print("multicast path:", res[0].get("mcast"))
 
 
 @pytest.mark.skipif(n_devices() < 4, reason="needs at least 4 GPUs")
