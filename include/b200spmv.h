@@ -153,8 +153,9 @@ typedef struct {
     int long_threshold; /* rows longer than this go to the block-per-row kernel */
     int n_long_rows;
     int stream_tiles; /* > 0: short rows everywhere -> the nnz-split stream kernel is used instead,
-                         with this many 1024-entry tiles (a plan then owns carry buffers: use it on
-                         one stream at a time) */
+                         with this many tiles (a plan then owns carry buffers: it serves the context
+                         it was created on) */
+    int stream_tile_entries; /* entries per tile: 1024 x groups per thread (1, 2 or 4) */
 } b200_csr_plan_info;
 int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_plan **plan);
 int b200_csr_plan_get_info(const b200_csr_plan *plan, b200_csr_plan_info *info);

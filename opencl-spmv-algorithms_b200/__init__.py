@@ -31,7 +31,8 @@ class B200Error(RuntimeError):
 class CsrPlanInfo(C.Structure):
     _fields_ = [("n_rows", C.c_int), ("nnz", C.c_longlong), ("min_len", C.c_int),
                 ("max_len", C.c_int), ("mean_len", C.c_double), ("lanes_per_row", C.c_int),
-                ("long_threshold", C.c_int), ("n_long_rows", C.c_int), ("stream_tiles", C.c_int)]
+                ("long_threshold", C.c_int), ("n_long_rows", C.c_int), ("stream_tiles", C.c_int),
+                ("stream_tile_entries", C.c_int)]
 
 
 class RowStats(C.Structure):

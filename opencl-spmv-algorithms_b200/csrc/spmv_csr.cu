@@ -165,9 +165,9 @@ csr_long_rows_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
 // it (a partial sum if the row runs on into later tiles); the piece of a row that started in an
 // earlier tile is a carry, added by csr_stream_fixup_kernel afterwards (same stream, so ordered).
 // tile_lo[] is part of the plan (one binary search per tile, done once).
-constexpr int kTile = 1024;  // entries per 256-thread block
+constexpr int kTile = 1024;  // entries per 256-thread block and group (a block owns G * kTile entries)
 
-__global__ void csr_tile_rows_kernel(const int *__restrict__ ptr, int n_rows, int n_tiles,
+__global__ void csr_tile_rows_kernel(const int *__restrict__ ptr, int n_rows, int n_tiles, int tile,
                                      int *__restrict__ tile_lo)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +176,7 @@ __global__ void csr_tile_rows_kernel(const int *__restrict__ ptr, int n_rows, in
         tile_lo[b] = n_rows;  // the last tile also owns trailing empty rows
         return;
     }
-    const int e0 = b * kTile;
+    const int e0 = b * tile;
     int lo = 0, hi = n_rows;  // smallest r in [0, n_rows] with ptr[r] >= e0
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
@@ -186,34 +186,52 @@ __global__ void csr_tile_rows_kernel(const int *__restrict__ ptr, int n_rows, in
     tile_lo[b] = lo;
 }
 
-template <typename T, bool VEC>
+// G = groups of four entries per thread (tile = G * 1024 entries): all G index/value loads of a thread
+// are issued before its gathers, and one barrier pair serves G times the entries (on power-law inputs
+// the kernel is bound by the gather's L1/L2 sector traffic and the barrier wait showed up as its
+// largest single stall, profiles/r2_ncu_summary.md)
+template <typename T, bool VEC, int G>
 __global__ void __launch_bounds__(kBlock)
 csr_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ col, const T *__restrict__ data,
                   const T *__restrict__ x, T *__restrict__ y, int nnz, const int *__restrict__ tile_lo,
                   int *__restrict__ carry_row, T *__restrict__ carry_val)
 {
-    __shared__ T prod[kTile];
-    __shared__ int long_list[kTile / 32];  // rows with > 32 entries inside this tile (at most 31)
+    constexpr int TILE = kTile * G;
+    __shared__ T prod[TILE];
+    __shared__ int long_list[TILE / 32];  // rows with > 32 entries inside this tile (fewer than TILE / 32)
     __shared__ int n_long;
     if (threadIdx.x == 0) n_long = 0;
     const int b = blockIdx.x;
-    const int e0 = b * kTile, e1 = min(e0 + kTile, nnz);
+    const int e0 = b * TILE, e1 = min(e0 + TILE, nnz);
     const int lo = __ldg(tile_lo + b), r_end = __ldg(tile_lo + b + 1);
-    const int j = e0 + 4 * threadIdx.x;
-    T p[4] = {0, 0, 0, 0};
-    if (j < e1) {
-        if (VEC) {
-            IVec4 c;
-            Vec4<T> v;
-            c.load(col + j);
-            v.load(data + j);
+    T p[G][4];
+    if (VEC) {
+        IVec4 c[G];
+        Vec4<T> v[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int j = e0 + 4 * (threadIdx.x + kBlock * g);
+            c[g].zero();
+            v[g].zero();
+            if (j < e1) {
+                c[g].load(col + j);
+                v[g].load(data + j);
+            }
+        }
+        const int hold = batch_hold<G, T>(c, v);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int j = e0 + 4 * (threadIdx.x + kBlock * g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[g][k] = (j + k < e1) ? v[g].v[k] * ld_x(x, c[g].v[k] + hold) : T(0);
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int j = e0 + 4 * (threadIdx.x + kBlock * g);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (j + k < e1) p[k] = v.v[k] * ld_x(x, c.v[k]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (j + k < e1) p[k] = ld_stream(data + j + k) * ld_x(x, ld_stream(col + j + k));
+                p[g][k] = (j + k < e1) ? ld_stream(data + j + k) * ld_x(x, ld_stream(col + j + k)) : T(0);
         }
     }
     // this thread's first row: pointers fetched before the barrier so the loads overlap the gather
@@ -225,7 +243,9 @@ csr_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ col, cons
     }
     const int first_start = __ldg(ptr + lo);  // lo <= n_rows: ptr has n_rows + 1 entries
 #pragma unroll
-    for (int k = 0; k < 4; ++k) prod[4 * threadIdx.x + k] = p[k];
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) prod[4 * (threadIdx.x + kBlock * g) + k] = p[g][k];
     __syncthreads();
 
     // carry: entries [e0, first_start) belong to row lo-1, which started in an earlier tile
@@ -389,6 +409,7 @@ struct b200_csr_plan {
     int *tile_lo;     // stream_tiles + 1 entries
     int *carry_row;   // stream_tiles entries
     void *carry_val;  // stream_tiles x 8 bytes (T = float or double)
+    int stream_groups; // G of csr_stream_kernel: a tile holds G * 1024 entries
     cudaStream_t owner;  // a stream plan's carry buffers serve ONE queue: the one it was created on
 };
 
@@ -405,6 +426,7 @@ static int csr_plan_fill(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
     }
     b200_csr_plan_info &in = p->info;
     in.stream_tiles = 0;
+    in.stream_tile_entries = 0;
     in.n_rows = n_rows;
     in.nnz = (long long)first_last[1] - first_last[0];
     in.mean_len = n_rows > 0 ? (double)in.nnz / n_rows : 0.0;
@@ -442,20 +464,30 @@ static int csr_plan_fill(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
     // (any maximum row length: rows longer than 32 entries inside a tile get a whole warp, rows
     // longer than a tile are stitched by the carries -- the split is by entries, so skewed
     // power-law inputs stay balanced)
-    const bool possible = first_last[0] == 0 && in.nnz > 0 && in.nnz < 0x7fffffffll - kTile;
+    const bool possible = first_last[0] == 0 && in.nnz > 0 && in.nnz < 0x7fffffffll - 4 * kTile;
     const bool short_rows = in.mean_len <= 16.0;
     const bool skewed = in.mean_len <= 32.0 && (double)in.max_len > 16.0 * in.mean_len;
     bool stream = (short_rows || skewed) && possible;
     if (opt_set(ctx, OPT_CSR_STREAM)) stream = ctx->opt[OPT_CSR_STREAM] != 0 && possible;
     if (stream) {
-        const int n_tiles = (int)((in.nnz + kTile - 1) / kTile);
+        // groups per thread (tuning hook B200_CSR_STREAM_G=1|2|4): 1 for stencil-like rows, 2 when the
+        // rows are skewed (the gather-bound power-law case)
+        int g = skewed ? 2 : 1;
+        {
+            const int v = opt_or(ctx, OPT_CSR_STREAM_G, 0);
+            if (v == 1 || v == 2 || v == 4) g = v;
+        }
+        p->stream_groups = g;
+        const int tile = kTile * g;
+        const int n_tiles = (int)((in.nnz + tile - 1) / tile);
         B200_CUDA(cudaMalloc(&p->tile_lo, sizeof(int) * ((size_t)n_tiles + 1)));
         B200_CUDA(cudaMalloc(&p->carry_row, sizeof(int) * (size_t)n_tiles));
         B200_CUDA(cudaMalloc(&p->carry_val, sizeof(double) * (size_t)n_tiles));
-        csr_tile_rows_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, ctx->stream>>>(ptr, n_rows, n_tiles, p->tile_lo);
+        csr_tile_rows_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, ctx->stream>>>(ptr, n_rows, n_tiles, tile, p->tile_lo);
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
         in.stream_tiles = n_tiles;
+        in.stream_tile_entries = tile;
     }
     return B200_SUCCESS;
 }
@@ -473,6 +505,7 @@ int b200_csr_plan_create(b200_ctx *ctx, const int *ptr, int n_rows, b200_csr_pla
     p->carry_row = nullptr;
     p->carry_val = nullptr;
     p->n_split = 1;
+    p->stream_groups = 1;
     p->owner = ctx->stream;
     const int rc = csr_plan_fill(ctx, ptr, n_rows, p);
     if (rc != B200_SUCCESS) {
@@ -557,12 +590,21 @@ int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, 
         }
         const int n_tiles = plan->info.stream_tiles;
         T *carry_val = static_cast<T *>(plan->carry_val);
-        if (vec)
-            csr_stream_kernel<T, true><<<n_tiles, kBlock, 0, ctx->stream>>>(
-                ptr, col, data, x, y, (int)plan->info.nnz, plan->tile_lo, plan->carry_row, carry_val);
-        else
-            csr_stream_kernel<T, false><<<n_tiles, kBlock, 0, ctx->stream>>>(
-                ptr, col, data, x, y, (int)plan->info.nnz, plan->tile_lo, plan->carry_row, carry_val);
+#define B200_CSR_STREAM(V, GG)                                                                   \
+    csr_stream_kernel<T, V, GG><<<n_tiles, kBlock, 0, ctx->stream>>>(ptr, col, data, x, y, (int)plan->info.nnz, \
+                                                                    plan->tile_lo, plan->carry_row, carry_val)
+        // the tile size is part of the plan (tile_lo): scalar-load and vector-load variants share it
+        if (plan->stream_groups == 4) {
+            if (vec) B200_CSR_STREAM(true, 4);
+            else B200_CSR_STREAM(false, 4);
+        } else if (plan->stream_groups == 2) {
+            if (vec) B200_CSR_STREAM(true, 2);
+            else B200_CSR_STREAM(false, 2);
+        } else {
+            if (vec) B200_CSR_STREAM(true, 1);
+            else B200_CSR_STREAM(false, 1);
+        }
+#undef B200_CSR_STREAM
         csr_stream_fixup_kernel<T><<<(n_tiles + 255) / 256, 256, 0, ctx->stream>>>(y, n_tiles, plan->carry_row, carry_val);
         cudaError_t e = cudaGetLastError();
         rc = e == cudaSuccess ? B200_SUCCESS : b200_cuda_fail(e, "csr_stream_kernel", __FILE__, __LINE__);

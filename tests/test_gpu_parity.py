@@ -249,6 +249,15 @@ def test_csr_stream_kernel(ctx, dtype):
     yd = ctx.array(np.full(n_rows, np.nan, dtype))
     csr.spmv(ctx.array(x.astype(dtype)), yd)
     check_y("csr-stream-forced", yd.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+    for g in (2, 4):        # G groups per thread: tiles of 2048 / 4096 entries (the power-law default is 2)
+        ctx.set_option("B200_CSR_STREAM_G", g)
+        csr_g = pkg.CsrMatrix(coo)
+        info = csr_g.plan_info()
+        assert info.stream_tile_entries == 1024 * g and info.stream_tiles == -(-rows.size // (1024 * g))
+        yg = ctx.array(np.full(n_rows, np.nan, dtype))
+        csr_g.spmv(ctx.array(x.astype(dtype)), yg)
+        check_y(f"csr-stream G={g}", yg.download(), O.yref(n_rows, rows, cols, vals, x), dtype)
+    ctx.set_option("B200_CSR_STREAM_G", None)
     ctx.set_option("B200_CSR_STREAM", "0")
     csr2 = pkg.CsrMatrix(coo)
     assert csr2.plan_info().stream_tiles == 0
