@@ -260,3 +260,27 @@ def test_halo_rows_from_column_ranges():
               for r in range(4)]
     lo, hi = pkg.halo_rows(ranges, blocks, 2)
     assert [h - l for l, h in zip(lo, hi)] == [0, 100, blocks.count, 100]
+
+
+def test_c_abi_halo_rows_equals_the_python_mirror():
+    """b200_halo_rows (what the C drivers call, host/src/driver_iterate.c) against halo_rows on random
+    column ranges, including ranks that own nothing and ranges that miss a block entirely."""
+    import ctypes as C
+    import numpy as np
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    L = pkg.lib()
+    rng = np.random.default_rng(0)
+    for world, n in ((1, 100), (2, 1000), (4, 1000), (8, 40), (8, 123457), (16, 5000)):
+        blocks = pkg.equal_row_blocks(n, world)
+        for _ in range(20):
+            a = rng.integers(0, n, world)
+            b = rng.integers(0, n, world)
+            ranges = [(int(min(x, y)), int(max(x, y))) for x, y in zip(a, b)]
+            cmin = (C.c_int * world)(*[r[0] for r in ranges])
+            cmax = (C.c_int * world)(*[r[1] for r in ranges])
+            for rank in range(world):
+                lo, hi = (C.c_int * world)(), (C.c_int * world)()
+                assert L.b200_halo_rows(cmin, cmax, world, rank, blocks.count, n, lo, hi) == 0
+                want = pkg.halo_rows(ranges, blocks, rank)
+                assert (list(lo), list(hi)) == (list(want[0]), list(want[1])), (world, n, rank, ranges)

@@ -44,6 +44,13 @@ def test_no_gpu_exit_code(tmp_path):
         assert p.returncode == 1, (f, p.stdout, p.stderr)
         assert "CPU calculations" not in p.stdout
     assert run(bins / "csr", tmp_path, "--bogus").returncode == 4      # OtherError
+    # the iterated mode: argument errors are OtherError, a missing device is OpenCLDeviceError -- and the
+    # synthetic path must not need a file
+    assert run(bins / "csr", tmp_path, "--gpus", "2").returncode == 4             # --gpus without --iters
+    assert run(bins / "sigma_c", tmp_path, "--iters", "5", "--sync", "smoke").returncode == 4
+    assert run(bins / "ell", tmp_path, "--iters", "5").returncode == 4            # csr and sigma_c only
+    p = run(bins / "sigma_c", tmp_path, "--synthetic", "laplace7:8x8x8", "--iters", "5", "--gpus", "2", "--json")
+    assert p.returncode == 1 and "No CUDA devices found" in p.stdout, (p.stdout, p.stderr)
 
 
 def test_fast_parallel_parse_equals_fscanf_parse(cant_dir, tmp_path):
