@@ -869,10 +869,12 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
         # "cmrs_packed" = the derived 4+V bytes/entry layout (row_in_strip folded into the column word),
         # measured next to the reference two-array layout, never in the headline
         extras = {"ell_colmajor": allm["ellcm"], "cmrs_packed": allm["cmrs"].packed()}
-        try:   # derived layout: 16-bit column deltas per SELL chunk (refused when a chunk spans > 65536 columns)
-            extras["sell_delta16"] = pkg.Sell16Matrix(allm["sell"])
-        except pkg.B200Error:
-            pass
+        if args.workload == "banded":
+            try:   # derived layout: 16-bit column deltas per SELL chunk (refused when a chunk spans > 65536
+                   # columns); its kernel is the one-warp-per-chunk SELL kernel, i.e. for large matrices
+                extras["sell_delta16"] = pkg.Sell16Matrix(allm["sell"])
+            except pkg.B200Error:
+                pass
         return ({f: allm[f] for f in FORMATS}, extras)
 
     # The cant-shaped formats (53-70 MB each) fit in the 126 MB L2.  "Inputs larger than L2" is

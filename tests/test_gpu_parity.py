@@ -778,3 +778,47 @@ def test_format_advice(ctx):
     assert a.sell_padding > a.sell_padding_sigma65536 >= 1.0
     assert (a.recommended_sigma == 65536) == (pkg.FORMAT_NAMES[a.recommended] == "sell")
     assert a.reason.decode().startswith("skewed rows")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_no_kernel_writes_outside_its_output(ctx, dtype):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are caught with guard bands:
+    every format's y sits inside a larger buffer of sentinels (32 elements before, the rest after, so y
+    starts 16-byte-misaligned for fp32 -- the kernels must not assume more than element alignment of y);
+    after the SpMV the sentinels must be intact.  Row counts that are not multiples of 32 / 8, a partly
+    empty last SELL chunk and CMRS strip, every launch variant the tuning hooks select."""
+    SENT = -12345.0
+    for n_rows, lo, hi in ((2333, 1, 150), (1001, 1, 8), (32, 3, 3), (5, 1, 300)):
+        n_cols = 4000
+        rows, cols, vals = random_sorted_matrix(n_rows, n_cols, lo, hi, n_rows)
+        x = np.random.default_rng(n_rows).uniform(-1, 1, n_cols)
+        y_ref = O.yref(n_rows, rows, cols, vals, x)
+        m = pkg.build_all(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows, cols, vals), dtype)
+        m["cmrs_packed"] = m["cmrs"].packed()
+        m["sell_sigma"] = pkg.SellMatrix(m["csr"], dtype, sigma=64)
+        m["sell16"] = pkg.Sell16Matrix(m["sell"])
+        xd = ctx.array(x.astype(dtype))
+        pad_before, total = 33, n_rows + 33 + 4096
+        for name, mat in m.items():
+            variants = [{}]
+            if name == "sell":
+                variants = [{"B200_SELL_WPC": w} for w in (1, 2, 4, 8)] + [{"B200_SELL_TMA": 1}]
+            if name == "cmrs":
+                variants = [{"B200_CMRS_WPS": w} for w in (1, 2, 4)] + [{"B200_CMRS_STREAM": 1}]
+            if name == "csr":
+                variants = [{}, {"B200_CSR_STREAM": 1}, {"B200_CSR_STREAM": 1, "B200_CSR_STREAM_G": 4}]
+            for env in variants:
+                for k, v in env.items():
+                    ctx.set_option(k, v)
+                if name == "csr":
+                    mat = pkg.CsrMatrix(m["csr"].coo)
+                if name == "cmrs" and "B200_CMRS_STREAM" in env:
+                    mat = pkg.CmrsMatrix(m["csr"])
+                buf = ctx.array(np.full(total, SENT, dtype))
+                y = pkg.DeviceArray.from_ptr(ctx, buf.ptr + pad_before * np.dtype(dtype).itemsize, n_rows, dtype)
+                mat.spmv(xd, y)
+                got = buf.download()
+                for k in env:
+                    ctx.set_option(k, None)
+                assert np.all(got[:pad_before] == SENT) and np.all(got[pad_before + n_rows:] == SENT), (name, env, n_rows)
+                check_y(f"guarded {name} {env}", got[pad_before:pad_before + n_rows], y_ref, dtype)
