@@ -197,6 +197,64 @@ def test_rmat_generator_and_formats(ctx):
     np.testing.assert_array_equal(m.slice_ptr.download(), sp)
 
 
+def test_full_size_rmat_sampled_rows(ctx):
+    """BASELINE configs[3] at FULL size (R-MAT scale 24: 16 777 216 rows, ~280 M nnz, fp32).  The CPU oracle
+    cannot do this matrix in seconds, so: (a) sampled row blocks -- the block holding the longest (hub) row,
+    the first rows, a block in the middle, the last rows -- are regenerated on their own (the generator is a
+    pure function of the row block), multiplied by the oracle in fp64 and compared with every kernel's y;
+    (b) all kernels agree with each other on ALL rows; (c) linearity of the CSR kernel."""
+    import ctypes as C
+    L = pkg.lib()
+    scale, ef, abc, seed = 24, 16, (0.57, 0.19, 0.19), 5          # bench.py's matrix
+    n = 1 << scale
+    cap = C.c_longlong(0)
+    pkg.check(L.b200_gen_rmat_count(ctx.h, scale, ef, *abc, seed, 0, n, C.byref(cap)), "count")
+    rows, cols, vals = ctx.empty(cap.value, np.int32), ctx.empty(cap.value, np.int32), ctx.empty(cap.value, np.float64)
+    nnz = C.c_longlong(0)
+    pkg.check(L.b200_gen_rmat_coo(ctx.h, scale, ef, *abc, seed, 0, n, cap.value, rows.ptr, cols.ptr, vals.ptr,
+                                  C.byref(nnz)), "gen")
+    rows.n = cols.n = vals.n = nnz.value
+    assert 2.5e8 < nnz.value < 3.0e8
+    dtype = np.float32
+    coo = pkg.CooMatrix(ctx, n, n, rows, cols, vals)
+    csr = pkg.CsrMatrix(coo, check_sorted=False)
+    info = csr.plan_info()
+    assert info.stream_tiles > 0 and info.stream_tile_entries == 2048       # skewed: nnz-split, two groups per thread
+    cmrs = pkg.CmrsMatrix(csr)
+    assert cmrs.plan_stream_tiles() > 0                                      # ... and the nnz-split CMRS kernel
+    mats = {"csr": csr, "coo": coo, "cmrs": cmrs, "cmrs_packed": cmrs.packed(),
+            "sell_sigma65536": pkg.SellMatrix(csr, dtype, sigma=65536, wide=True)}
+    rng = np.random.default_rng(0)
+    xh, zh = rng.uniform(0, 1, n).astype(dtype), rng.uniform(-1, 1, n).astype(dtype)
+    x, z = ctx.array(xh), ctx.array(zh)
+    ys = {}
+    for name, mat in mats.items():
+        yd = ctx.array(np.full(n, np.nan, dtype))
+        mat.spmv(x, yd)
+        ys[name] = yd.download().astype(np.float64)
+    scale_y = np.abs(ys["csr"]).max()
+    for name in ys:
+        assert np.max(np.abs(ys[name] - ys["csr"])) / scale_y <= 1e-5, name
+    a, b = 0.75, -1.5
+    w = ctx.array((a * xh + b * zh).astype(dtype))
+    yz, yw = ctx.zeros(n, dtype), ctx.zeros(n, dtype)
+    csr.spmv(z, yz)
+    csr.spmv(w, yw)
+    lin = a * ys["csr"] + b * yz.download().astype(np.float64)
+    assert np.max(np.abs(yw.download() - lin)) / np.abs(lin).max() <= 1e-5
+    ptr = csr.ptr.download()
+    hub = int(np.argmax(np.diff(ptr)))
+    assert ptr[hub + 1] - ptr[hub] > 100000                                  # a real hub row
+    x64 = xh.astype(np.float64)
+    for r0 in sorted({0, hub // 1024 * 1024, n // 2 + 4096, n - 1024}):
+        rh, ch, vh = gen_rmat(ctx, scale, ef, r0, 1024, seed=seed, abc=abc)
+        assert rh.size == ptr[r0 + 1024] - ptr[r0]                           # the block of the full build
+        y_ref = O.yref(1024, rh - r0, ch, vh, x64)
+        for name in ys:
+            err = np.max(np.abs(ys[name][r0:r0 + 1024] - y_ref)) / scale_y
+            assert err <= 1e-5, (name, r0, err)
+
+
 def test_fused_power_iteration_one_gpu(ctx):
     """The fused SpMV + exchange kernel with a single destination (world = 1) must reproduce the
     NCCL-formulation iteration and the CPU power iteration."""
