@@ -69,8 +69,10 @@ int b200_ctx_create(int device, b200_ctx **ctx);
 int b200_ctx_create_on_stream(int device, void *cuda_stream, b200_ctx **ctx);
 int b200_ctx_destroy(b200_ctx *ctx);
 int b200_ctx_device(const b200_ctx *ctx, int *device);
-/* keep `bytes` at `dptr` (normally x) resident in L2 for later launches (access-policy window);
- * bytes = 0 clears the window.  New: the OpenCL reference has no equivalent. */
+/* keep `bytes` at `dptr` (normally x) resident in L2 for later launches (access-policy window on this
+ * context's queue + a persisting-L2 set-aside, which is DEVICE-wide: up to 79 of the 126 MB); bytes = 0
+ * clears the window and gives the set-aside back (so does b200_ctx_destroy) -- a stale one slows every
+ * other kernel on the device.  New: the OpenCL reference has no equivalent. */
 int b200_ctx_set_l2_persist(b200_ctx *ctx, const void *dptr, size_t bytes);
 
 /* Launch overlap (new; programmatic dependent launch).  With overlap on, an SpMV launch (CSR / ELL /
@@ -496,9 +498,10 @@ int b200_comm_allgather_f64(b200_comm *comm, double *full_device, long long coun
 int b200_ctx_enable_peer_access(b200_ctx *ctx, int peer_device);
 
 /* ---- NVSwitch multicast block (new): one 2 MiB block of every rank's GPU memory bound to
- *      ONE multicast object; a multimem.red to its address is carried out by the switch on every GPU's
- *      copy.  The iterated mode uses it for the per-step all-reduce of the 32 partial sums of ||y||^2 and
- *      the barrier that orders the halo stores -- one 32-thread kernel per step, no NCCL call
+ *      ONE multicast object; a multimem.st / multimem.red to its address is carried out by the switch on
+ *      every GPU's copy.  The iterated mode uses it for the per-step all-reduce of ||y||^2 (one store per
+ *      rank into its own slot, slots added in rank order after the barrier: bit-identical on every rank)
+ *      and the barrier that orders the halo stores -- one 32-thread kernel per step, no NCCL call
  *      (B200_ITER_FUSED_MCAST).  Needs NVLink multicast support (b200_mcast_supported); every entry point
  *      returns B200_ERR_UNSUPPORTED where the driver, the device or the container's permissions lack it.
  *      Set-up, in this order:  rank 0 b200_mcast_create;  other ranks b200_mcast_import_pid_fd (other
@@ -512,7 +515,7 @@ int b200_mcast_import_fd(b200_ctx *ctx, int world, int fd, b200_mcast **mcast);
 int b200_mcast_import_pid_fd(b200_ctx *ctx, int world, int owner_pid, int owner_fd, b200_mcast **mcast);
 int b200_mcast_share(b200_ctx *ctx, const b200_mcast *owner, b200_mcast **mcast);
 int b200_mcast_add_device(b200_mcast *mcast);
-int b200_mcast_bind(b200_mcast *mcast);
+int b200_mcast_bind(b200_mcast *mcast, int rank /* this rank's slot: 0 .. world-1, world <= 16 */);
 /* the multicast address (stores / reductions reach every rank's copy) and this rank's own copy */
 int b200_mcast_pointers(const b200_mcast *mcast, void **multicast_ptr, void **local_ptr, size_t *bytes);
 /* the two 32-slot device arrays of a step: the accumulator the fused SpMV kernel adds ||y_r||^2 into

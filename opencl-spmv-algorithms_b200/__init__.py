@@ -187,7 +187,7 @@ SIGNATURES = {
     "b200_mcast_import_pid_fd": (_i, [_vp, _i, _i, _i, _vpp]),
     "b200_mcast_share": (_i, [_vp, _vp, _vpp]),
     "b200_mcast_add_device": (_i, [_vp]),
-    "b200_mcast_bind": (_i, [_vp]),
+    "b200_mcast_bind": (_i, [_vp, _i]),
     "b200_mcast_pointers": (_i, [_vp, _vpp, _vpp, C.POINTER(_sz)]),
     "b200_mcast_step_buffers": (_i, [_vp, _vpp, _vpp]),
     "b200_mcast_allreduce_barrier": (_i, [_vp]),

@@ -39,6 +39,7 @@ struct b200_ctx {
     void *host_scratch;    // pinned, 4 KiB, for small readbacks
     bool watch_flag;       // a bulk-copy kernel ran since the last sync: b200_sync reads kWatchFlag
     bool watch_saved;      // watch_flag as it was when b200_graph_begin started recording
+    bool persist_set;      // b200_ctx_set_l2_persist reserved a (device-wide) persisting-L2 carve-out
     bool overlap;          // b200_ctx_set_launch_overlap: SpMV kernels are launched as programmatic
                            // dependents (they stream their matrix arrays while earlier work drains)
     mutable bool needs_order;  // something other than an SpMV launch entered this context since the last

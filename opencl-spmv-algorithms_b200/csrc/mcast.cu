@@ -3,9 +3,10 @@
 // What a power-iteration step has to exchange besides the halo rows is tiny and goes to EVERYBODY: the 32
 // partial sums of ||y||^2 and a "this rank is done" signal.  That is what NVLink multicast is for: a
 // multicast object spans one 2 MiB block of every GPU's memory; a `multimem.red` to its address is
-// carried out by the switch on EVERY GPU's copy, so
-//     all-reduce  = every rank adds its partial sums into the multicast address  (1 instruction per lane)
-//     barrier     = every rank adds 1 to a multicast counter and polls its OWN copy
+// carried out by the switch on EVERY GPU's copy (and a `multimem.st` stores to every copy), so
+//     all-gather  = every rank stores its sum into ITS slot of the multicast block   (1 instruction)
+//     barrier     = every rank adds 1 to a multicast counter and polls its OWN copy  (1 instruction)
+//     all-reduce  = after the barrier every rank adds the slots in rank order (bit-identical everywhere)
 // -- no ring, no tree, no peer loops, no NCCL call: one 32-thread kernel per step.  The halo rows stay
 // unicast peer stores from the SpMV kernel's epilogue (each boundary row has exactly one reader, so
 // there is nothing to multicast there).
@@ -101,8 +102,8 @@ int cu_fail(CUresult r, const char *what, const char *file, int line)
 
 // layout of the multicast block, in 8-byte words
 constexpr int kMcFlag = 0;    // arrivals so far, summed over ranks and steps (multimem.red +1 per rank and step)
-constexpr int kMcSums = 16;   // [parity][32] partial sums of ||y||^2, summed over ranks by the switch
-constexpr int kMcWords = kMcSums + 2 * 32;
+constexpr int kMcSlots = 16;  // [parity][16] one slot per rank: that rank's ||y_r||^2 of the step
+constexpr int kMcWords = kMcSlots + 2 * 16;
 constexpr unsigned long long kWaitLimitNs = 2000000000ull;
 
 __device__ __forceinline__ unsigned long long timer_ns()
@@ -114,55 +115,67 @@ __device__ __forceinline__ unsigned long long timer_ns()
 
 // One warp per rank and step, launched right after the fused SpMV kernel on the same queue (so all of that
 // kernel's stores -- its own x block and the halo rows in the peers' memory -- have been performed):
-//   1. clear this GPU's copy of the OTHER parity's sums (the next step's target; nobody touches it before
-//      having seen this rank's arrival below),
-//   2. add this rank's 32 partial sums into the multicast address: the switch adds them on every GPU,
-//   3. add 1 to the multicast arrival counter (release: covers 1 and 2 and the SpMV kernel's stores),
-//   4. poll the LOCAL copy of the counter until all `world` ranks of this step have arrived (acquire),
-//   5. hand the summed sums to the next SpMV kernel (scale_out) and clear the local accumulator.
-// The step number lives in device memory (local[0]) so that the launch can be replayed from a graph.
+//   1. fold this rank's 32 partial sums (shuffles, fixed order) and clear the accumulator,
+//   2. lane 0: ONE multimem.st puts the sum into this rank's slot of the multicast block on every GPU, ONE
+//      multimem.red (release) adds 1 to the multicast arrival counter.  Two multicast operations per rank
+//      and step: a first version sent the 32 partial sums as 32 multimem.red.add.f64 and its cost grew
+//      with the square of the rank count (every operation fans out to every GPU): 0.29 ms per step at 4
+//      GPUs, 0.68 at 8, against 0.18 / 0.19 with NCCL's all-reduce;
+//   3. poll the LOCAL copy of the counter until all `world` ranks of this step have arrived (acquire),
+//   4. add the ranks' slots in rank order -- every GPU computes bit-identical sums, unlike reductions that
+//      land in arrival order -- and hand the total to the next SpMV kernel (scale_out).
+// Slots alternate with the step parity: a rank overwrites its slot of parity p only two steps later, after
+// everybody has passed the barrier in between.  The step number lives in device memory so that the launch
+// can be replayed from a graph.
 __global__ void mcast_sync_kernel(double *__restrict__ acc_local, double *__restrict__ scale_out,
                                   unsigned long long *__restrict__ step_counter, unsigned long long *mc,
-                                  unsigned long long *uc, int world, int *__restrict__ err_flag)
+                                  unsigned long long *uc, int world, int my_rank, int *__restrict__ err_flag)
 {
     const int lane = threadIdx.x;
     const unsigned long long step = *step_counter;
     const int p = (int)(step & 1);
-    double *mc_sums = reinterpret_cast<double *>(mc + kMcSums) + p * 32;
-    double *uc_sums = reinterpret_cast<double *>(uc + kMcSums);
-    const double v = acc_local[lane];
+    double v = acc_local[lane];
     acc_local[lane] = 0.0;
-    uc_sums[(p ^ 1) * 32 + lane] = 0.0;
-    __threadfence_system();
-    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(mc_sums + lane), "d"(v) : "memory");
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) {
+        double *slot = reinterpret_cast<double *>(mc + kMcSlots) + p * 16 + my_rank;
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(v) : "memory");
         asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(mc + kMcFlag), "l"(1ull) : "memory");
+    }
     const unsigned long long want = (unsigned long long)world * (step + 1);
     const unsigned long long t0 = timer_ns();
     for (;;) {
-        unsigned long long f;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(uc + kMcFlag) : "memory");
+        unsigned long long f = 0;
+        if (lane == 0) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(uc + kMcFlag) : "memory");
+        f = __shfl_sync(0xffffffffu, f, 0);
         if (f >= want) break;
-        __nanosleep(64);
+        __nanosleep(32);
         if (timer_ns() - t0 > kWaitLimitNs) {  // a rank never arrived: flag it, do not hang
             if (lane == 0) atomicExch(err_flag, 3);
             break;
         }
     }
-    double total;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(total) : "l"(uc_sums + p * 32 + lane) : "memory");
-    scale_out[lane] = total;
-    __syncwarp();
-    if (lane == 0) *step_counter = step + 1;
+    if (lane == 0) {
+        const double *slots = reinterpret_cast<const double *>(uc + kMcSlots) + p * 16;
+        double total = 0.0;
+        for (int r = 0; r < world; ++r) {
+            double t;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t) : "l"(slots + r) : "memory");
+            total += t;
+        }
+        scale_out[0] = total;
+        *step_counter = step + 1;
+    } else {
+        scale_out[lane] = 0.0;  // the consumer adds the 32 slots up
+    }
 }
 
 }  // namespace
 
 struct b200_mcast {
     b200_ctx *ctx;
-    int world;
+    int world, rank;
     size_t bytes;  // rounded up to the multicast granularity
     CUmemGenericAllocationHandle mc_handle, mem_handle;
     CUdeviceptr mc_va, uc_va;
@@ -325,9 +338,11 @@ int b200_mcast_add_device(b200_mcast *m)
     return B200_SUCCESS;
 }
 
-int b200_mcast_bind(b200_mcast *m)
+int b200_mcast_bind(b200_mcast *m, int rank)
 {
     B200_REQUIRE(m && m->added, "b200_mcast_add_device (on every rank, then a barrier) comes first");
+    B200_REQUIRE(rank >= 0 && rank < m->world && m->world <= 16, "rank must be in [0, world), world at most 16");
+    m->rank = rank;
     b200_ctx *ctx = m->ctx;
     B200_ENTER(ctx);
     CUmemAllocationProp prop;
@@ -384,7 +399,7 @@ int b200_mcast_allreduce_barrier(b200_mcast *m)
     B200_ENTER(ctx);
     mcast_sync_kernel<<<1, 32, 0, ctx->stream>>>(m->acc_local, m->scale_out, m->step_counter,
                                                  reinterpret_cast<unsigned long long *>(m->mc_va),
-                                                 reinterpret_cast<unsigned long long *>(m->uc_va), m->world,
+                                                 reinterpret_cast<unsigned long long *>(m->uc_va), m->world, m->rank,
                                                  ctx->scratch + kWatchFlag);
     B200_LAUNCH_CHECK();
     ctx->watch_flag = true;

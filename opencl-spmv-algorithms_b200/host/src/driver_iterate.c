@@ -180,7 +180,7 @@ static void *rank_main(void *argp)
         wait_all(s);
         int all_ok = 1;
         for (int p = 0; p < world; ++p) all_ok &= s->mcast_status[p] == B200_SUCCESS;
-        st = all_ok ? b200_mcast_bind(mc) : B200_ERR_UNSUPPORTED;
+        st = all_ok ? b200_mcast_bind(mc, r) : B200_ERR_UNSUPPORTED;
         wait_all(s);
         s->mcast_status[r] = st;
         wait_all(s);

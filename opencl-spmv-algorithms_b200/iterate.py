@@ -208,7 +208,7 @@ class McastBlock:
         agree(status or st0, "b200_mcast_create / import")
         agree(L.b200_mcast_add_device(self.h), "b200_mcast_add_device")
         barrier()
-        agree(L.b200_mcast_bind(self.h), "b200_mcast_bind")
+        agree(L.b200_mcast_bind(self.h, rank), "b200_mcast_bind")
         barrier()
 
     def close(self) -> None:

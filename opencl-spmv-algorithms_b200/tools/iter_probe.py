@@ -133,6 +133,87 @@ def main():
             t = torch.tensor([us], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             out[f"{name}{'_graph' if graph else '_direct'}_us"] = round(float(t[0]), 2)
+    # the library's own iterator (b200_iterator_*), in this very process, under conditions bench.py adds one at a time
+    def iterator_us(label, graph_steps=100, pre=None, post=None):
+        pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[0].ptr, n, 11, 0.0, 1.0), "x0")
+        bufs.local[1].fill_bytes(0)
+        barrier()
+        it = pkg.Iterator(pkg, ctx, comm, sell, blocks, rank, world, bufs.ptrs[:2], mode="fused", halo=halo,
+                          graph_steps=graph_steps)
+        it.run(1 + 2 * max(graph_steps, 2))
+        barrier()
+        if pre:
+            pre()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        it.run(100)
+        b.record()
+        barrier()
+        if post:
+            post()
+        us = a.elapsed_ms_until(b) * 10.0
+        it.close()
+        t = torch.tensor([us], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[label] = round(float(t[0]), 2)
+
+    iterator_us("iterator_graph100_us")
+    iterator_us("iterator_graph10_us", graph_steps=10)
+    iterator_us("iterator_direct_us", graph_steps=0)
+    import bench
+    holder = {}
+
+    def sampler_on():
+        holder["clk"] = bench.ClockSampler(local)
+        holder["clk"].__enter__()
+
+    def sampler_off():
+        holder["clk"].__exit__()
+
+    iterator_us("iterator_graph100_with_clock_sampler_us", pre=sampler_on, post=sampler_off)
+    ctx2 = pkg.Context(local)
+    big = ctx2.zeros(1 << 26, np.float64)
+    iterator_us("iterator_graph100_second_context_us")
+    ctx2.set_l2_persist(big)          # what the banded arm leaves behind: a device-wide persisting-L2 carve-out
+    ctx2.sync()
+    iterator_us("iterator_graph100_after_l2_persist_carveout_us")
+    ctx2.set_l2_persist(None)
+    ctx2.sync()
+    iterator_us("iterator_graph100_after_clearing_it_us")
+    bench.bind_to_gpu_numa(local)
+    iterator_us("iterator_graph100_after_cpu_binding_us")
+    # the NVSwitch-multicast all-reduce + barrier (b200_mcast_*): alone, and as the step's hand-over
+    try:
+        mc = pkg.McastBlock(pkg, ctx, rank, world)
+    except pkg.B200Error as e:
+        mc = None
+        out["mcast"] = f"unavailable: {e}"
+    if mc is not None:
+        def mc_sync():
+            pkg.check(L.b200_mcast_allreduce_barrier(mc.h), "mcast sync")
+        for graph in (True, False):
+            us = timed(mc_sync, 100, graph)
+            t = torch.tensor([us], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[f"mcast_allreduce_barrier{'_graph' if graph else '_direct'}_us"] = round(float(t[0]), 2)
+        pkg.check(L.b200_gen_uniform_f64(ctx.h, bufs.local[0].ptr, n, 11, 0.0, 1.0), "x0")
+        bufs.local[1].fill_bytes(0)
+        barrier()
+        it = pkg.Iterator(pkg, ctx, None, sell, blocks, rank, world, bufs.ptrs[:2], mode="fused_mcast", halo=halo,
+                          graph_steps=100, mcast=mc)
+        it.run(201)
+        barrier()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        it.run(100)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_ms_until(b) * 10.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["iterator_mcast_graph100_us"] = round(float(t[0]), 2)
+        it.close()
+        barrier()
+        mc.close()
     if rank == 0:
         print(json.dumps({"world": world, "nccl": comm.nccl_version(), **out}))
     barrier()

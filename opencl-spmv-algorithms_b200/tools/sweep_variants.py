@@ -29,7 +29,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
-HOOKS = ("B200_SELL_TMA", "B200_SELL_TMA_BLOCKS", "B200_CSR_LANES", "B200_CSR_UNROLL", "B200_ELL_LANES", "B200_ELL_UNROLL", "B200_SELL_WPC",
+HOOKS = ("B200_CMRS_STREAM", "B200_SELL_TMA", "B200_SELL_TMA_BLOCKS", "B200_CSR_LANES", "B200_CSR_UNROLL", "B200_ELL_LANES", "B200_ELL_UNROLL", "B200_SELL_WPC",
          "B200_SELL_UNROLL", "B200_COO_U", "B200_CMRS_U", "B200_CMRS_WPS", "B200_CSR_STREAM")
 
 
@@ -48,6 +48,8 @@ def variants(workload: str, args_no_tma: bool = False, tma_only: bool = False):
         out["sell"] += [{"B200_SELL_TMA": 1, "B200_SELL_TMA_BLOCKS": b} for b in (1, 2, 3)]
     if small:
         out["csr"].append({"B200_CSR_STREAM": 1})
+        for f in ("cmrs", "cmrs_packed"):   # the nnz-split kernel (atomics at run ends, like COO), forced
+            out[f] += [{"B200_CMRS_STREAM": 1, "B200_CMRS_U": u} for u in (1, 2)]
     if tma_only:
         return {"sell": [{}] + [e for e in out["sell"] if "B200_SELL_TMA" in e]}
     for f in out:
@@ -118,6 +120,15 @@ def main():
                 m._plan = None
             m.plan()
 
+    def reset_cmrs_plans():
+        # ... and so does the CMRS plan (strip kernel vs nnz-split kernel); cmrs_packed shares it
+        for st in sets:
+            m = st["cmrs"]
+            if getattr(m, "_plan", None):
+                pkg.lib().b200_cmrs_plan_destroy(m._plan)
+                m._plan = None
+            m.plan()
+
     results = []
     for fmt, envs in variants(args.workload, args.no_tma, args.tma_only).items():
         if args.only and fmt not in args.only.split(","):
@@ -127,6 +138,8 @@ def main():
             set_env(env)
             if fmt == "csr":
                 reset_plans()
+            if fmt in ("cmrs", "cmrs_packed"):
+                reset_cmrs_plans()
             for st in sets:  # un-graphed pass: builds plans, loads the kernel
                 st[fmt].spmv(x, y)
             ctx.sync()

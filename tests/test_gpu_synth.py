@@ -325,6 +325,16 @@ def test_library_iterator_one_gpu(ctx, mode, graph_steps):
         pkg.Iterator(pkg, ctx, None, mats[0], blocks, 0, 1, [[bufs[0].ptr], [bufs[1].ptr]], mode=mode, graph_steps=3)
 
 
+def test_iterated_80_cubed_matches_the_cpu_restatement(ctx):
+    """the iterated mode on an 80^3 7-point Laplacian (512 000 rows) through the
+    library's iterator (fused kernel, launch-graph replay) against the CPU restatement, same seeded x0 --
+    the very check bench.py reports as iterated.oracle_80cubed."""
+    import bench
+    res = bench.iterated_oracle_check(pkg, ctx, g=80, steps=50)
+    assert res["ok"] and res["rel_diff"] <= 1e-10, res
+    assert 11.0 < res["norm_gpu"] < 12.0            # the Laplacian's largest eigenvalue is just below 12
+
+
 def test_halo_limited_exchange_three_emulated_ranks(ctx):
     """b200_spmv_sell_halo_f64: three row blocks of a 7-point Laplacian run one after the other on ONE
     GPU, each storing into the next-x buffers of all three 'ranks' but only the rows the destination
