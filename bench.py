@@ -599,8 +599,11 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
         it.close()
         return ms, norm, launches
 
+    fused_ms, fused_norm, fused_launches = run("fused", sell, halo)
+    # the same run once more with the NVML clock sampler on: a polling thread next to a 20-40 ms region of
+    # lock-step collectives perturbs it (probe: 178 -> 185..400 us per step), so the headline is the run above
     with ClockSampler(local_rank) as clk:
-        fused_ms, fused_norm, fused_launches = run("fused", sell, halo)
+        sampled_ms, _, _ = run("fused", sell, halo)
     ag_ms, ag_norm, _ = run("allgather", csr, None)
     direct_ms, direct_norm, _ = run("fused", sell, halo, graph_steps=0)   # same steps, launch by launch
     # the same kernel with the all-reduce + barrier done by the NVSwitch (multimem.red on a multicast block):
@@ -672,7 +675,8 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
     it.close()
     L.b200_host_free_pinned(hx)
 
-    fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms = D.reduce([fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms], "max")
+    fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms, sampled_ms = D.reduce(
+        [fused_ms, ag_ms, direct_ms, spmv_ms, csr_ms, e2e_ms, sampled_ms], "max")
     if mc_ms is not None:
         (mc_ms,) = D.reduce([mc_ms], "max")
     (nnz_total,) = D.reduce([nnz], "sum")
@@ -698,6 +702,7 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
         "halo_bytes_sent_per_step_max_rank": int(halo_max),
         "gpu_launches": int(fused_launches),
         "direct_launches_no_graph": {"ms_per_step": round(direct_ms, 5)},
+        "ms_per_step_while_sampling_clocks": round(sampled_ms, 5),
         "nccl_allgather_formulation": {"ms_per_step": round(ag_ms, 5), "gflops": round(flops / (ag_ms * 1e-3) * 1e-9, 2),
                                        "what": "CSR SpMV into the rank's segment, sum of squares, 1-element all-reduce, "
                                                "scale, in-place ncclAllGather; same launch-graph replay"},
