@@ -384,9 +384,10 @@ def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, segments, d
         np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(n_cols * V,)).view(dtype)[:] = x_host
         return dict(ctx=q, hx=hx, hy=hy, xin=q.zeros(n_cols, dtype))
 
-    q1 = make_queue(ctx)
-    ctx2 = pkg.Context(local_rank)
-    q2 = make_queue(ctx2)
+    # queue 0 is the caller's context; the others are further in-order queues of the same device
+    queues = [make_queue(ctx)]
+    extra_ctx = [pkg.Context(local_rank) for _ in range(len(mats) - 1)]
+    queues += [make_queue(c) for c in extra_ctx]
 
     def call(f, m, q):
         m.ctx = q["ctx"]
@@ -395,67 +396,78 @@ def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, segments, d
         m.spmv(q["xin"], y[f])
         pkg.check(L.b200_memcpy_d2h_async(q["ctx"].h, q["hy"], y[f].ptr, n_rows * V), "d2h y")
 
-    def step_one_queue():
-        for f, m in mats.items():
-            call(f, m, q1)
-        ctx.sync()
+    # The same five calls spread over K in-order queues of the same device (K = 1, 2, one per format): PCIe is
+    # full duplex and the copy engines run next to the SMs, so the y download of one call overlaps the x upload
+    # of the next and the kernel of a third.  Every call still moves its own x in and its own y out.
+    csr_pinned = "csr" in mats and mats["csr"].plan_info().stream_tiles > 0  # a stream plan serves one queue only
 
-    # the same five calls on TWO in-order queues of the same device, formats alternating: PCIe is full
-    # duplex, so the y download of one call overlaps the x upload and kernel of the next
-    csr_on_two = "csr" in mats and mats["csr"].plan_info().stream_tiles > 0  # its plan serves one queue only
-    owner = {f: (q1 if (i % 2 == 0 or (f == "csr" and csr_on_two)) else q2) for i, f in enumerate(mats)}
+    def owners(k):
+        out, i = {}, 0
+        for f in mats:
+            if f == "csr" and csr_pinned:
+                out[f] = queues[0]
+                continue
+            out[f] = queues[i % k]
+            i += 1
+        return out
 
-    def step_two_queues():
-        for f, m in mats.items():
-            call(f, m, owner[f])
-        ctx.sync()
-        ctx2.sync()
+    def timed(k):
+        own = owners(k)
+        used = queues[:k]
 
-    for _ in range(2):
-        step_one_queue()
-    D.barrier(ctx)
-    a, b = ctx.event(), ctx.event()
-    t0 = time.perf_counter()
-    a.record()
-    for _ in range(steps):
-        step_one_queue()
-    b.record()
-    D.barrier(ctx)
-    one_ms = a.elapsed_ms_until(b) / steps
-    one_wall = (time.perf_counter() - t0) * 1e3 / steps
-    for _ in range(2):
-        step_two_queues()
-    D.barrier(ctx)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step_two_queues()
-    D.barrier(ctx)
-    two_wall = (time.perf_counter() - t0) * 1e3 / steps
+        def step():
+            for f, m in mats.items():
+                call(f, m, own[f])
+
+        def drain():
+            for q in used:
+                q["ctx"].sync()
+        for _ in range(2):
+            step()
+        drain()
+        D.barrier(ctx)
+        a, b = ctx.event(), ctx.event()
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        drain()
+        D.barrier(ctx)
+        wall = (time.perf_counter() - t0) * 1e3 / steps
+        return wall, a.elapsed_ms_until(b) / steps
+
+    one_wall, one_ms = timed(1)
+    two_wall, _ = timed(2)
+    all_wall, _ = timed(len(queues))
     for m in mats.values():
         m.ctx = ctx
-    one_ms, one_wall, two_wall = D.reduce([one_ms, one_wall, two_wall], "max")
+    one_ms, one_wall, two_wall, all_wall = D.reduce([one_ms, one_wall, two_wall, all_wall], "max")
     h2d, d2h = D.reduce([len(mats) * n_up * V, len(mats) * n_rows * V], "sum")
-    best = min(one_ms, two_wall)
-    ctx2.sync()
-    for q in (q1, q2):
+    best = min(one_ms, two_wall, all_wall)
+    for q in queues:
+        q["ctx"].sync()
         L.b200_host_free_pinned(q["hx"])
         L.b200_host_free_pinned(q["hy"])
-    del q1, q2
-    ctx2.close()
-    return {"value": round(flops_step / (best * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
+    del queues
+    for c in extra_ctx:
+        c.close()
+    gf = lambda ms: round(flops_step / (ms * 1e-3) * 1e-9, 2)  # noqa: E731
+    return {"value": gf(best), "unit": "GFLOP/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": round(best, 4), "steps": steps,
             "x_columns_uploaded_per_rank": int(n_up), "x_columns_total": int(n_cols),
             "x_segments_rank0": [list(sg) for sg in segments[:8]],
-            "one_queue": {"ms_per_step": round(one_ms, 4), "wall_ms_per_step": round(one_wall, 4),
-                          "gflops": round(flops_step / (one_ms * 1e-3) * 1e-9, 2)},
-            "two_queues": {"wall_ms_per_step": round(two_wall, 4),
-                           "gflops": round(flops_step / (two_wall * 1e-3) * 1e-9, 2)},
+            "one_queue": {"ms_per_step": round(one_ms, 4), "wall_ms_per_step": round(one_wall, 4), "gflops": gf(one_ms)},
+            "two_queues": {"wall_ms_per_step": round(two_wall, 4), "gflops": gf(two_wall)},
+            "queue_per_format": {"queues": len(mats), "wall_ms_per_step": round(all_wall, 4), "gflops": gf(all_wall)},
+            "link_gbs_each_way": round(max(h2d, d2h) / (best * 1e-3) * 1e-9, 1),
             "what": "per format: x from pinned host memory -> device (only the 4096-column blocks this rank's row block "
                     "reads, b200_used_column_blocks), SpMV through the C ABI, y -> pinned host; format arrays uploaded "
-                    "once before the timed region, as the reference driver does (csr.c:183-193). value = the better of one "
-                    "in-order queue (CUDA events) and two queues with alternating formats (wall clock, both drained); max "
-                    "over ranks"}
+                    "once before the timed region, as the reference driver does (csr.c:183-193). The five calls of a step "
+                    "go to 1, 2 or 5 in-order queues (contexts) of the device, every call with its own x upload and y "
+                    "download; value = the best of the three (one queue: CUDA events; several: wall clock, all queues "
+                    "drained); max over ranks"}
 
 
 def time_formats(ctx, D, mats, x, y, steps, warmup, local_rank=None):
@@ -526,7 +538,8 @@ def strong_section(pkg, ctx, D, args, rank, world, dtype, peak):
     D.barrier(ctx)
     (ms,) = D.reduce([e0.elapsed_ms_until(e1) / steps], "max")
     (nnz_total,) = D.reduce([coo.nnz], "sum")
-    (bytes_max,) = D.reduce([sum(m.nbytes(dtype) for m in mats.values())], "max")
+    x_unread = (n - sum(c for _, c in column_segments(pkg, ctx, coo.cols, n))) * np.dtype(dtype).itemsize
+    (bytes_max,) = D.reduce([sum(m.nbytes(dtype) - x_unread for m in mats.values())], "max")
     flops = 2.0 * nnz_total * len(mats)
     return {"value": round(flops / (ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "scaling": "strong",
             "ms_per_step": round(ms, 5), "steps": steps, "n_gpus": world,
@@ -689,7 +702,9 @@ def iterated_section(pkg, D, args, rank, world, local_rank, steps, extras=False,
     rel_direct = abs(fused_norm - direct_norm) / abs(ag_norm)
     parity_ok = bool(rel <= 1e-10 and rel_direct <= 1e-10 and same_on_all_ranks)
     peak, peak_src = measured_peak()
-    alg = sell.nbytes(np.float64)
+    # x is counted over the rows this rank reads (its block + the halo planes), not the whole padded vector
+    x_read = min(int(ranges[rank][1]) + 1, n) - max(int(ranges[rank][0]), 0) if world > 1 else n
+    alg = sell.nbytes(np.float64) - 8 * (n - x_read)
     flops = 2.0 * nnz_total
     out = {
         "ms_per_step": round(fused_ms, 5), "value": round(flops / (fused_ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s",
@@ -896,7 +911,11 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
         sets.append(build_set(pkg.CooMatrix.from_host(ctx, n_rows, n_cols, rows_h, cols_h, vals_h)))
     mats, extra = sets[0]
     y = {f: ctx.zeros(n_rows, dtype) for f in list(mats) + list(extra)}
-    bytes_alg = {f: m.nbytes(dtype) for f, m in {**mats, **extra}.items()}
+    # algorithmic bytes count x ONCE over the columns this row block actually reads (one or two windows of
+    # the replicated x for a banded shard), not the whole replicated vector: at N ranks n_cols is N * R
+    segments = column_segments(pkg, ctx, coo.cols, n_cols)
+    x_unread = (n_cols - sum(c for _, c in segments)) * dtype.itemsize
+    bytes_alg = {f: m.nbytes(dtype) - x_unread for f, m in {**mats, **extra}.items()}
     l2_persist = args.l2_persist != 0
     if l2_persist:
         ctx.set_l2_persist(x)
@@ -1043,7 +1062,6 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
 
     # ---------------- e2e: host x in, host y out, through the C ABI, matrix resident ----------
     e2e = None
-    segments = column_segments(pkg, ctx, coo.cols, n_cols)
     steps_e = max(3, min(args.steps, 20))
     if not args.no_e2e:
         e2e = measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, segments, dtype, steps_e, flops_step)
@@ -1068,7 +1086,7 @@ def spmv_arm(pkg, args, rank, world, local_rank, dtype):
         s64 = red[0]
         for i, f in enumerate(m64):
             p64[f] = red[1 + i]
-        b64 = {f: m.nbytes(d64) for f, m in m64.items()}
+        b64 = {f: m.nbytes(d64) - 2 * x_unread for f, m in m64.items()}   # x_unread counted 4-byte entries
         f64 = {"value": round(flops_step / (s64 * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "ms_per_step": round(s64, 5),
                "steps": k64, "dtype": "f64", "formats": format_table(list(m64), p64, b64, nnz, peak),
                "what": "the same matrix and step in fp64, the reference's only arithmetic (what --impl reference times)"}

@@ -549,6 +549,172 @@ sell32_bcast_kernel(const T *__restrict__ data, const int *__restrict__ idx, con
     }
 }
 
+// The same step as a PERSISTENT, software-pipelined kernel for stencil-width chunks.  sell32_bcast_kernel
+// walks three dependent round trips per 2.7 KB chunk (chunk pointers -> index/value loads -> gathers), and
+// only during the second one does a warp have matrix bytes in flight: measured 5.2 TB/s on the 7-point
+// Laplacian = warps x 2.7 KB x 1/3 of the time / latency.  Here a warp stays resident and walks chunks
+// gw, gw + W, gw + 2W, ... (W = warps of the grid; neighbouring warps work on neighbouring chunks, so the
+// x gathers of a block still share lines): while chunk i is gathered, multiplied and stored, the index and
+// value loads of chunk i+1 are already in flight and the pointers of chunk i+2 are being fetched, so every
+// resident warp keeps one whole chunk in flight all the time.  1/||x|| is folded once per warp instead of
+// once per chunk, and ||y||^2 costs one atomic per block of the (SMs x blocks-per-SM)-block grid instead of
+// 31 250.  Chunks wider than kNarrowW columns take the general 128-bit path inline (not pipelined).
+constexpr int kPipeDefaultBlocks = 3;
+template <typename T>
+struct ChunkRegs {
+    int c[kNarrowW];
+    T v[kNarrowW];
+};
+
+template <typename T, typename P>
+__device__ __forceinline__ void chunk_issue(ChunkRegs<T> &r, const T *__restrict__ data, const int *__restrict__ idx,
+                                            P base, int w, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < kNarrowW; ++k) {
+        r.c[k] = 0;
+        r.v[k] = T(0);
+        if (k < w) {
+            r.c[k] = ld_stream(idx + (long long)base + 32 * k + lane);
+            r.v[k] = ld_stream(data + (long long)base + 32 * k + lane);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T chunk_dot(const ChunkRegs<T> &r, const T *__restrict__ x)
+{
+    int hold = 0;  // 0 at run time; makes every gather wait for ALL of the chunk's loads (see narrow_chunk_dot)
+#pragma unroll
+    for (int k = 0; k < kNarrowW; ++k)
+        hold |= r.c[k] & (sizeof(T) == 8 ? __double2hiint((double)r.v[k]) : __float_as_int((float)r.v[k]));
+    hold >>= 31;
+    T xv[kNarrowW];
+#pragma unroll
+    for (int k = 0; k < kNarrowW; ++k) xv[k] = ld_x(x, r.c[k] + hold);
+    T a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < kNarrowW; k += 2) {
+        a0 += r.v[k] * xv[k];
+        a1 += r.v[k + 1] * xv[k + 1];
+    }
+    return a0 + a1;
+}
+
+template <typename T, typename P, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+sell32_bcast_pipe_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
+                         const P *__restrict__ slice_ptr, int n_slices, int n_rows,
+                         const T *__restrict__ scale2, T *__restrict__ sumsq_out, PeerDst<T> dst, int n_dst,
+                         long long dst_offset)
+{
+    __shared__ T warp_sq[kBlock / 32];
+    // the destinations that take any row at all, compacted once per block (the halo-limited exchange of a
+    // banded matrix has 3 of up to 16: own block + two neighbours): the per-chunk store loop then runs over
+    // those only -- the fully unrolled 16-way test of sell32_bcast_kernel is ~160 instructions per chunk
+    __shared__ T *s_ptr[kMaxPeers];
+    __shared__ int s_lo[kMaxPeers], s_hi[kMaxPeers], s_n;
+    if (threadIdx.x == 0) {
+        int n = 0;
+#pragma unroll
+        for (int d = 0; d < kMaxPeers; ++d)
+            if (d < n_dst && dst.hi[d] > dst.lo[d]) {
+                s_ptr[n] = dst.p[d] + dst_offset;
+                s_lo[n] = dst.lo[d];
+                s_hi[n] = dst.hi[d];
+                ++n;
+            }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n_act = s_n;
+    const int lane = threadIdx.x & 31;
+    const long long W = ((long long)gridDim.x * kBlock) >> 5;
+    long long s = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    T inv_norm = T(1);
+    if (scale2) inv_norm = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
+    // pointers of the first two chunks of this warp, loads of the first
+    P b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+    if (s < n_slices) {
+        b0 = slice_ptr[s];
+        e0 = slice_ptr[s + 1];
+    }
+    if (s + W < n_slices) {
+        b1 = slice_ptr[s + W];
+        e1 = slice_ptr[s + W + 1];
+    }
+    ChunkRegs<T> cur, nxt;
+    int w0 = (int)(((long long)e0 - (long long)b0) >> 5);  // columns of the chunk
+    if (s < n_slices && w0 <= kNarrowW) chunk_issue<T, P>(cur, data, idx, b0, w0, lane);
+    T sq = 0;
+    for (; s < n_slices; s += W) {
+        // chunk i+2: pointers;  chunk i+1: index / value loads -- all issued before chunk i is touched
+        P b2 = 0, e2 = 0;
+        if (s + 2 * W < n_slices) {
+            b2 = slice_ptr[s + 2 * W];
+            e2 = slice_ptr[s + 2 * W + 1];
+        }
+        const int w1 = (int)(((long long)e1 - (long long)b1) >> 5);
+        const bool have1 = s + W < n_slices;
+        if (have1 && w1 <= kNarrowW) chunk_issue<T, P>(nxt, data, idx, b1, w1, lane);
+        T mine;
+        if (w0 <= kNarrowW) {
+            mine = chunk_dot<T>(cur, x);
+        } else {  // general chunk: 128-bit groups, lanes 0-7 end up with rows 4L..4L+3, re-dealt to lane = row
+            const long long n_groups = ((long long)e0 - (long long)b0) >> 2;
+            const int *ip = idx + (long long)b0;
+            const T *dp = data + (long long)b0;
+            T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll 2
+            for (long long g = lane; g < n_groups; g += 32) {
+                IVec4 c;
+                Vec4<T> v;
+                c.load(ip + (g << 2));
+                v.load(dp + (g << 2));
+                acc0 += v.v[0] * ld_x(x, c.v[0]);
+                acc1 += v.v[1] * ld_x(x, c.v[1]);
+                acc2 += v.v[2] * ld_x(x, c.v[2]);
+                acc3 += v.v[3] * ld_x(x, c.v[3]);
+            }
+#pragma unroll
+            for (int off = 8; off <= 16; off <<= 1) {
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+                acc2 += __shfl_xor_sync(0xffffffffu, acc2, off);
+                acc3 += __shfl_xor_sync(0xffffffffu, acc3, off);
+            }
+            const int src = lane >> 2;
+            const T q0 = __shfl_sync(0xffffffffu, acc0, src), q1 = __shfl_sync(0xffffffffu, acc1, src);
+            const T q2 = __shfl_sync(0xffffffffu, acc2, src), q3 = __shfl_sync(0xffffffffu, acc3, src);
+            mine = (lane & 2) ? ((lane & 1) ? q3 : q2) : ((lane & 1) ? q1 : q0);
+        }
+        mine *= inv_norm;
+        const long long r = s * 32 + lane;
+        if (r < n_rows) {
+            sq += mine * mine;
+            for (int i = 0; i < n_act; ++i)
+                if (r >= s_lo[i] && r < s_hi[i]) s_ptr[i][r] = mine;
+        }
+        cur = nxt;
+        w0 = w1;
+        b0 = b1;
+        e0 = e1;
+        b1 = b2;
+        e1 = e2;
+    }
+    if (sumsq_out) {
+        sq = subwarp_sum<32>(sq);
+        if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T total = 0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) total += warp_sq[w];
+            atomicAdd(sumsq_out + (blockIdx.x & (kSumsqSlots - 1)), total);
+        }
+    }
+}
+
 // Second (one-warp) launch of a ring step -- the whole "all-reduce + barrier" of the step:
 //   publish  this rank's 32 partial sums of ||y||^2 go to every rank's sync block, a system-wide fence,
 //            then flag[my_rank] = k+1 is released in every rank's block.  The kernel runs after the SpMV
@@ -912,8 +1078,27 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         ring_sync_kernel<<<1, 32, 0, ctx->stream>>>(sync);
         ctx->watch_flag = true;
     } else {
-        sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
-            data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
+        // B200_BCAST_U = 2 / 3 / 4: the persistent pipelined kernel at that many blocks per SM; 1: one warp per
+        // chunk, one chunk per warp.  Default: pipelined when the launch has at least 4 chunks per resident warp.
+        int pipe = opt_or(ctx, OPT_BCAST_U, 0);
+        if (pipe == 0) pipe = (long long)n_slices >= 4ll * ctx->sm_count * kPipeDefaultBlocks * (kBlock / 32) ? kPipeDefaultBlocks : 1;
+        if (pipe >= 2) {
+            int per_sm = 0;
+            void (*kern)(const double *, const int *, const double *, const int *, int, int, const double *, double *,
+                         PeerDst<double>, int, long long) =
+                pipe == 2 ? sell32_bcast_pipe_kernel<double, int, 2>
+                : pipe == 3 ? sell32_bcast_pipe_kernel<double, int, 3>
+                            : sell32_bcast_pipe_kernel<double, int, 4>;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
+            if (per_sm < 1) per_sm = 1;
+            unsigned pgrid = (unsigned)ctx->sm_count * (unsigned)per_sm;
+            if (pgrid > grid) pgrid = grid;
+            kern<<<pgrid, kBlock, 0, ctx->stream>>>(data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out,
+                                                    d, n_dst, dst_offset);
+        } else {
+            sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
+                data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
+        }
     }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;

@@ -212,7 +212,7 @@ static void *rank_main(void *argp)
         d.rows_per_rank = s->rows_per_rank;
         d.x[0] = s->x[0];
         d.x[1] = s->x[1];
-        if (d.mode == B200_ITER_FUSED) {
+        if (d.mode != B200_ITER_ALLGATHER) { /* both fused modes send only the rows a peer reads */
             d.halo_lo = halo_lo;
             d.halo_hi = halo_hi;
         }

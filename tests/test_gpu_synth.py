@@ -335,14 +335,18 @@ def test_iterated_80_cubed_matches_the_cpu_restatement(ctx):
     assert 11.0 < res["norm_gpu"] < 12.0            # the Laplacian's largest eigenvalue is just below 12
 
 
-def test_halo_limited_exchange_three_emulated_ranks(ctx):
+@pytest.mark.parametrize("bcast_u", [None, 1, 2, 3, 4])
+def test_halo_limited_exchange_three_emulated_ranks(ctx, bcast_u):
     """b200_spmv_sell_halo_f64: three row blocks of a 7-point Laplacian run one after the other on ONE
     GPU, each storing into the next-x buffers of all three 'ranks' but only the rows the destination
     reads (halo_rows from the blocks' column ranges).  The all-reduce of ||y||^2 is emulated on the
     host.  Must reproduce the CPU power iteration; rows outside a rank's block + halo must never be
-    touched."""
+    touched.  B200_BCAST_U: 1 = one chunk per warp, 2..4 = the persistent pipelined kernel at that many
+    blocks per SM (the default picks it for large launches only, so it is forced here)."""
     import ctypes as C
     L = pkg.lib()
+    if bcast_u is not None:
+        ctx.set_option("B200_BCAST_U", bcast_u)
     nx, ny, nz, steps, G = 16, 12, 30, 25, 3
     n, rows, cols, vals = laplace7(nx, ny, nz)
     blocks = pkg.equal_row_blocks(n, G)
@@ -408,3 +412,35 @@ def test_halo_limited_exchange_three_emulated_ranks(ctx):
             assert np.all(got[outside] == SENTINEL), r
         assert not np.any(got[need_lo:need_hi] == SENTINEL)
 
+
+
+@pytest.mark.parametrize("bcast_u", [1, 2, 3, 4])
+def test_fused_kernel_variants_on_mixed_chunk_widths(ctx, bcast_u):
+    """The fused kernel on a matrix whose SELL chunks are narrow (<= 8 columns: the pipelined lane = row
+    path), wide (the 128-bit general path) and empty-rowed, in an order that alternates them inside one
+    warp's walk, with a single destination: y / ||x|| and ||y||^2 against the oracle."""
+    import ctypes as C
+    L = pkg.lib()
+    rng = np.random.default_rng(11)
+    n = 32 * 700 + 13                                   # a ragged last chunk
+    lens = rng.integers(0, 8, n)                         # narrow by default (some rows empty)
+    for c0 in rng.choice(n // 32, 90, replace=False):    # ~13 % of the chunks get one long row
+        lens[c0 * 32 + rng.integers(0, 32)] = rng.integers(9, 200)
+    rows = np.repeat(np.arange(n, dtype=np.int32), lens)
+    cols = rng.integers(0, n, rows.size).astype(np.int32)
+    vals = rng.uniform(-1, 1, rows.size)
+    x = rng.uniform(0.5, 1.5, n)
+    prev = rng.uniform(0, 2, 32)                         # the 32 partial sums of ||x||^2 the kernel scales by
+    y_ref = O.yref(n, rows, cols, vals, x) / np.sqrt(prev.sum())
+    coo = pkg.CooMatrix.from_host(ctx, n, n, rows, cols, vals)
+    sell = pkg.SellMatrix(pkg.CsrMatrix(coo, check_sorted=False), np.float64)
+    ctx.set_option("B200_BCAST_U", bcast_u)
+    xd, scale, acc = ctx.array(x), ctx.array(prev), ctx.zeros(32, np.float64)
+    out = ctx.array(np.full(n + 64, -7.0))
+    dst = (C.c_void_p * 1)(out.ptr)
+    pkg.check(L.b200_spmv_sell_halo_f64(ctx.h, sell.data.ptr, sell.cols.ptr, xd.ptr, sell.row_indices.ptr, 32,
+                                        sell.n_slices, n, scale.ptr, acc.ptr, dst, 1, 32, None, None), "fused kernel")
+    got = out.download()
+    assert np.all(got[:32] == -7.0) and np.all(got[32 + n:] == -7.0)       # offset respected, nothing past the end
+    assert np.max(np.abs(got[32:32 + n] - y_ref)) <= 1e-12 * np.abs(y_ref).max()
+    assert abs(acc.download().sum() - np.dot(y_ref, y_ref)) <= 1e-12 * np.dot(y_ref, y_ref)
