@@ -1058,6 +1058,32 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
     PeerSync sync;
     memset(&sync, 0, sizeof sync);
     const unsigned grid = ceil_div_u((long long)n_slices * 32, kBlock);
+    // B200_BCAST_U = 2 / 3 / 4: the persistent pipelined kernel at that many blocks per SM; 1: one warp per
+    // chunk, one chunk per warp.  Default: pipelined when the launch has at least 4 chunks per resident warp
+    // (7-point Laplacian, 8 M rows: 0.151 -> 0.122 ms at 3 blocks per SM, 0.140 at 2, 0.172 at 4 -- spills).
+    int pipe = opt_or(ctx, OPT_BCAST_U, 0);
+    if (pipe == 0) pipe = (long long)n_slices >= 4ll * ctx->sm_count * kPipeDefaultBlocks * (kBlock / 32) ? kPipeDefaultBlocks : 1;
+    unsigned pgrid = 0;
+    void (*pipe_kernel)(const double *, const int *, const double *, const int *, int, int, const double *, double *,
+                        PeerDst<double>, int, long long) = nullptr;
+    if (pipe >= 2) {
+        pipe_kernel = pipe == 2   ? sell32_bcast_pipe_kernel<double, int, 2>
+                      : pipe == 3 ? sell32_bcast_pipe_kernel<double, int, 3>
+                                  : sell32_bcast_pipe_kernel<double, int, 4>;
+        int per_sm = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipe_kernel, kBlock, 0));
+        if (per_sm < 1) per_sm = 1;
+        pgrid = (unsigned)ctx->sm_count * (unsigned)per_sm;
+        if (pgrid > grid) pgrid = grid;
+    }
+    auto launch_fused = [&](const double *scale, double *sums) {
+        if (pipe_kernel)
+            pipe_kernel<<<pgrid, kBlock, 0, ctx->stream>>>(data, indices, vect, row_indices, n_slices, n_rows, scale, sums, d,
+                                                           n_dst, dst_offset);
+        else
+            sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(data, indices, vect, row_indices, n_slices,
+                                                                               n_rows, scale, sums, d, n_dst, dst_offset);
+    };
     if (sync_blocks) {
         for (int i = 0; i < n_dst; ++i) {
             B200_REQUIRE(sync_blocks[i], "null sync block");
@@ -1073,32 +1099,11 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
         sync.sleep_ns = opt_or(ctx, OPT_RING_SLEEP_NS, 100);
         double *acc = reinterpret_cast<double *>(sync.mine + kSyncAcc);
         const double *scale = step > 0 ? reinterpret_cast<const double *>(sync.mine + kSyncScale) : nullptr;
-        sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
-            data, indices, vect, row_indices, n_slices, n_rows, scale, acc, d, n_dst, dst_offset);
+        launch_fused(scale, acc);
         ring_sync_kernel<<<1, 32, 0, ctx->stream>>>(sync);
         ctx->watch_flag = true;
     } else {
-        // B200_BCAST_U = 2 / 3 / 4: the persistent pipelined kernel at that many blocks per SM; 1: one warp per
-        // chunk, one chunk per warp.  Default: pipelined when the launch has at least 4 chunks per resident warp.
-        int pipe = opt_or(ctx, OPT_BCAST_U, 0);
-        if (pipe == 0) pipe = (long long)n_slices >= 4ll * ctx->sm_count * kPipeDefaultBlocks * (kBlock / 32) ? kPipeDefaultBlocks : 1;
-        if (pipe >= 2) {
-            int per_sm = 0;
-            void (*kern)(const double *, const int *, const double *, const int *, int, int, const double *, double *,
-                         PeerDst<double>, int, long long) =
-                pipe == 2 ? sell32_bcast_pipe_kernel<double, int, 2>
-                : pipe == 3 ? sell32_bcast_pipe_kernel<double, int, 3>
-                            : sell32_bcast_pipe_kernel<double, int, 4>;
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
-            if (per_sm < 1) per_sm = 1;
-            unsigned pgrid = (unsigned)ctx->sm_count * (unsigned)per_sm;
-            if (pgrid > grid) pgrid = grid;
-            kern<<<pgrid, kBlock, 0, ctx->stream>>>(data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out,
-                                                    d, n_dst, dst_offset);
-        } else {
-            sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(
-                data, indices, vect, row_indices, n_slices, n_rows, scale_sumsq, sumsq_out, d, n_dst, dst_offset);
-        }
+        launch_fused(scale_sumsq, sumsq_out);
     }
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;

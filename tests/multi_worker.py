@@ -84,26 +84,35 @@ def main():
         check(name + " own block", float(np.max(np.abs(own - x[b0:b1]))) <= 1e-12)
         return got
 
-    for mode, graph in (("fused", 0), ("fused", 4), ("allgather", 0), ("allgather", 4)):
+    # "fused" runs twice: with the library's choice of kernel (one chunk per warp at this size) and with the
+    # persistent pipelined kernel forced (B200_BCAST_U = 3), which large blocks take by default
+    for mode, graph, bcast_u in (("fused", 0, None), ("fused", 4, None), ("fused", 0, 3), ("fused", 4, 3),
+                                 ("allgather", 0, None), ("allgather", 4, None)):
         reset()
+        ctx.set_option("B200_BCAST_U", bcast_u)
+        if bcast_u is not None:
+            mode_name = f"{mode}(pipelined)"
+        else:
+            mode_name = mode
         it = pkg.Iterator(pkg, ctx, comm, sell if mode == "fused" else csr, blocks, rank, world, bufs.ptrs[:2],
                           mode=mode, halo=halo if mode == "fused" else None, graph_steps=graph)
         it.run(7)
         it.run(steps - 7)           # 24 more: graph of 4 replayed six times, or 24 direct steps
         norm = it.norm()
         k, xptr, launches = it.state()
-        check(f"{mode}/g{graph} steps", k == steps and launches > 0, (k, launches))
-        got = verify(f"{mode}/g{graph}", norm, xptr, normalised=(mode == "allgather"))
+        check(f"{mode_name}/g{graph} steps", k == steps and launches > 0, (k, launches))
+        got = verify(f"{mode_name}/g{graph}", norm, xptr, normalised=(mode == "allgather"))
         if mode == "fused":
             # only this rank's block and its neighbours' halo planes were ever written
             need_lo, need_hi = max(b0 - plane, 0), min(b1 + plane, n)
             outside = np.ones(blocks.padded, bool)
             outside[need_lo:need_hi] = False
-            check(f"{mode}/g{graph} nothing outside block + halo", np.all(got[outside] == -7.0))
-            check(f"{mode}/g{graph} block + halo complete", not np.any(got[need_lo:need_hi] == -7.0))
+            check(f"{mode_name}/g{graph} nothing outside block + halo", np.all(got[outside] == -7.0))
+            check(f"{mode_name}/g{graph} block + halo complete", not np.any(got[need_lo:need_hi] == -7.0))
         else:
-            check(f"{mode}/g{graph} whole vector gathered", float(np.max(np.abs(got[:n] - x))) <= 1e-12)
+            check(f"{mode_name}/g{graph} whole vector gathered", float(np.max(np.abs(got[:n] - x))) <= 1e-12)
         it.close()
+    ctx.set_option("B200_BCAST_U", None)
 
     # the same fused kernel with the all-reduce + barrier done by the NVSwitch (multimem.red on a multicast
     # block) instead of NCCL: two launches per step, no collective call.  Skipped (recorded) where the box
