@@ -22,7 +22,7 @@ enum b200_opt {
     OPT_CSR_LANES, OPT_ELL_LANES, OPT_CSR_UNROLL, OPT_ELL_UNROLL, OPT_CSR_STREAM, OPT_SELL_WPC,
     OPT_SELL_UNROLL, OPT_SELL_TMA, OPT_SELL_TMA_BLOCKS, OPT_SELL_TMA_SUSPEND_NS, OPT_COO_U, OPT_CMRS_U,
     OPT_CMRS_WPS, OPT_CMRS_STREAM, OPT_ELLCM_Q, OPT_RING_FLUSH, OPT_RING_POLL, OPT_RING_SLEEP_NS,
-    OPT_BCAST_U, OPT_CSR_STREAM_G, OPT_COUNT
+    OPT_BCAST_U, OPT_CSR_STREAM_G, OPT_SELL_PIPE, OPT_COUNT
 };
 constexpr int kOptUnset = INT_MIN;
 extern const char *const b200_opt_names[OPT_COUNT];

@@ -398,6 +398,7 @@ __global__ void sell_wide_items_kernel(const P *__restrict__ slice_ptr, int n_sl
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slices) return;
     const long long width = ((long long)slice_ptr[s + 1] - (long long)slice_ptr[s]) >> 5;
+    if (!items && width > kNarrowW) atomicAdd(counter + 1, 1);  // first pass only: chunks off the lane = row path
     const int extra = (int)((width + wmax - 1) / wmax) - 1;
     if (extra <= 0) return;
     const int at = atomicAdd(counter, extra);
@@ -601,12 +602,14 @@ __device__ __forceinline__ T chunk_dot(const ChunkRegs<T> &r, const T *__restric
     return a0 + a1;
 }
 
-template <typename T, typename P, int MINB>
+// FUSED = false is the plain SpMV (b200_spmv_sell_*) of a matrix whose plan found stencil-width chunks only:
+// y[perm ? perm[r] : r] = row sum, nothing else.
+template <typename T, typename P, int MINB, bool FUSED>
 __global__ void __launch_bounds__(kBlock, MINB)
-sell32_bcast_pipe_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
-                         const P *__restrict__ slice_ptr, int n_slices, int n_rows,
-                         const T *__restrict__ scale2, T *__restrict__ sumsq_out, PeerDst<T> dst, int n_dst,
-                         long long dst_offset)
+sell32_pipe_kernel(const T *__restrict__ data, const int *__restrict__ idx, const T *__restrict__ x,
+                   const P *__restrict__ slice_ptr, int n_slices, int n_rows,
+                   const T *__restrict__ scale2, T *__restrict__ sumsq_out, PeerDst<T> dst, int n_dst,
+                   long long dst_offset, T *__restrict__ y, const int *__restrict__ perm)
 {
     __shared__ T warp_sq[kBlock / 32];
     // the destinations that take any row at all, compacted once per block (the halo-limited exchange of a
@@ -614,25 +617,27 @@ sell32_bcast_pipe_kernel(const T *__restrict__ data, const int *__restrict__ idx
     // those only -- the fully unrolled 16-way test of sell32_bcast_kernel is ~160 instructions per chunk
     __shared__ T *s_ptr[kMaxPeers];
     __shared__ int s_lo[kMaxPeers], s_hi[kMaxPeers], s_n;
-    if (threadIdx.x == 0) {
-        int n = 0;
+    if (FUSED) {
+        if (threadIdx.x == 0) {
+            int n = 0;
 #pragma unroll
-        for (int d = 0; d < kMaxPeers; ++d)
-            if (d < n_dst && dst.hi[d] > dst.lo[d]) {
-                s_ptr[n] = dst.p[d] + dst_offset;
-                s_lo[n] = dst.lo[d];
-                s_hi[n] = dst.hi[d];
-                ++n;
-            }
-        s_n = n;
+            for (int d = 0; d < kMaxPeers; ++d)
+                if (d < n_dst && dst.hi[d] > dst.lo[d]) {
+                    s_ptr[n] = dst.p[d] + dst_offset;
+                    s_lo[n] = dst.lo[d];
+                    s_hi[n] = dst.hi[d];
+                    ++n;
+                }
+            s_n = n;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int n_act = s_n;
+    const int n_act = FUSED ? s_n : 0;
     const int lane = threadIdx.x & 31;
     const long long W = ((long long)gridDim.x * kBlock) >> 5;
     long long s = ((long long)blockIdx.x * kBlock + threadIdx.x) >> 5;
     T inv_norm = T(1);
-    if (scale2) inv_norm = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
+    if (FUSED && scale2) inv_norm = rsqrt(subwarp_sum<32>(__ldg(scale2 + lane)));
     // pointers of the first two chunks of this warp, loads of the first
     P b0 = 0, e0 = 0, b1 = 0, e1 = 0;
     if (s < n_slices) {
@@ -688,12 +693,16 @@ sell32_bcast_pipe_kernel(const T *__restrict__ data, const int *__restrict__ idx
             const T q2 = __shfl_sync(0xffffffffu, acc2, src), q3 = __shfl_sync(0xffffffffu, acc3, src);
             mine = (lane & 2) ? ((lane & 1) ? q3 : q2) : ((lane & 1) ? q1 : q0);
         }
-        mine *= inv_norm;
         const long long r = s * 32 + lane;
-        if (r < n_rows) {
-            sq += mine * mine;
-            for (int i = 0; i < n_act; ++i)
-                if (r >= s_lo[i] && r < s_hi[i]) s_ptr[i][r] = mine;
+        if (FUSED) {
+            mine *= inv_norm;
+            if (r < n_rows) {
+                sq += mine * mine;
+                for (int i = 0; i < n_act; ++i)
+                    if (r >= s_lo[i] && r < s_hi[i]) s_ptr[i][r] = mine;
+            }
+        } else if (r < n_rows) {
+            y[perm ? perm[r] : r] = mine;
         }
         cur = nxt;
         w0 = w1;
@@ -702,7 +711,7 @@ sell32_bcast_pipe_kernel(const T *__restrict__ data, const int *__restrict__ idx
         b1 = b2;
         e1 = e2;
     }
-    if (sumsq_out) {
+    if (FUSED && sumsq_out) {
         sq = subwarp_sum<32>(sq);
         if (lane == 0) warp_sq[threadIdx.x >> 5] = sq;
         __syncthreads();
@@ -839,6 +848,7 @@ struct b200_sell_plan {
     int n_items;   // extra (chunk, segment) work items
     int wmax;      // columns per segment
     int2 *items;   // device
+    int n_not_narrow;  // chunks wider than kNarrowW columns (0: a stencil matrix, served by the pipelined kernel)
 };
 
 namespace {
@@ -853,17 +863,20 @@ int sell_plan_create_impl(b200_ctx *ctx, const P *slice_ptr, int n_slices, b200_
     p->device = ctx->device;
     p->n_slices = n_slices;
     p->n_items = 0;
+    p->n_not_narrow = n_slices;
     p->wmax = kSellWmax;
     p->items = nullptr;
     if (n_slices > 0) {
         int *counter = ctx->scratch + 192;
         const unsigned blocks = ceil_div_u(n_slices, 256);
-        int count = 0;
-        cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
+        int counts[2] = {0, 0};
+        cudaError_t e = cudaMemsetAsync(counter, 0, 2 * sizeof(int), ctx->stream);
         sell_wide_items_kernel<P><<<blocks, 256, 0, ctx->stream>>>(slice_ptr, n_slices, p->wmax, counter, nullptr);
         if (e == cudaSuccess) e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&count, counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts, counter, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        const int count = counts[0];
+        p->n_not_narrow = counts[1];
         if (e == cudaSuccess && count > 0) {
             e = cudaMalloc(&p->items, sizeof(int2) * (size_t)count);
             if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream);
@@ -930,6 +943,34 @@ int spmv_sell_impl(b200_ctx *ctx, const T *data, const int *idx, const T *x, T *
             B200_LAUNCH_CHECK();
             ctx->watch_flag = true;
             return B200_SUCCESS;
+        }
+        // Stencil matrices (the plan found no chunk wider than kNarrowW columns) in launches of at least 4 chunks
+        // per resident warp: the persistent software-pipelined kernel (sell32_pipe_kernel; 7-point Laplacian,
+        // 8 M rows, fp64: see profiles/r2_pipelined_kernels.md).  B200_SELL_PIPE = 0 turns it off, 2 | 3 | 4 force
+        // it at that many blocks per SM (any matrix: wider chunks take its inline general path, un-pipelined).
+        {
+            int pipe = opt_or(ctx, OPT_SELL_PIPE, -1);
+            if (pipe < 0)
+                pipe = (plan && plan->n_not_narrow == 0 && wmax == 0 &&
+                        (long long)n_slices >= 4ll * ctx->sm_count * kPipeDefaultBlocks * (kBlock / 32))
+                           ? kPipeDefaultBlocks
+                           : 0;
+            if (pipe >= 2 && wmax == 0) {
+                void (*kern)(const T *, const int *, const T *, const P *, int, int, const T *, T *, PeerDst<T>, int,
+                             long long, T *, const int *) = pipe == 2   ? sell32_pipe_kernel<T, P, 2, false>
+                                                           : pipe == 3 ? sell32_pipe_kernel<T, P, 3, false>
+                                                                       : sell32_pipe_kernel<T, P, 4, false>;
+                int per_sm = 0;
+                B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
+                if (per_sm < 1) per_sm = 1;
+                unsigned pgrid = (unsigned)ctx->sm_count * (unsigned)per_sm;
+                if (pgrid > blocks) pgrid = blocks;
+                PeerDst<T> none;
+                memset(&none, 0, sizeof none);
+                B200_CUDA(b200_launch(ctx, false, kern, dim3(pgrid), dim3(kBlock), 0, data, idx, x, slice_ptr, n_slices, n_out,
+                                      (const T *)nullptr, (T *)nullptr, none, 0, 0ll, y, perm));
+                return B200_SUCCESS;
+            }
         }
         // warps per chunk: enough warps for ~32 per SM (tuning hook B200_SELL_WPC=1|2|4|8); chunks
         // that the plan splits by columns anyway stay one warp each
@@ -1065,11 +1106,11 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
     if (pipe == 0) pipe = (long long)n_slices >= 4ll * ctx->sm_count * kPipeDefaultBlocks * (kBlock / 32) ? kPipeDefaultBlocks : 1;
     unsigned pgrid = 0;
     void (*pipe_kernel)(const double *, const int *, const double *, const int *, int, int, const double *, double *,
-                        PeerDst<double>, int, long long) = nullptr;
+                        PeerDst<double>, int, long long, double *, const int *) = nullptr;
     if (pipe >= 2) {
-        pipe_kernel = pipe == 2   ? sell32_bcast_pipe_kernel<double, int, 2>
-                      : pipe == 3 ? sell32_bcast_pipe_kernel<double, int, 3>
-                                  : sell32_bcast_pipe_kernel<double, int, 4>;
+        pipe_kernel = pipe == 2   ? sell32_pipe_kernel<double, int, 2, true>
+                      : pipe == 3 ? sell32_pipe_kernel<double, int, 3, true>
+                                  : sell32_pipe_kernel<double, int, 4, true>;
         int per_sm = 0;
         B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipe_kernel, kBlock, 0));
         if (per_sm < 1) per_sm = 1;
@@ -1079,7 +1120,7 @@ static int sell_exchange_impl(b200_ctx *ctx, const double *data, const int *indi
     auto launch_fused = [&](const double *scale, double *sums) {
         if (pipe_kernel)
             pipe_kernel<<<pgrid, kBlock, 0, ctx->stream>>>(data, indices, vect, row_indices, n_slices, n_rows, scale, sums, d,
-                                                           n_dst, dst_offset);
+                                                           n_dst, dst_offset, nullptr, nullptr);
         else
             sell32_bcast_kernel<double, int><<<grid, kBlock, 0, ctx->stream>>>(data, indices, vect, row_indices, n_slices,
                                                                                n_rows, scale, sums, d, n_dst, dst_offset);

@@ -82,6 +82,35 @@ def main():
         out["variants"][str(v)] = {"kernel_ms": round(ms, 5), "gbs": round(alg / (ms * 1e-3) * 1e-9, 1),
                                    "iterator_step_ms": round(step_ms, 5), "norm_after_301_steps": norm,
                                    "max_abs_diff_vs_first": float(np.max(np.abs(y - ref)))}
+    # the plain SpMV (b200_spmv_sell_*, plan attached) of the same matrix: B200_SELL_PIPE = 0 (one chunk per
+    # warp) | 2 | 3 | 4 (persistent pipelined kernel at that many blocks per SM) | unset (the plan's choice)
+    ctx.set_option("B200_BCAST_U", None)
+    out["plain_spmv"] = {}
+    csr = sell.csr
+    for dt in (np.float64, np.float32):
+        m = sell if dt == np.float64 else pkg.SellMatrix(csr, dt)
+        xs, ys = ctx.zeros(n, dt), ctx.zeros(n, dt)
+        gen = L.b200_gen_uniform_f64 if dt == np.float64 else L.b200_gen_uniform_f32
+        pkg.check(gen(ctx.h, xs.ptr, n, 11, 0.0, 1.0), "x")
+        alg_p = m.nbytes(dt)
+        res, first = {}, None
+        for v in (0, 2, 3, 4, None):
+            ctx.set_option("B200_SELL_PIPE", v)
+            for _ in range(5):
+                m.spmv(xs, ys)
+            e0, e1 = ctx.event(), ctx.event()
+            e0.record()
+            for _ in range(args.reps):
+                m.spmv(xs, ys)
+            e1.record()
+            ctx.sync()
+            ms = e0.elapsed_ms_until(e1) / args.reps
+            got = ys.download()
+            first = got if first is None else first
+            res["auto" if v is None else str(v)] = {"ms": round(ms, 5), "gbs": round(alg_p / (ms * 1e-3) * 1e-9, 1),
+                                                    "bit_identical_to_pipe0": bool(np.array_equal(got, first))}
+        out["plain_spmv"]["f64" if dt == np.float64 else "f32"] = {"alg_bytes": int(alg_p), "variants": res}
+    ctx.set_option("B200_SELL_PIPE", None)
     print(json.dumps(out))
     ctx.close()
 

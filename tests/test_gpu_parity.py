@@ -802,7 +802,10 @@ def test_no_kernel_writes_outside_its_output(ctx, dtype):
         for name, mat in m.items():
             variants = [{}]
             if name == "sell":
-                variants = [{"B200_SELL_WPC": w} for w in (1, 2, 4, 8)] + [{"B200_SELL_TMA": 1}]
+                variants = ([{"B200_SELL_WPC": w} for w in (1, 2, 4, 8)] + [{"B200_SELL_TMA": 1}] +
+                            [{"B200_SELL_PIPE": k} for k in (2, 3, 4)])
+            if name == "sell_sigma":
+                variants = [{}, {"B200_SELL_PIPE": 3}]
             if name == "cmrs":
                 variants = [{"B200_CMRS_WPS": w} for w in (1, 2, 4)] + [{"B200_CMRS_STREAM": 1}]
             if name == "csr":
@@ -822,3 +825,26 @@ def test_no_kernel_writes_outside_its_output(ctx, dtype):
                     ctx.set_option(k, None)
                 assert np.all(got[:pad_before] == SENT) and np.all(got[pad_before + n_rows:] == SENT), (name, env, n_rows)
                 check_y(f"guarded {name} {env}", got[pad_before:pad_before + n_rows], y_ref, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sell_pipelined_kernel_on_a_stencil_matrix(ctx, dtype):
+    """A 7-point Laplacian large enough (80^3 rows = 16 000 chunks, none wider than 8 columns) that
+    b200_spmv_sell_* with a plan takes the persistent pipelined kernel by itself; every forced variant
+    (B200_SELL_PIPE = 0 | 2 | 3 | 4) must return the same y bit for bit, equal to the oracle's."""
+    from test_distributed_cpu import laplace7
+    n, rows, cols, vals = laplace7(80, 80, 80)
+    x = np.random.default_rng(3).uniform(-1, 1, n)
+    y_ref = O.yref(n, rows, cols, vals.astype(dtype).astype(np.float64), x.astype(dtype).astype(np.float64))
+    coo = pkg.CooMatrix.from_host(ctx, n, n, rows, cols, vals)
+    sell = pkg.SellMatrix(pkg.CsrMatrix(coo), dtype, wide=True)       # wide=True: the SpMV call carries a plan
+    xd = ctx.array(x.astype(dtype))
+    outs = {}
+    for pipe in (None, 0, 2, 3, 4):
+        ctx.set_option("B200_SELL_PIPE", pipe)
+        yd = ctx.array(np.full(n, np.nan, dtype))
+        sell.spmv(xd, yd)
+        outs[pipe] = yd.download()
+    for pipe, got in outs.items():
+        assert np.array_equal(got, outs[0]), pipe                      # same products, same summation order
+    check_y("sell pipelined stencil", outs[None], y_ref, dtype)
