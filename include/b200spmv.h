@@ -199,7 +199,10 @@ int b200_spmv_ellcm_f32(b200_ctx *ctx, const float *data_cm, const int *indices_
  * output[perm[new_row]].  chunk must be 32 (warp-aligned chunks).
  * `plan` (new; NULL = one warp walks each chunk whole, which is what FEM-like inputs want) lists
  * the chunks wider than 256 columns -- power-law inputs, where one hub row makes a chunk 10^5
- * columns wide -- so that their columns are split over many warps (atomics for the extra pieces). */
+ * columns wide -- so that their columns are split over many warps (atomics for the extra pieces).
+ * The plan also counts the chunks wider than 8 columns: a matrix with none (a stencil) in a launch of
+ * at least 4 chunks per resident warp is served by the persistent software-pipelined kernel
+ * (B200_SELL_PIPE = 0 turns that off, 2 | 3 | 4 force it at that many blocks per SM). */
 typedef struct b200_sell_plan b200_sell_plan;
 int b200_sell_plan_create(b200_ctx *ctx, const int *row_indices, int n_slices, b200_sell_plan **plan);
 int b200_sell64_plan_create(b200_ctx *ctx, const long long *slice_ptr, int n_slices, b200_sell_plan **plan);
@@ -360,7 +363,11 @@ int b200_partition_rows(const int *ptr_host, int n_rows, int n_parts, int align,
  * chunk pointers, no permutation.  The caller orders steps with one small all-reduce of those
  * slots (which it needs anyway for the norm): no other launch is needed per step.
  * A warp stores its chunk's 32 rows as one contiguous 256-byte write per destination; dst[i] only
- * needs the natural 8-byte alignment of a double array (checked: B200_ERR_INVALID_VALUE). */
+ * needs the natural 8-byte alignment of a double array (checked: B200_ERR_INVALID_VALUE).
+ * Blocks of at least 4 chunks per resident warp run as a persistent grid whose warps keep the next
+ * chunk's loads in flight while the current one is gathered and stored (B200_BCAST_U = 1: one chunk
+ * per warp always; 2 | 3 | 4: the persistent kernel at that many blocks per SM); ||y||^2 then costs one
+ * atomic per resident block.  Same y bit for bit either way. */
 #define B200_SUMSQ_SLOTS 32
 int b200_spmv_sell_bcast_f64(b200_ctx *ctx, const double *data, const int *indices, const double *vect,
                              const int *row_indices, int chunk, int n_slices, int n_rows,
