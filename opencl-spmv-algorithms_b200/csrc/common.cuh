@@ -22,7 +22,7 @@ enum b200_opt {
     OPT_CSR_LANES, OPT_ELL_LANES, OPT_CSR_UNROLL, OPT_ELL_UNROLL, OPT_CSR_STREAM, OPT_SELL_WPC,
     OPT_SELL_UNROLL, OPT_SELL_TMA, OPT_SELL_TMA_BLOCKS, OPT_SELL_TMA_SUSPEND_NS, OPT_COO_U, OPT_CMRS_U,
     OPT_CMRS_WPS, OPT_CMRS_STREAM, OPT_ELLCM_Q, OPT_RING_FLUSH, OPT_RING_POLL, OPT_RING_SLEEP_NS,
-    OPT_BCAST_U, OPT_CSR_STREAM_G, OPT_SELL_PIPE, OPT_L2_PREFETCH, OPT_COUNT
+    OPT_BCAST_U, OPT_CSR_STREAM_G, OPT_SELL_PIPE, OPT_COUNT
 };
 constexpr int kOptUnset = INT_MIN;
 extern const char *const b200_opt_names[OPT_COUNT];
@@ -240,26 +240,6 @@ template <bool OVL, typename T>
 __device__ __forceinline__ T ld_xo(const T *x, int c)
 {
     return OVL ? __ldca(x + c) : __ldg(x + c);
-}
-
-// L2 prefetch of a whole matrix array through the bulk-copy engine (cp.async.bulk.prefetch.L2), for
-// launches of a few waves (cant: 35-70 MB per format, 8-17 us per kernel).  Such a kernel is a chain of
-// dependent round trips per block (pointers -> index/value loads -> gathers) times 2.6-3.3 waves of
-// blocks, and the DRAM pipe idles during two thirds of every block's life.  Thread 0 of the first
-// `issuers` blocks asks the L2 for the array in 16 KB slices (block b: slices b, b + issuers, ...: low
-// addresses first, which is the order the blocks need them) before anything else happens -- in an OVL
-// kernel even before griddepcontrol.wait, i.e. while the previous kernel drains.  The prefetch holds no
-// registers and no shared memory; the kernel's own 128-bit loads then hit L2 or merge with a fill in flight.
-__device__ __forceinline__ void l2_prefetch_slices(const void *base, long long bytes, int issuers)
-{
-    constexpr long long kSlice = 16384;
-    const char *p = static_cast<const char *>(base);
-    for (long long off = (long long)blockIdx.x * kSlice; off < bytes; off += (long long)issuers * kSlice) {
-        long long n = bytes - off;
-        if (n > kSlice) n = kSlice;
-        n &= ~15ll;  // whole 16-byte units (the array's last few bytes are fetched by the kernel's own loads)
-        if (n > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"((unsigned)n) : "memory");
-    }
 }
 
 // Load batching.  The kernels issue U groups of matrix loads, then the x gathers, then the FMAs.

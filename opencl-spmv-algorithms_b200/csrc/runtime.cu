@@ -12,7 +12,7 @@ const char *const b200_opt_names[OPT_COUNT] = {
     "B200_CSR_LANES", "B200_ELL_LANES", "B200_CSR_UNROLL", "B200_ELL_UNROLL", "B200_CSR_STREAM", "B200_SELL_WPC",
     "B200_SELL_UNROLL", "B200_SELL_TMA", "B200_SELL_TMA_BLOCKS", "B200_SELL_TMA_SUSPEND_NS", "B200_COO_U", "B200_CMRS_U",
     "B200_CMRS_WPS", "B200_CMRS_STREAM", "B200_ELLCM_Q", "B200_RING_FLUSH", "B200_RING_POLL", "B200_RING_SLEEP_NS",
-    "B200_BCAST_U", "B200_CSR_STREAM_G", "B200_SELL_PIPE", "B200_L2_PREFETCH",
+    "B200_BCAST_U", "B200_CSR_STREAM_G", "B200_SELL_PIPE",
 };
 
 static thread_local char g_last_error[512] = "";

@@ -90,14 +90,9 @@ __device__ __forceinline__ T row_dot_scalar(const int *__restrict__ col, const T
 template <typename T, int LPR, bool VEC, int U, bool OVL>
 __global__ void __launch_bounds__(kBlock)
 csr_vector_kernel(const int *__restrict__ ptr, const int *__restrict__ col, const T *__restrict__ data,
-                  const T *__restrict__ x, T *__restrict__ y, int n_rows, int long_threshold,
-                  long long pf_entries, int pf_issuers)
+                  const T *__restrict__ x, T *__restrict__ y, int n_rows, int long_threshold)
 {
     pdl_launch_dependents();
-    if (VEC && threadIdx.x == 0 && (int)blockIdx.x < pf_issuers) {  // small launches: see l2_prefetch_slices
-        l2_prefetch_slices(col, pf_entries * 4, pf_issuers);
-        l2_prefetch_slices(data, pf_entries * (long long)sizeof(T), pf_issuers);
-    }
     bool waited = false;
     const int lane = threadIdx.x & (LPR - 1);
     const long long row = ((long long)blockIdx.x * kBlock + threadIdx.x) / LPR;
@@ -315,13 +310,9 @@ __global__ void csr_stream_fixup_kernel(T *__restrict__ y, int n_tiles, const in
 template <typename T, int LPR, bool VEC, int U, bool OVL>
 __global__ void __launch_bounds__(kBlock)
 ell_rowmajor_kernel(const T *__restrict__ data, const int *__restrict__ col, const T *__restrict__ x,
-                    T *__restrict__ y, int n_rows, int row_size, int pf_issuers)
+                    T *__restrict__ y, int n_rows, int row_size)
 {
     pdl_launch_dependents();
-    if (VEC && threadIdx.x == 0 && (int)blockIdx.x < pf_issuers) {  // small launches: see l2_prefetch_slices
-        l2_prefetch_slices(col, (long long)n_rows * row_size * 4, pf_issuers);
-        l2_prefetch_slices(data, (long long)n_rows * row_size * (long long)sizeof(T), pf_issuers);
-    }
     bool waited = false;
     const int lane = threadIdx.x & (LPR - 1);
     const long long row = ((long long)blockIdx.x * kBlock + threadIdx.x) / LPR;
@@ -550,28 +541,23 @@ namespace {
 
 template <typename T, int LPR>
 int launch_csr_lpr(b200_ctx *ctx, const int *ptr, const int *col, const T *data, const T *x, T *y,
-                   int n_rows, int long_threshold, bool vec, long long nnz)
+                   int n_rows, int long_threshold, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
     const bool ovl = ovl_on(ctx, (long long)n_rows * LPR);
-    // L2 prefetch of the index / value arrays for launches of a few waves (B200_L2_PREFETCH = 0 | 1)
-    const bool small = (long long)n_rows * LPR <= 8ll * ctx->sm_count * 2048;
-    const long long pf_entries = nnz;
-    const int pf_issuers = (vec && nnz > 0 && opt_or(ctx, OPT_L2_PREFETCH, small ? 1 : 0) != 0)
-                               ? (int)min((long long)blocks, 2ll * ctx->sm_count) : 0;
     const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), false, OPT_CSR_UNROLL);
     if (!vec)
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers)
-                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else if (u == 4)
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers)
-                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else if (u == 2)
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers)
-                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     else
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers)
-                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold, pf_entries, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold)
+                               : b200_launch(ctx, ovl, csr_vector_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, ptr, col, data, x, y, n_rows, long_threshold));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
@@ -629,11 +615,11 @@ int spmv_csr_impl(b200_ctx *ctx, const int *ptr, const int *col, const T *data, 
         return rc;
     }
     switch (plan->info.lanes_per_row) {
-    case 2: rc = launch_csr_lpr<T, 2>(ctx, ptr, col, data, x, y, n_rows, thr, vec, plan->info.nnz); break;
-    case 4: rc = launch_csr_lpr<T, 4>(ctx, ptr, col, data, x, y, n_rows, thr, vec, plan->info.nnz); break;
-    case 8: rc = launch_csr_lpr<T, 8>(ctx, ptr, col, data, x, y, n_rows, thr, vec, plan->info.nnz); break;
-    case 16: rc = launch_csr_lpr<T, 16>(ctx, ptr, col, data, x, y, n_rows, thr, vec, plan->info.nnz); break;
-    default: rc = launch_csr_lpr<T, 32>(ctx, ptr, col, data, x, y, n_rows, thr, vec, plan->info.nnz); break;
+    case 2: rc = launch_csr_lpr<T, 2>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    case 4: rc = launch_csr_lpr<T, 4>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    case 8: rc = launch_csr_lpr<T, 8>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    case 16: rc = launch_csr_lpr<T, 16>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
+    default: rc = launch_csr_lpr<T, 32>(ctx, ptr, col, data, x, y, n_rows, thr, vec); break;
     }
     if (rc == B200_SUCCESS && plan->info.n_long_rows > 0) {
         dim3 grid(plan->info.n_long_rows, plan->n_split);
@@ -656,23 +642,20 @@ int launch_ell_lpr(b200_ctx *ctx, const T *data, const int *col, const T *x, T *
                    int row_size, bool vec)
 {
     unsigned blocks = ceil_div_u((long long)n_rows * LPR, kBlock);
-    const bool small_launch = (long long)n_rows * LPR <= 8ll * ctx->sm_count * 2048;
-    const int pf_issuers = (vec && row_size > 0 && opt_or(ctx, OPT_L2_PREFETCH, small_launch ? 1 : 0) != 0)
-                               ? (int)min((long long)blocks, 2ll * ctx->sm_count) : 0;
     const bool ovl = ovl_on(ctx, (long long)n_rows * LPR);
     const int u = pick_unroll(ctx, (long long)n_rows * LPR, (int)sizeof(T), true, OPT_ELL_UNROLL);
     if (!vec)
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers)
-                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, false, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, false, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else if (u == 4)
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers)
-                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 4, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 4, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else if (u == 2)
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers)
-                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 2, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 2, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     else
-        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers)
-                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size, pf_issuers));
+        B200_CUDA(ovl ? b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 1, true>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size)
+                               : b200_launch(ctx, ovl, ell_rowmajor_kernel<T, LPR, true, 1, false>, dim3(blocks), dim3(kBlock), 0, data, col, x, y, n_rows, row_size));
     B200_LAUNCH_CHECK();
     return B200_SUCCESS;
 }
