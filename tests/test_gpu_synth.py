@@ -90,17 +90,18 @@ def test_power_iteration_one_gpu_matches_cpu(ctx):
     tctx.close()
 
 
-def test_full_size_banded_properties(ctx):
-    """BASELINE configs[2] at full size (2 097 152 rows x 64 nnz/row, fp32): too big for the CPU
-    oracle in seconds, so check (a) all six kernels agree with each other, (b) linearity
-    A(ax + bz) = aAx + bAz, (c) 4096 sampled rows against the oracle on the host twin."""
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-12)])
+def test_full_size_banded_properties(ctx, dtype, tol):
+    """BASELINE configs[2] at full size (2 097 152 rows x 64 nnz/row; fp32 as benchmarked and fp64, the
+    reference's arithmetic): too big for the CPU oracle in seconds, so check (a) all six kernels agree with
+    each other, (b) linearity A(ax + bz) = aAx + bAz, (c) 8 x 1024 sampled rows -- first, last, around the
+    middle and around every eighth -- against the oracle on the host twin of the generator."""
     L = pkg.lib()
     n, npr, hb, seed = 2097152, 64, 2000, 42
     nnz = n * npr
     rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
     pkg.check(L.b200_gen_banded_coo(ctx.h, n, 0, n, npr, hb, seed, rows.ptr, cols.ptr, vals.ptr), "gen")
     coo = pkg.CooMatrix(ctx, n, n, rows, cols, vals)
-    dtype = np.float32
     m = pkg.build_all(coo, dtype)
     assert m["csr"].plan_info().lanes_per_row == 4 and m["ell"].row_size == 64
     assert m["sell"].total == nnz and m["sell"].n_slices == n // 32
@@ -114,7 +115,7 @@ def test_full_size_banded_properties(ctx):
         ys[name] = yd.download().astype(np.float64)
     scale = np.abs(ys["csr"]).max()
     for name in ys:
-        assert np.max(np.abs(ys[name] - ys["csr"])) / scale <= 1e-5, name
+        assert np.max(np.abs(ys[name] - ys["csr"])) / scale <= tol, name
     # linearity on the SELL kernel
     a, b = 0.75, -1.5
     w = ctx.array((a * xh + b * zh).astype(dtype))
@@ -122,16 +123,16 @@ def test_full_size_banded_properties(ctx):
     m["sell"].spmv(z, yz)
     m["sell"].spmv(w, yw)
     lin = a * ys["sell"] + b * yz.download().astype(np.float64)
-    assert np.max(np.abs(yw.download() - lin)) / max(np.abs(lin).max(), 1e-30) <= 1e-5
+    assert np.max(np.abs(yw.download() - lin)) / max(np.abs(lin).max(), 1e-30) <= tol
     # sampled row blocks against the oracle (host twin of the generator)
-    for r0 in (0, 1048576 - 512, n - 1024):
+    for r0 in (0, 262144 - 100, 524288 + 7, 786432, 1048576 - 512, 1310720 + 33, 1835008 - 1000, n - 1024):
         cnt = 1024
         rh, ch, vh = np.empty(cnt * npr, np.int32), np.empty(cnt * npr, np.int32), np.empty(cnt * npr)
         pkg.check(L.b200_gen_banded_coo_host(n, r0, cnt, npr, hb, seed, rh.ctypes.data, ch.ctypes.data,
                                              vh.ctypes.data), "gen host")
         y_ref = O.yref(cnt, rh - r0, ch, vh, xh.astype(np.float64))
         for name in ys:
-            assert O.rel_maxnorm(ys[name][r0:r0 + cnt], y_ref) <= 1e-5, (name, r0)
+            assert O.rel_maxnorm(ys[name][r0:r0 + cnt], y_ref) <= tol, (name, r0)
 
 
 def gen_rmat(ctx, scale, ef, r0, cnt, seed=3, abc=(0.57, 0.19, 0.19)):
@@ -444,3 +445,49 @@ def test_fused_kernel_variants_on_mixed_chunk_widths(ctx, bcast_u):
     assert np.all(got[:32] == -7.0) and np.all(got[32 + n:] == -7.0)       # offset respected, nothing past the end
     assert np.max(np.abs(got[32:32 + n] - y_ref)) <= 1e-12 * np.abs(y_ref).max()
     assert abs(acc.download().sum() - np.dot(y_ref, y_ref)) <= 1e-12 * np.dot(y_ref, y_ref)
+
+
+def test_full_size_laplacian_all_rows(ctx):
+    """BASELINE configs[4], one rank's block at full size (400 x 400 x 50 = 8 M rows, fp64): the device
+    generator, the SELL build and the kernels the iterated mode runs at this size -- the persistent
+    pipelined kernel behind the plain SELL SpMV and behind the fused SpMV + exchange call (1/||x|| scaling,
+    ||y||^2, offset destination), and the CSR nnz-split kernel -- against the stencil applied with numpy
+    slices to EVERY row."""
+    import ctypes as C
+    L = pkg.lib()
+    nx = ny = 400
+    nz = 50
+    n = nx * ny * nz
+    nnz = L.b200_gen_laplace7_nnz(nx, ny, nz, 0, n)
+    assert nnz == 7 * n - 2 * (nx * ny + ny * nz + nx * nz)
+    rows, cols, vals = ctx.empty(nnz, np.int32), ctx.empty(nnz, np.int32), ctx.empty(nnz, np.float64)
+    pkg.check(L.b200_gen_laplace7_coo(ctx.h, nx, ny, nz, 0, n, rows.ptr, cols.ptr, vals.ptr), "gen")
+    csr = pkg.CsrMatrix(pkg.CooMatrix(ctx, n, n, rows, cols, vals))
+    sell = pkg.SellMatrix(csr, np.float64)
+    assert sell.n_slices == n // 32 and sell.total <= 7 * n
+    xh = np.random.default_rng(4).uniform(-1, 1, n)
+    g = xh.reshape(nz, ny, nx)
+    ref = 6.0 * g
+    ref[1:, :, :] -= g[:-1, :, :]
+    ref[:-1, :, :] -= g[1:, :, :]
+    ref[:, 1:, :] -= g[:, :-1, :]
+    ref[:, :-1, :] -= g[:, 1:, :]
+    ref[:, :, 1:] -= g[:, :, :-1]
+    ref[:, :, :-1] -= g[:, :, 1:]
+    ref = ref.reshape(n)
+    xd = ctx.array(xh)
+    for name, mat in (("sell (pipelined)", sell), ("csr (nnz-split)", csr)):
+        yd = ctx.array(np.full(n, np.nan))
+        mat.spmv(xd, yd)
+        assert O.rel_maxnorm(yd.download(), ref) <= 1e-12, name
+    prev = np.random.default_rng(5).uniform(0, 2, 32)           # partial sums of ||x||^2 the kernel scales by
+    scale, acc = ctx.array(prev), ctx.zeros(32, np.float64)
+    out = ctx.array(np.full(n + 96, -7.0))
+    dst = (C.c_void_p * 1)(out.ptr)
+    pkg.check(L.b200_spmv_sell_halo_f64(ctx.h, sell.data.ptr, sell.cols.ptr, xd.ptr, sell.row_indices.ptr, 32,
+                                        sell.n_slices, n, scale.ptr, acc.ptr, dst, 1, 64, None, None), "fused kernel")
+    got = out.download()
+    y_scaled = ref / np.sqrt(prev.sum())
+    assert np.all(got[:64] == -7.0) and np.all(got[64 + n:] == -7.0)
+    assert O.rel_maxnorm(got[64:64 + n], y_scaled) <= 1e-12
+    assert abs(acc.download().sum() - np.dot(y_scaled, y_scaled)) <= 1e-12 * np.dot(y_scaled, y_scaled)
