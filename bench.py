@@ -467,7 +467,9 @@ def measure_e2e(pkg, ctx, D, local_rank, mats, y, x, n_rows, n_cols, segments, d
                     "once before the timed region, as the reference driver does (csr.c:183-193). The five calls of a step "
                     "go to 1, 2 or 5 in-order queues (contexts) of the device, every call with its own x upload and y "
                     "download; value = the best of the three (one queue: CUDA events; several: wall clock, all queues "
-                    "drained); max over ranks"}
+                    "drained); max over ranks.  With one queue per format the kernels of different formats also overlap "
+                    "each other's ramp and drain, so this number can come within a few percent of -- or just above -- the "
+                    "device-resident `value`, whose five launches run strictly one after the other on one queue"}
 
 
 def time_formats(ctx, D, mats, x, y, steps, warmup, local_rank=None):
@@ -1295,6 +1297,9 @@ def rmat_arm(pkg, args, rank, world, local_rank):
         e2e = measure_e2e(pkg, ctx, D, local_rank, mats3, y3, x, n_rows, n, column_segments(pkg, ctx, coo.cols, n), dtype,
                           max(3, min(args.steps, 10)), 2.0 * tot * len(mats3))
         e2e["formats"] = list(mats3)
+        if world > 1:
+            e2e["x_sharded_upload_nvlink_allgather"] = rmat_e2e_sharded(pkg, ctx, D, local_rank, rank, world, mats3, y, x, n_rows, n,
+                                                                        dtype, max(3, min(args.steps, 10)), 2.0 * tot * len(mats3))
 
     # CPU baseline (rank 0, N = 1): the oracle port's CSR / COO / CMRS on the first rows of the same matrix
     cpu = None
@@ -1357,6 +1362,58 @@ def rmat_arm(pkg, args, rank, world, local_rank):
     D.close()
     ctx.close()
     return 0
+
+
+def rmat_e2e_sharded(pkg, ctx, D, local_rank, rank, world, mats, y, x, n_rows, n_cols, dtype, steps, flops_step):
+    """e2e of the row-partitioned single-shot SpMV with a REPLICATED x that comes from the host: every rank
+    uploads only its 1/N slice of x, the ranks all-gather it over NVLink (b200_comm_allgather_bytes: NCCL called
+    from the library), then SpMV, then this rank's rows of y back to pinned host memory.  Host-link bytes per call
+    and rank: (n_cols / N + n_rows) * V instead of (n_cols + n_rows) * V."""
+    import ctypes as C
+    L = pkg.lib()
+    V = np.dtype(dtype).itemsize
+    per = (n_cols + world - 1) // world
+    per = (per * V + 15) // 16 * 16 // V                      # 16-byte slices
+    padded = per * world
+    x_host = x.download()
+    hx, hy = C.c_void_p(), C.c_void_p()
+    pkg.check(L.b200_host_alloc_pinned(per * V, C.byref(hx)), "pinned x slice")
+    pkg.check(L.b200_host_alloc_pinned(n_rows * V, C.byref(hy)), "pinned y")
+    mine = np.zeros(per, dtype)
+    lo = rank * per
+    mine[:max(0, min(per, n_cols - lo))] = x_host[lo:lo + per]
+    np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_byte)), shape=(per * V,)).view(dtype)[:] = mine
+    xin = ctx.zeros(padded, dtype)
+    comm = pkg.Comm(pkg, ctx, rank, world)
+
+    def step():
+        for m in mats.values():
+            pkg.check(L.b200_memcpy_h2d_async(ctx.h, xin.ptr + lo * V, hx, per * V), "h2d x slice")
+            comm.allgather_bytes(xin.ptr, per * V)
+            m.spmv(xin, y)
+            pkg.check(L.b200_memcpy_d2h_async(ctx.h, hy, y.ptr, n_rows * V), "d2h y")
+    for _ in range(2):
+        step()
+    ctx.sync()
+    ok = bool(np.array_equal(xin.download()[:n_cols], x_host))        # the gathered x is the host's x
+    D.barrier(ctx)
+    a, b = ctx.event(), ctx.event()
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    D.barrier(ctx)
+    (ms,) = D.reduce([a.elapsed_ms_until(b) / steps], "max")
+    (ok_all,) = D.reduce([0.0 if ok else 1.0], "max")
+    h2d, d2h = D.reduce([len(mats) * per * V, len(mats) * n_rows * V], "sum")
+    comm.close()
+    L.b200_host_free_pinned(hx)
+    L.b200_host_free_pinned(hy)
+    return {"value": round(flops_step / (ms * 1e-3) * 1e-9, 2), "unit": "GFLOP/s", "ms_per_step": round(ms, 4), "steps": steps,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "gathered_x_equals_host_x": ok_all == 0.0,
+            "what": "per format: this rank's 1/N slice of x from pinned host memory -> device, all-gather of x over NVLink "
+                    "(b200_comm_allgather_bytes), SpMV through the C ABI, y -> pinned host; one in-order queue, CUDA events, "
+                    "max over ranks"}
 
 
 def laplace_iter_arm(pkg, args, rank, world, local_rank):

@@ -501,6 +501,11 @@ int b200_comm_check(b200_comm *comm);
 int b200_comm_allreduce_sum_f64(b200_comm *comm, double *buf_device, long long count); /* in place */
 /* in place: rank r's segment is full[r*count_per_rank .. (r+1)*count_per_rank) */
 int b200_comm_allgather_f64(b200_comm *comm, double *full_device, long long count_per_rank);
+/* the same for any element type: rank r's segment is the bytes [r*bytes_per_rank, (r+1)*bytes_per_rank) of
+ * `full_device`.  What it is for: a replicated x that arrives from the HOST (single-shot SpMV over a
+ * row-partitioned matrix) crosses the host link once -- every rank uploads 1/N of it -- and reaches the other
+ * ranks over NVLink, instead of every rank uploading all of it. */
+int b200_comm_allgather_bytes(b200_comm *comm, void *full_device, long long bytes_per_rank);
 /* threads-of-one-process ranks: let this context's device store into `peer_device`'s allocations */
 int b200_ctx_enable_peer_access(b200_ctx *ctx, int peer_device);
 

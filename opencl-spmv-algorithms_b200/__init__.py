@@ -179,6 +179,7 @@ SIGNATURES = {
     "b200_comm_check": (_i, [_vp]),
     "b200_comm_allreduce_sum_f64": (_i, [_vp, _vp, _ll]),
     "b200_comm_allgather_f64": (_i, [_vp, _vp, _ll]),
+    "b200_comm_allgather_bytes": (_i, [_vp, _vp, _ll]),
     "b200_ctx_enable_peer_access": (_i, [_vp, _i]),
     "b200_halo_rows": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _vp]),
     "b200_mcast_supported": (_i, [_vp, C.POINTER(_i)]),

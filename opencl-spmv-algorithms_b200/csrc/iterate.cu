@@ -275,6 +275,17 @@ int b200_comm_allgather_f64(b200_comm *comm, double *full, long long count_per_r
     return B200_SUCCESS;
 }
 
+int b200_comm_allgather_bytes(b200_comm *comm, void *full, long long bytes_per_rank)
+{
+    B200_TRACE("b200 allgather");
+    B200_REQUIRE(comm && full && bytes_per_rank >= 0, "bad argument");
+    B200_ENTER(comm->ctx);
+    if (bytes_per_rank == 0) return B200_SUCCESS;
+    B200_NCCL(g_nccl.AllGather(static_cast<char *>(full) + (long long)comm->rank * bytes_per_rank, full, (size_t)bytes_per_rank,
+                               ncclChar, comm->comm, comm->ctx->stream));
+    return B200_SUCCESS;
+}
+
 int b200_ctx_enable_peer_access(b200_ctx *ctx, int peer_device)
 {
     B200_ENTER(ctx);

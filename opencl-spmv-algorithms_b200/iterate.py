@@ -162,6 +162,9 @@ class Comm:
     def allgather(self, full_ptr: int, count_per_rank: int) -> None:
         self.pkg.check(self.pkg.lib().b200_comm_allgather_f64(self.h, full_ptr, count_per_rank), "b200_comm_allgather_f64")
 
+    def allgather_bytes(self, full_ptr: int, bytes_per_rank: int) -> None:
+        self.pkg.check(self.pkg.lib().b200_comm_allgather_bytes(self.h, full_ptr, bytes_per_rank), "b200_comm_allgather_bytes")
+
     def close(self) -> None:
         if self.h:
             self.pkg.lib().b200_comm_destroy(self.h)

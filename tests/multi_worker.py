@@ -168,6 +168,10 @@ def main():
     g = ctx.array(np.where(np.arange(4 * world) // 4 == rank, rank + 1.0, 0.0))
     comm.allgather(g.ptr, 4)
     check("allgather", np.array_equal(g.download(), np.repeat(np.arange(world) + 1.0, 4)))
+    # ... and for any element type: 12 float32 per rank (48 bytes), the sharded upload of a replicated x
+    gb = ctx.array(np.where(np.arange(12 * world) // 12 == rank, rank + 0.5, -1.0).astype(np.float32))
+    comm.allgather_bytes(gb.ptr, 48)
+    check("allgather_bytes", np.array_equal(gb.download(), np.repeat(np.arange(world) + 0.5, 12).astype(np.float32)))
     comm.check()
 
     # single-shot, row-sharded: every format's y block equals the oracle's rows
