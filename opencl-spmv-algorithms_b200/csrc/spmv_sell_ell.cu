@@ -8,10 +8,13 @@
 // quarter of the columns; two __shfl_xor_sync steps (8, 16) fold the quarters and lanes 0-7
 // store the 32 results as 128-bit writes (or scatter through the sigma permutation).
 //
-// Variants in this file: 1-8 warps per chunk for matrices with few chunks (WPC), an opt-in kernel
-// that stages the chunks through shared memory with the TMA engine (sell32_tma_kernel), and the
-// fused SpMV + exchange kernel of the multi-GPU power iteration (sell32_bcast_kernel: halo-limited
-// peer stores; ring_sync_kernel: collective-free hand-over of the norm).
+// Variants in this file: 1-8 warps per chunk for matrices with few chunks (WPC), a lane = row path for
+// stencil-width chunks, an opt-in kernel that stages the chunks through shared memory with the TMA
+// engine (sell32_tma_kernel), the fused SpMV + exchange kernels of the multi-GPU power iteration
+// (sell32_bcast_kernel: halo-limited peer stores; ring_sync_kernel: collective-free hand-over of the
+// norm), and sell32_pipe_kernel: the persistent, software-pipelined kernel that serves large stencil
+// matrices both in the fused step and in the plain SpMV (next chunk's loads in flight while the current
+// one is gathered; profiles/r2_pipelined_kernels.md).
 //
 // Column-major ELL is the same idea with one "chunk" spanning the whole matrix: thread t owns rows
 // 4t..4t+3 and walks the K columns (optionally split over KS thread-slices when the matrix has
