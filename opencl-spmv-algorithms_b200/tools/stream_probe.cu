@@ -72,8 +72,105 @@ __global__ void __launch_bounds__(256) read_persist(const int4 *__restrict__ a, 
     if ((threadIdx.x & 31) == 0 && s == 0x5a5a5a5a) out[blockIdx.x] = s;
 }
 
+// ---- the same stream with the gather of an SpMV (--gather): what the x gather costs by itself -------------
+// idx[j] = a column within +-half_band of row j / npr (the banded bench matrix in spirit), val[j] = 1.  A thread
+// loads U groups of four (index, value) pairs with 128-bit loads, gathers x through the read-only path (or not:
+// GATHER = false multiplies by a constant instead), and adds everything up; one 4-byte store per warp.
+__global__ void fill_banded(int *idx, float *val, long long n, int npr, int half_band, int n_cols)
+{
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const long long row = j / npr;
+        unsigned h = (unsigned)(j * 2654435761u) ^ (unsigned)(j >> 17);
+        h ^= h >> 13;
+        h *= 0x5bd1e995u;
+        h ^= h >> 15;
+        long long c = row - half_band + (long long)(h % (2u * half_band + 1u));
+        c = c < 0 ? c + n_cols : (c >= n_cols ? c - n_cols : c);
+        idx[j] = (int)c;
+        val[j] = 1.0f;
+    }
+}
+
+template <int U, bool GATHER>
+__global__ void __launch_bounds__(256) spmv_like(const int4 *__restrict__ idx, const float4 *__restrict__ val,
+                                                 const float *__restrict__ x, long long n4, float *__restrict__ out)
+{
+    const long long base = (long long)blockIdx.x * 256 * U + threadIdx.x;
+    int4 c[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long i = base + (long long)u * 256;
+        c[u] = i < n4 ? __ldcs(idx + i) : make_int4(0, 0, 0, 0);
+        v[u] = i < n4 ? __ldcs(val + i) : make_float4(0, 0, 0, 0);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (GATHER)
+            acc += v[u].x * __ldg(x + c[u].x) + v[u].y * __ldg(x + c[u].y) + v[u].z * __ldg(x + c[u].z) + v[u].w * __ldg(x + c[u].w);
+        else
+            acc += v[u].x * (float)c[u].x + v[u].y * (float)c[u].y + v[u].z * (float)c[u].z + v[u].w * (float)c[u].w;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) out[((long long)blockIdx.x * 256 + threadIdx.x) >> 5] = acc;
+}
+
+static int gather_probe()
+{
+    const long long rows = 2097152, npr = 64, n = rows * npr, n4 = n / 4;
+    int *idx = nullptr;
+    float *val = nullptr, *x = nullptr, *out = nullptr;
+    CK(cudaMalloc(&idx, n * 4));
+    CK(cudaMalloc(&val, n * 4));
+    CK(cudaMalloc(&x, rows * 4));
+    CK(cudaMalloc(&out, (n4 / 32 + 1024) * 4));
+    CK(cudaMemset(x, 0, rows * 4));
+    fill_banded<<<2368, 256>>>(idx, val, n, (int)npr, 2000, (int)rows);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    printf("{\"gather_probe\": {\"entries\": %lld, \"bytes_streamed\": %lld, \"variants\": {", n, n * 8);
+    bool first = true;
+    for (int variant = 0; variant < 6; ++variant) {
+        const int u = variant % 3 == 0 ? 1 : (variant % 3 == 1 ? 2 : 4);
+        const bool gather = variant >= 3;
+        const unsigned grid = (unsigned)((n4 + 256ll * u - 1) / (256ll * u));
+        auto launch = [&]() {
+            const int4 *ci = reinterpret_cast<const int4 *>(idx);
+            const float4 *cv = reinterpret_cast<const float4 *>(val);
+            if (gather) {
+                if (u == 1) spmv_like<1, true><<<grid, 256>>>(ci, cv, x, n4, out);
+                else if (u == 2) spmv_like<2, true><<<grid, 256>>>(ci, cv, x, n4, out);
+                else spmv_like<4, true><<<grid, 256>>>(ci, cv, x, n4, out);
+            } else {
+                if (u == 1) spmv_like<1, false><<<grid, 256>>>(ci, cv, x, n4, out);
+                else if (u == 2) spmv_like<2, false><<<grid, 256>>>(ci, cv, x, n4, out);
+                else spmv_like<4, false><<<grid, 256>>>(ci, cv, x, n4, out);
+            }
+        };
+        for (int i = 0; i < 3; ++i) launch();
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < 20; ++i) launch();
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double us = ms * 1e3 / 20;
+        printf("%s\"%s_u%d\": {\"us\": %.2f, \"gbs\": %.0f}", first ? "" : ", ", gather ? "gather" : "no_gather", u, us,
+               (n * 8.0 + rows * 4.0 + n / 32.0) / us * 1e-3);
+        first = false;
+    }
+    printf("}}}\n");
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    for (int i = 1; i < argc; ++i)
+        if (!strcmp(argv[i], "--gather")) return gather_probe();
     std::vector<double> mbs = {35.4, 53.2, 70.2, 280, 1090};
     int copies = 7, reps = 28;
     for (int i = 1; i < argc; ++i) {
