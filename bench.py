@@ -16,7 +16,13 @@ larger than the 126 MB L2, so no flush is needed between iterations.
 Prints ONE JSON line.  metric = aggregate SpMV GFLOP/s (2*nnz flops per SpMV, the reference's own
 FLOP model, inc/helper_functions.h:171-172) over the five formats; `formats` carries the per-format
 GFLOP/s, algorithmic GB/s and fraction of the measured HBM peak; `roofline` describes the dominant
-(slowest) kernel; `cpu_baseline` is the oracle port on the host cores on a bounded sample.
+(slowest) kernel; `cpu_baseline` is the oracle port on the host cores on a bounded sample; `e2e` is the
+same step through the C ABI with x coming from and y going back to pinned host memory on every call
+(the five calls of a step on 1, 2 or 5 in-order queues; the best is `value`).  The default line also
+carries `f64` (the same matrix in the reference's arithmetic), `strong` (the fixed matrix cut into N
+row blocks) and `iterated` (BASELINE configs[4]: power iteration on the row-partitioned Laplacian, the
+fused SpMV + halo-exchange kernel with NCCL's all-reduce or the NVSwitch multicast hand-over, checked
+against the SpMV + ncclAllGather formulation in the same run).
 
 --impl reference times the reference's own CPU code (oracle/_ref, compute_using_cpu built -O3 from
 the unmodified sources; fp64 because the reference has no fp32) on the box's host cores.
