@@ -114,6 +114,7 @@ struct b200_iterator {
     unsigned long long step;  // steps issued so far
     double *acc;              // device: FUSED 2 x B200_SUMSQ_SLOTS partial sums, ALLGATHER 2 x 1
     b200_graph *graph[2];     // d.graph_steps steps recorded from a step of parity p (NULL: not yet)
+    b200_sell_plan *sell_plan;  // ALLGATHER on a SELL block: tells the SpMV whether the block is a stencil (pipelined kernel)
     unsigned long long launches;  // kernels + collectives issued (bench.py's gpu_launches)
 };
 
@@ -167,7 +168,7 @@ int issue_step(b200_iterator *it, unsigned long long k)
     if (a.format == B200_FORMAT_CSR)
         rc = b200_spmv_csr_f64(ctx, a.ptr, a.indices, a.data, x_cur, seg, a.n_rows, a.csr_plan);
     else
-        rc = b200_spmv_sell_f64(ctx, a.data, a.indices, x_cur, seg, a.ptr, 32, a.n_slices, a.n_rows, nullptr, nullptr);
+        rc = b200_spmv_sell_f64(ctx, a.data, a.indices, x_cur, seg, a.ptr, 32, a.n_slices, a.n_rows, nullptr, it->sell_plan);
     if (rc) return rc;
     rc = b200_memset_async(ctx, sum, 0, sizeof(double));
     if (rc) return rc;
@@ -362,6 +363,7 @@ int b200_iterator_create(b200_ctx *ctx, b200_comm *comm, const b200_block_f64 *b
     it->step = 0;
     it->acc = nullptr;
     it->graph[0] = it->graph[1] = nullptr;
+    it->sell_plan = nullptr;
     it->launches = 0;
     for (int b = 0; b < 2; ++b) {
         it->xs[b].resize(d.world, nullptr);
@@ -388,6 +390,14 @@ int b200_iterator_create(b200_ctx *ctx, b200_comm *comm, const b200_block_f64 *b
         if (it->acc) cudaFree(it->acc);
         delete it;
         return b200_cuda_fail(e, "iterator scratch", __FILE__, __LINE__);
+    }
+    if (d.mode == B200_ITER_ALLGATHER && block->format == B200_FORMAT_SELL && block->n_slices > 0) {
+        const int rc = b200_sell_plan_create(ctx, block->ptr, block->n_slices, &it->sell_plan);
+        if (rc != B200_SUCCESS) {
+            cudaFree(it->acc);
+            delete it;
+            return rc;
+        }
     }
     *iterator = it;
     return B200_SUCCESS;
@@ -486,6 +496,7 @@ int b200_iterator_destroy(b200_iterator *it)
     for (int p = 0; p < 2; ++p)
         if (it->graph[p]) b200_graph_destroy(it->graph[p]);
     if (it->acc) cudaFree(it->acc);
+    if (it->sell_plan) b200_sell_plan_destroy(it->sell_plan);
     delete it;
     return B200_SUCCESS;
 }
