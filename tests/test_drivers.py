@@ -95,6 +95,64 @@ def test_fast_parallel_parse_equals_fscanf_parse(cant_dir, tmp_path):
         assert a.tobytes() == b.tobytes()
 
 
+def test_number_scanners_equal_fscanf_on_awkward_spellings(tmp_path):
+    """The drivers' own integer / double scanners (fast_int, fast_double: Clinger's fast path, strtod for the
+    rest) against the reference-style fscanf("%d %d %lg") on every spelling %lg accepts: 1..25 significant
+    digits, decimal exponents inside and outside [-22, 22], leading zeros, bare '.5' / '5.', signs, signed
+    zero, overflow to inf, underflow to zero and to denormals, inf / nan, hex floats; row / column numbers with
+    a '+' or leading zeros.  Bit-identical triples, serial and parallel parse, mapped and copied file."""
+    import numpy as np
+    bins = build_drivers()
+    rng = np.random.default_rng(12)
+    special = ["0", "-0", "0.0", "-0.0e7", ".5", "5.", "+7", "-.25e1", "1e5", "1E-5", "1.5e+300", "4.9e-324", "2.2250738585072014e-308",
+               "1e-400", "-1e400", "inf", "-inf", "nan", "0x1.8p3", "-0X10", "123456789012345678901234", "0.000000000000000000000123",
+               "9007199254740993", "9007199254740992e1", "1e22", "1e23", "9007199254740991e22", "8.5e-22", "8.5e-23",
+               "179769313486231570814527423731704356798070567525844996598917476803157260780028538760589558632766878171540458953"
+               "514382464234321326889464182768467546703537516986049910576551282076245490090389328944075868508455133942304583236"
+               "90322294816580855933212334827479782620414472316873817718091929988125040402618412485836800000000000000000000000"]
+    vals = list(special)
+    while len(vals) < 20000:
+        digits = int(rng.integers(1, 26))
+        mant = "".join(str(d) for d in rng.integers(0, 10, digits))
+        cut = int(rng.integers(0, digits + 1))
+        text = (mant[:cut] or ("" if rng.random() < 0.3 else "0")) + "." + mant[cut:] if rng.random() < 0.8 else mant
+        if text == ".":
+            text = "0."
+        if rng.random() < 0.5:
+            text += ("e", "E")[int(rng.integers(0, 2))] + ("", "+", "-")[int(rng.integers(0, 3))] + str(int(rng.integers(0, 40)))
+        vals.append(("-", "+", "")[int(rng.integers(0, 3))] + text)
+    n = len(vals)
+    r, c = rng.integers(1, 900, n), rng.integers(1, 900, n)
+
+    def write(path, pad_to_page):
+        body = "%%MatrixMarket matrix coordinate real general\n" + f"900 900 {n}\n"
+        for i in range(n):
+            rr = f"+{r[i]}" if i % 7 == 0 else (f"00{r[i]}" if i % 11 == 0 else str(r[i]))
+            body += f"{rr} {c[i]} {vals[i]}\n"
+        if pad_to_page:
+            body += " " * ((-len(body) - 1) % 4096) + "\n"
+            assert len(body) % 4096 == 0
+        else:
+            assert len(body) % 4096 != 0
+        path.write_text(body)
+
+    for pad in (False, True):
+        path = tmp_path / f"awkward{int(pad)}.mtx"
+        write(path, pad)
+        ref = O.read_mtx(path)
+        assert np.isnan(ref[4]).sum() >= 1 and np.isinf(ref[4]).sum() >= 3      # the reference-style reader took them all
+        for threads in (1, 8):
+            out = tmp_path / "p.bin"
+            p = subprocess.run([str(bins / "mtx_parse"), str(path), str(out)], capture_output=True, text=True,
+                               env=dict(os.environ, OMP_NUM_THREADS=str(threads), B200_PARSE_TIMING="1"))
+            assert p.returncode == 0, p.stderr
+            assert ("mapped" if not pad else "read") in p.stderr, p.stderr
+            raw = out.read_bytes()
+            got = (np.frombuffer(raw, np.int32, n, 0), np.frombuffer(raw, np.int32, n, 4 * n), np.frombuffer(raw, np.float64, n, 8 * n))
+            for a, b in zip(got, ref[2:]):
+                assert a.tobytes() == b.tobytes(), (pad, threads)
+
+
 def test_expand_symmetric_equals_the_full_matrix(tmp_path):
     """--expand-symmetric (new, optional): the lower triangle of a file whose banner says `symmetric`,
     mirrored and sorted by (row, column), must equal the row-sorted FULL matrix bit for bit (the
