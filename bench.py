@@ -1378,9 +1378,7 @@ def rmat_e2e_sharded(pkg, ctx, D, local_rank, rank, world, mats, y, x, n_rows, n
     import ctypes as C
     L = pkg.lib()
     V = np.dtype(dtype).itemsize
-    per = (n_cols + world - 1) // world
-    per = (per * V + 15) // 16 * 16 // V                      # 16-byte slices
-    padded = per * world
+    per, padded = pkg.x_upload_slices(n_cols, world, V)      # 16-byte slices
     x_host = x.download()
     hx, hy = C.c_void_p(), C.c_void_p()
     pkg.check(L.b200_host_alloc_pinned(per * V, C.byref(hx)), "pinned x slice")

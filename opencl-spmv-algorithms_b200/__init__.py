@@ -424,4 +424,4 @@ class Event:
 from .formats import (CooMatrix, CsrMatrix, EllMatrix, EllCmMatrix, SellMatrix, Sell16Matrix, CmrsMatrix,  # noqa: E402,F401
                       CmrsPackedMatrix, algorithmic_bytes, build_all, partition_rows)
 from .iterate import (Comm, Iterator, McastBlock, PeerBuffers, RowBlocks, equal_row_blocks, exchange_col_ranges,  # noqa: E402,F401
-                      gpu_callables, halo_rows, power_iteration, power_iteration_ring, power_iteration_fused)
+                      gpu_callables, halo_rows, power_iteration, power_iteration_ring, power_iteration_fused, x_upload_slices)

@@ -46,6 +46,17 @@ def equal_row_blocks(n_rows: int, world: int, align: int = 32) -> RowBlocks:
     return RowBlocks(n_rows, world, count)
 
 
+def x_upload_slices(n_cols: int, world: int, itemsize: int) -> tuple[int, int]:
+    """(entries per rank, padded length) for the sharded upload of a replicated x: rank r uploads entries
+    [r*per, (r+1)*per) from the host and the ranks all-gather the slices over NVLink
+    (b200_comm_allgather_bytes).  `per` = ceil(n_cols / world) rounded up so that a slice is a whole number
+    of 16-byte units (every rank's segment of the gathered buffer stays 16-byte aligned); entries of the
+    last slices beyond n_cols are padding."""
+    per = -(-n_cols // world)
+    per = -(-per * itemsize // 16) * 16 // itemsize
+    return per, per * world
+
+
 @dataclass
 class IterationResult:
     steps: int

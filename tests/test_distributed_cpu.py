@@ -284,3 +284,56 @@ def test_c_abi_halo_rows_equals_the_python_mirror():
                 assert L.b200_halo_rows(cmin, cmax, world, rank, blocks.count, n, lo, hi) == 0
                 want = pkg.halo_rows(ranges, blocks, rank)
                 assert (list(lo), list(hi)) == (list(want[0]), list(want[1])), (world, n, rank, ranges)
+
+
+def _sharded_x_worker(rank, world, port, out_dir):
+    """The sharded upload of a replicated x (bench.py --workload rmat at N > 1, b200_comm_allgather_bytes on the
+    GPU): every rank holds only ITS slice of the host's x, the slices are all-gathered into a padded buffer,
+    and the row-sharded SpMV with the gathered x must equal the oracle's rows."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from __graft_entry__ import load_package
+        from oracle import binding as O
+        pkg = load_package()
+        O.lib().orc_set_threads(1)
+        rng = np.random.default_rng(21)
+        n_rows, n_cols = 1111, 1237                                # neither divisible by the world size nor by 4
+        lens = rng.integers(1, 9, n_rows)                           # no empty rows: the reference's CSR build (oracle) needs none
+        rows = np.repeat(np.arange(n_rows, dtype=np.int32), lens)
+        cols = rng.integers(0, n_cols, rows.size).astype(np.int32)
+        vals = rng.uniform(-1, 1, rows.size)
+        x_host = rng.uniform(0, 1, n_cols).astype(np.float32)      # fp32: 4 entries per 16-byte unit
+        per, padded = pkg.x_upload_slices(n_cols, world, 4)
+        lo = rank * per
+        mine = np.zeros(per, np.float32)
+        mine[:max(0, min(per, n_cols - lo))] = x_host[lo:lo + per]                  # what this rank "uploads"
+        outs = [torch.empty(per, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(outs, torch.from_numpy(mine))
+        x = torch.cat(outs).numpy()
+        assert x.size == padded and np.array_equal(x[:n_cols], x_host) and not x[n_cols:].any()
+        ptr_host = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+        cuts = pkg.partition_rows(ptr_host, world, 32)
+        r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+        sel = slice(ptr_host[r0], ptr_host[r1])
+        lptr, _ = O.build_csr(r1 - r0, rows[sel] - r0)
+        y = O.spmv_csr(r1 - r0, lptr, cols[sel], vals[sel], x[:n_cols].astype(np.float64))
+        y_ref = O.yref(n_rows, rows, cols, vals, x_host.astype(np.float64))
+        np.save(Path(out_dir) / f"sharded_x_{rank}.npy", np.array([O.rel_maxnorm(y, y_ref[r0:r1]) if r1 > r0 else 0.0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_x_upload_world2(tmp_path):
+    import importlib
+    pkg = importlib.import_module("__graft_entry__").load_package()
+    for n, world, itemsize in ((1237, 2, 4), (1 << 24, 8, 4), (1001, 3, 8), (16, 8, 8), (5, 4, 4)):
+        per, padded = pkg.x_upload_slices(n, world, itemsize)
+        assert padded == per * world >= n and (per * itemsize) % 16 == 0
+        assert (per - 16 // itemsize) * world < n or per * itemsize == 16           # no more padding than one unit per rank
+    assert pkg.x_upload_slices(1 << 24, 8, 4) == (1 << 21, 1 << 24)
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_sharded_x_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert float(np.load(tmp_path / f"sharded_x_{r}.npy")[0]) <= 1e-12
